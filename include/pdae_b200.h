@@ -1,0 +1,134 @@
+/* pdae_b200 -- C-ABI of the B200-native PDAE hot path (libpdae_b200.so).
+ *
+ * The reference (ckczzj/PDAE) has no FFI: its hot path is PyTorch ATen dispatches issued from
+ * model/module.py, model/unet.py, model/shift_unet.py, diffusion/ddim.py and
+ * diffusion/gaussian_diffusion.py.  Each entry point below replaces the ATen call group named in
+ * its comment (reference file:line) with one hand-written sm_100a kernel launch.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller;
+ *   - activations are NHWC ("channels last", [B][H][W][C]) unless a flag says NCHW;
+ *   - every call is asynchronous on `stream` (a cudaStream_t), allocates nothing, and is legal
+ *     inside CUDA-graph capture;
+ *   - return 0 on success, a negative PDAE_E* code otherwise; pdae_last_error() gives the message
+ *     (thread-local).  Nothing throws or aborts.
+ *   - there is NO CPU fallback: without an sm_100 device every compute entry point fails.
+ */
+#ifndef PDAE_B200_H
+#define PDAE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* pdae_stream_t; /* cudaStream_t */
+
+#define PDAE_OK 0
+#define PDAE_EINVAL (-1)  /* bad argument / unsupported shape */
+#define PDAE_ECUDA (-2)   /* CUDA runtime / launch error      */
+#define PDAE_ENODEV (-3)  /* no sm_100 device                 */
+
+#define PDAE_F32 0
+#define PDAE_BF16 1
+
+#define PDAE_RESAMPLE_NONE 0
+#define PDAE_RESAMPLE_UP2 1   /* nearest x2   (model/module.py:162-172) */
+#define PDAE_RESAMPLE_DOWN2 2 /* avgpool 2x2  (model/module.py:200-202) */
+
+const char* pdae_last_error(void);
+int pdae_abi_version(void);
+/* 0 if the current device is sm_100 (B200), PDAE_ENODEV otherwise. */
+int pdae_device_check(void);
+
+/* ---- implicit-GEMM convolution / linear, fp32 CUDA-core math ("parity mode") -------------------
+ * out[b,oy,ox,n] = bias[n] + residual[b,oy,ox,n] + sum_{ky,kx,c} w[ky*k+kx][c][n] * f(in[b, oy*s-p+ky, ox*s-p+kx, c])
+ * f = SiLU if a_silu else identity.  Replaces nn.Conv2d / nn.Conv1d(k=1) / nn.Linear (H=W=1,k=1)
+ * at model/module.py:241-243,255-266,268-276,410,420; unet.py:51-55; shift_unet.py:52-63;
+ * encoder/ffhq.py:12-35; mlp_skip_net.py:96,99.
+ * w_packed: fp32 [k*k][Cin][Cout].  in_nchw / out_nchw select NCHW addressing for that tensor
+ * (fp32 only).  residual (optional) is fp32 NHWC shaped like out.                                   */
+int pdae_conv2d_simt(const void* in, int in_dtype, int in_nchw, const float* w_packed, const float* bias,
+                     const float* residual, float* out, int out_nchw, int B, int H, int W, int Cin, int Cout,
+                     int ksize, int stride, int pad, int a_silu, pdae_stream_t stream);
+
+/* 3x3 pad-1 stride-1 conv with Cout <= 4 (the UNet `out` / `shift_out` heads, unet.py:171-175,
+ * shift_unet.py:239-249): bandwidth kernel, NHWC in (fp32|bf16), NCHW fp32 out.
+ * w_packed4: fp32 [9][Cin][4] (zero-padded over Cout).                                              */
+int pdae_conv3x3_smalln(const void* in, int in_dtype, const float* w_packed4, const float* bias, float* out_nchw,
+                        int B, int H, int W, int Cin, int Cout, pdae_stream_t stream);
+
+/* ---- GroupNorm(32, C) split into stats -> per-(b,c) affine coefficients -> apply ------------------
+ * Replaces F.group_norm + SiLU + AdaGN modulation + F.interpolate / AvgPool2d + torch.cat
+ * (model/module.py:56-63,278-297,361-384,162-172,200-202; unet.py:199-200; shift_unet.py:276-281). */
+
+/* sums[b][g] = (sum x, sum x^2) in fp64 over the virtual channel-concat [src1 (C1) | src2 (C2)].
+ * src2 may be NULL (C2 = 0).  C1, C2 multiples of 4; (C1+C2) % 32 == 0.                              */
+int pdae_gn_stats(const float* src1, int C1, const float* src2, int C2, int B, int HW, double* sums,
+                  pdae_stream_t stream);
+
+/* ab[b][0][c] = a, ab[b][1][c] = b with  y = a*x + b  ==  (1+zs)*((x-mu)*rstd*gamma+beta)*(1+s)+sh)+zsh.
+ * emb / embz (optional) are rows of 2C floats (scale | shift) with leading dimension *_ld.            */
+int pdae_gn_coef(const double* sums, const float* gamma, const float* beta, int B, int C, int HW, float eps,
+                 const float* emb, int emb_ld, const float* embz, int embz_ld, float* ab, pdae_stream_t stream);
+
+/* out_act = resample( f(a*x+b) ) over the virtual concat; f = SiLU if silu.  ab == NULL -> a=1,b=0.
+ * out_raw (optional) = resample(x) (the un-normalised input, for the skip path).  H, W are the SOURCE
+ * dims; outputs are [B][H'][W'][C1+C2] with H' = 2H (UP2), H/2 (DOWN2) or H.                          */
+int pdae_gn_apply(const float* src1, int C1, const float* src2, int C2, const float* ab, int silu, int resample,
+                  int B, int H, int W, void* out_act, int act_dtype, void* out_raw, int raw_dtype,
+                  pdae_stream_t stream);
+
+/* ---- attention (model/module.py:422-488) ---------------------------------------------------------
+ * qkv: fp32 [B][T][3C] token-major.  legacy != 0: per-head channel blocks [q|k|v] (QKVAttentionLegacy);
+ * else [all q | all k | all v] (QKVAttention).  out: fp32 [B][T][C], head h at channels h*ch.
+ * scratch: fp32 [B*heads][T][T].                                                                     */
+int pdae_attention_simt(const float* qkv, float* out, float* scratch, int B, int T, int C, int heads, int legacy,
+                        pdae_stream_t stream);
+
+/* ---- embeddings -------------------------------------------------------------------------------- */
+/* model/module.py:66-84: out[b] = [cos(t*f) | sin(t*f) | 0 if dim odd]; freqs = device fp32 [dim/2],
+ * f_i = exp(-ln(1e4) i/half) evaluated by the caller with the reference's fp32 op order.             */
+int pdae_timestep_embedding(const int64_t* t, int B, int dim, const float* freqs, float* out, pdae_stream_t stream);
+/* unet.py:190-192: emb[b] += table[idx[b]].                                                          */
+int pdae_embedding_add(float* emb, const float* table, const int64_t* idx, int B, int E, pdae_stream_t stream);
+
+/* ---- per-step diffusion arithmetic -------------------------------------------------------------- */
+/* ddim.py:43-55,66-79,91-107,123-138.  Tables are the fp32 DDIM tables indexed by t[b]:
+ * e = eps - s1m[t]*grad (if grad); x0 = clamp(A[t]*x - Bm[t]*e, -1, 1); e' = (A[t]*x - x0)/Bm[t];
+ * out = x0*sqrt(ab[t]) + sqrt(1-ab[t])*e'  with ab = alphas_cumprod_prev (sample) or _next (encode).  */
+int pdae_ddim_step(const float* x, const float* eps, const float* grad, const int64_t* t, const float* tab_A,
+                   const float* tab_Bm, const float* tab_s1m, const float* tab_ab, float* out, int B,
+                   int64_t per_sample, pdae_stream_t stream);
+/* gaussian_diffusion.py:98-103: out = c1[t]*x0 + c2[t]*noise.                                         */
+int pdae_q_sample(const float* x0, const float* noise, const int64_t* t, const float* tab_c1, const float* tab_c2,
+                  float* out, int B, int64_t per_sample, pdae_stream_t stream);
+/* gaussian_diffusion.py:112-126,148-154: DDPM ancestral step with caller-provided N(0,1) noise.
+ * learned_range optional (then tab_logbeta is log(betas)).                                           */
+int pdae_noise_p_sample(const float* x, const float* eps, const float* noise, const float* learned_range,
+                        const int64_t* t, const float* tab_cx, const float* tab_ce, const float* tab_logvar,
+                        const float* tab_logbeta, float* out, int B, int64_t per_sample, pdae_stream_t stream);
+
+/* ---- latent MLP row op (mlp_skip_net.py:123-141) -------------------------------------------------
+ * y = act( LN( h * (1 + cond) ) ) per row; cond/ln_w optional; act = SiLU if silu.  out has row stride
+ * out_ld (so it can land inside the [h | x] concat buffer of the next layer).                         */
+int pdae_mlp_mod_ln_act(const float* h, const float* cond, const float* ln_w, const float* ln_b, float eps,
+                        int silu, float* out, int out_ld, int B, int N, pdae_stream_t stream);
+/* dst[b][col0 + j] = src[b][j], j < N (row strides dst_ld / N).                                       */
+int pdae_copy_cols(const float* src, float* dst, int dst_ld, int col0, int B, int N, pdae_stream_t stream);
+
+/* ---- tensor-core convolution: TMA -> tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) ---------------------
+ * Same contract as pdae_conv2d_simt for ksize in {1,3}, stride 1, pad ksize/2, Cin % 64 == 0,
+ * Cout % 64 == 0, bf16 NHWC input (already normalised/activated by pdae_gn_apply), weights bf16
+ * [k*k][Cout][Cin].  A plan owns the TMA descriptors for fixed buffers; run it any number of times.   */
+typedef struct pdae_conv_tc_plan pdae_conv_tc_plan;
+int pdae_conv_tc_create(pdae_conv_tc_plan** plan, const void* in_bf16, const void* w_bf16, const float* bias,
+                        const float* residual, float* out, int B, int H, int W, int Cin, int Cout, int ksize);
+int pdae_conv_tc_run(const pdae_conv_tc_plan* plan, pdae_stream_t stream);
+void pdae_conv_tc_destroy(pdae_conv_tc_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDAE_B200_H */

@@ -1,0 +1,148 @@
+// fp32 CUDA-core QKV attention ("parity mode"): S = (Q K^T) * ch^-1/2, softmax over keys, O = P V.
+// Three launches per call: batched GEMM (NT) -> row softmax -> batched GEMM (NN).  Token-major
+// (NHWC) operands, so Q/K/V are strided column blocks of the [B][T][3C] qkv tensor.
+#include "common.cuh"
+
+namespace pdae {
+
+constexpr int GM = 64, GN = 64, GK = 16;
+
+struct GemmArgs {
+  const float* A; const float* Bm; float* C;
+  int M, N, K;
+  long long lda, ldb, ldc;
+  // batch z = (b, h): offset = b * *_bs + h * *_hs
+  long long a_bs, a_hs, b_bs, b_hs, c_bs, c_hs;
+  int heads;
+  int transB;  // 1: B given as [N][K] (row n, k contiguous) ; 0: [K][N]
+  float alpha;
+};
+
+__global__ void __launch_bounds__(256) gemm_batched_kernel(GemmArgs p) {
+  __shared__ float As[GK][GM + 4];
+  __shared__ float Bs[GK][GN + 4];
+  const int z = blockIdx.z, bb = z / p.heads, hh = z % p.heads;
+  const float* __restrict__ A = p.A + bb * p.a_bs + hh * p.a_hs;
+  const float* __restrict__ Bm = p.Bm + bb * p.b_bs + hh * p.b_hs;
+  float* __restrict__ C = p.C + bb * p.c_bs + hh * p.c_hs;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * GM, n0 = blockIdx.y * GN;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < p.K; k0 += GK) {
+    // A: 64 rows x 16 k ; thread -> (row = tid/4, k = (tid%4)*4 + i)
+    {
+      const int r = tid >> 2, kq = (tid & 3) * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = m0 + r, k = k0 + kq + i;
+        As[kq + i][r] = (m < p.M && k < p.K) ? A[(long long)m * p.lda + k] : 0.f;
+      }
+    }
+    if (p.transB) {
+      const int r = tid >> 2, kq = (tid & 3) * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int n = n0 + r, k = k0 + kq + i;
+        Bs[kq + i][r] = (n < p.N && k < p.K) ? Bm[(long long)n * p.ldb + k] : 0.f;
+      }
+    } else {
+      const int k = tid >> 4, nq = (tid & 15) * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int n = n0 + nq + i, kk = k0 + k;
+        Bs[k][nq + i] = (n < p.N && kk < p.K) ? Bm[(long long)kk * p.ldb + n] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { av[i] = As[k][ty * 4 + i]; bv[i] = Bs[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < p.N) C[(long long)m * p.ldc + n] = p.alpha * acc[i][j];
+    }
+  }
+}
+
+// one warp per row, cols <= 4096
+__global__ void softmax_rows_kernel(float* __restrict__ S, long long rows, int cols) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float* r = S + row * cols;
+  float mx = -INFINITY;
+  for (int j = lane; j < cols; j += 32) mx = fmaxf(mx, r[j]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int j = lane; j < cols; j += 32) {
+    const float e = expf(r[j] - mx);
+    r[j] = e;
+    sum += e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.0f / sum;
+  for (int j = lane; j < cols; j += 32) r[j] *= inv;
+}
+
+}  // namespace pdae
+
+using namespace pdae;
+
+extern "C" int pdae_attention_simt(const float* qkv, float* out, float* scratch, int B, int T, int C, int heads,
+                                   int legacy, pdae_stream_t stream) {
+  PDAE_REQUIRE(qkv && out && scratch, "attention_simt: null pointer");
+  PDAE_REQUIRE(heads > 0 && C % heads == 0, "attention_simt: C %% heads != 0");
+  PDAE_REQUIRE((long long)B * heads <= 65535, "attention_simt: B*heads too large for grid.z");
+  const int ch = C / heads;
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long row = 3LL * C;
+  // channel offsets of q, k, v for head h: legacy -> h*3ch + {0, ch, 2ch} ; new -> {0, C, 2C} + h*ch
+  const long long hs = legacy ? 3LL * ch : ch;
+  const long long qo = 0, ko = legacy ? ch : C, vo = legacy ? 2LL * ch : 2LL * C;
+  GemmArgs g;
+  g.heads = heads;
+  // S[z] = alpha * Q K^T
+  g.A = qkv + qo; g.Bm = qkv + ko; g.C = scratch;
+  g.M = T; g.N = T; g.K = ch; g.lda = row; g.ldb = row; g.ldc = T;
+  g.a_bs = (long long)T * row; g.a_hs = hs; g.b_bs = (long long)T * row; g.b_hs = hs;
+  g.c_bs = (long long)heads * T * T; g.c_hs = (long long)T * T;
+  g.transB = 1;
+  g.alpha = 1.0f / sqrtf((float)ch);
+  dim3 grid1(cdiv(T, GM), cdiv(T, GN), B * heads);
+  gemm_batched_kernel<<<grid1, 256, 0, s>>>(g);
+  PDAE_LAUNCH_CHECK("gemm_batched_kernel(QK)");
+  const long long rows = (long long)B * heads * T;
+  softmax_rows_kernel<<<cdiv(rows * 32, 256), 256, 0, s>>>(scratch, rows, T);
+  PDAE_LAUNCH_CHECK("softmax_rows_kernel");
+  // O[z] = P V  -> out[b][t][h*ch + c]
+  g.A = scratch; g.Bm = qkv + vo; g.C = out;
+  g.M = T; g.N = ch; g.K = T; g.lda = T; g.ldb = row; g.ldc = C;
+  g.a_bs = (long long)heads * T * T; g.a_hs = (long long)T * T; g.b_bs = (long long)T * row; g.b_hs = hs;
+  g.c_bs = (long long)T * C; g.c_hs = ch;
+  g.transB = 0;
+  g.alpha = 1.0f;
+  dim3 grid2(cdiv(T, GM), cdiv(ch, GN), B * heads);
+  gemm_batched_kernel<<<grid2, 256, 0, s>>>(g);
+  PDAE_LAUNCH_CHECK("gemm_batched_kernel(PV)");
+  return PDAE_OK;
+}

@@ -1,0 +1,447 @@
+// GroupNorm(32) stats / coefficients / apply (+SiLU, +AdaGN, +concat, +up/down resample), embeddings,
+// per-step diffusion arithmetic and the latent-MLP row op.  All HBM-bound: vectorised, coalesced along
+// the NHWC channel axis, one pass over the data each.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace pdae {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---------------------------------------------------------------------------------------------
+// stats: grid (pixel chunks, B). Thread = (channel quad, pixel row) ; per-channel partial sums in
+// registers -> shared per-channel fp32 -> per-group fp64 atomics.
+constexpr int STATS_PIX = 256;
+
+__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ s1, int C1,
+                                                       const float* __restrict__ s2, int C2, int HW,
+                                                       double* __restrict__ sums) {
+  extern __shared__ float sh[];  // [2][C]
+  const int C = C1 + C2, L = C >> 2;
+  const int Lb = L < 256 ? L : 256;
+  const int R = 256 / Lb;
+  const int tid = threadIdx.x;
+  const int lane = tid % Lb, row = tid / Lb;
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * STATS_PIX;
+  const int p1 = min(HW, p0 + STATS_PIX);
+  for (int i = tid; i < 2 * C; i += 256) sh[i] = 0.f;
+  __syncthreads();
+  if (row < R) {
+    for (int cq = lane; cq < L; cq += Lb) {
+      const int c = cq * 4;
+      const float* base;
+      int cs, cc;
+      if (c < C1) { base = s1; cs = C1; cc = c; } else { base = s2; cs = C2; cc = c - C1; }
+      base += (long long)b * HW * cs + cc;
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+      for (int p = p0 + row; p < p1; p += R) {
+        const float4 v = *reinterpret_cast<const float4*>(base + (long long)p * cs);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+      }
+      atomicAdd(&sh[c + 0], s.x); atomicAdd(&sh[c + 1], s.y); atomicAdd(&sh[c + 2], s.z); atomicAdd(&sh[c + 3], s.w);
+      atomicAdd(&sh[C + c + 0], q.x); atomicAdd(&sh[C + c + 1], q.y); atomicAdd(&sh[C + c + 2], q.z); atomicAdd(&sh[C + c + 3], q.w);
+    }
+  }
+  __syncthreads();
+  if (tid < 64) {
+    const int g = tid & 31, which = tid >> 5;
+    const int cpg = C / 32;
+    double a = 0.0;
+    for (int j = 0; j < cpg; ++j) a += (double)sh[which * C + g * cpg + j];
+    atomicAdd(&sums[((long long)b * 32 + g) * 2 + which], a);
+  }
+}
+
+__global__ void gn_coef_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, int C, int HW, float eps,
+                               const float* __restrict__ emb, int emb_ld, const float* __restrict__ embz, int embz_ld,
+                               float* __restrict__ ab) {
+  const int b = blockIdx.x;
+  const int cpg = C / 32;
+  const double n = (double)HW * cpg;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const double mean = sums[((long long)b * 32 + g) * 2] / n;
+    double var = sums[((long long)b * 32 + g) * 2 + 1] / n - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    float a = gamma[c] * rstd;
+    float bb = beta[c] - (float)mean * a;
+    if (emb) {
+      const float s = 1.0f + emb[(long long)b * emb_ld + c], shv = emb[(long long)b * emb_ld + C + c];
+      a *= s;
+      bb = bb * s + shv;
+    }
+    if (embz) {
+      const float s = 1.0f + embz[(long long)b * embz_ld + c], shv = embz[(long long)b * embz_ld + C + c];
+      a *= s;
+      bb = bb * s + shv;
+    }
+    ab[((long long)b * 2 + 0) * C + c] = a;
+    ab[((long long)b * 2 + 1) * C + c] = bb;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// apply: flat float4 work items over [pixels][C/4]; consecutive threads walk consecutive channel quads.
+__device__ __forceinline__ float4 affine_act(float4 v, float4 a, float4 b, int silu) {
+  float4 r;
+  r.x = fmaf(a.x, v.x, b.x); r.y = fmaf(a.y, v.y, b.y); r.z = fmaf(a.z, v.z, b.z); r.w = fmaf(a.w, v.w, b.w);
+  if (silu) { r.x = silu_f(r.x); r.y = silu_f(r.y); r.z = silu_f(r.z); r.w = silu_f(r.w); }
+  return r;
+}
+
+template <typename TAct, typename TRaw, int RS>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ s1, int C1,
+                                                       const float* __restrict__ s2, int C2,
+                                                       const float* __restrict__ ab, int silu, int H, int W,
+                                                       TAct* __restrict__ out_act, TRaw* __restrict__ out_raw) {
+  const int C = C1 + C2, L = C >> 2;
+  const int b = blockIdx.y;
+  // iteration space: source pixels for NONE / UP2, output pixels for DOWN2
+  const int Hi = RS == PDAE_RESAMPLE_DOWN2 ? H / 2 : H, Wi = RS == PDAE_RESAMPLE_DOWN2 ? W / 2 : W;
+  const long long items = (long long)Hi * Wi * L;
+  const int Ho = RS == PDAE_RESAMPLE_UP2 ? 2 * H : Hi, Wo = RS == PDAE_RESAMPLE_UP2 ? 2 * W : Wi;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
+       it += (long long)gridDim.x * blockDim.x) {
+    const int cq = (int)(it % L);
+    const long long pix = it / L;
+    const int x = (int)(pix % Wi), y = (int)(pix / Wi);
+    const int c = cq * 4;
+    const float* base;
+    int cs, cc;
+    if (c < C1) { base = s1; cs = C1; cc = c; } else { base = s2; cs = C2; cc = c - C1; }
+    base += (long long)b * H * W * cs + cc;
+    float4 a = make_float4(1.f, 1.f, 1.f, 1.f), bb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ab) {
+      a = *reinterpret_cast<const float4*>(ab + ((long long)b * 2 + 0) * C + c);
+      bb = *reinterpret_cast<const float4*>(ab + ((long long)b * 2 + 1) * C + c);
+    }
+    if (RS == PDAE_RESAMPLE_DOWN2) {
+      float4 accA = make_float4(0.f, 0.f, 0.f, 0.f), accR = accA;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const float4 v = *reinterpret_cast<const float4*>(base + ((long long)(2 * y + dy) * W + 2 * x + dx) * cs);
+          const float4 r = affine_act(v, a, bb, silu);
+          accA.x += r.x; accA.y += r.y; accA.z += r.z; accA.w += r.w;
+          accR.x += v.x; accR.y += v.y; accR.z += v.z; accR.w += v.w;
+        }
+      const long long o = (((long long)b * Ho + y) * Wo + x) * C + c;
+      store4<TAct>(out_act + o, make_float4(accA.x * 0.25f, accA.y * 0.25f, accA.z * 0.25f, accA.w * 0.25f));
+      if (out_raw) store4<TRaw>(out_raw + o, make_float4(accR.x * 0.25f, accR.y * 0.25f, accR.z * 0.25f, accR.w * 0.25f));
+    } else {
+      const float4 v = *reinterpret_cast<const float4*>(base + ((long long)y * W + x) * cs);
+      const float4 r = affine_act(v, a, bb, silu);
+      if (RS == PDAE_RESAMPLE_UP2) {
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) {
+            const long long o = (((long long)b * Ho + 2 * y + dy) * Wo + 2 * x + dx) * C + c;
+            store4<TAct>(out_act + o, r);
+            if (out_raw) store4<TRaw>(out_raw + o, v);
+          }
+      } else {
+        const long long o = (((long long)b * Ho + y) * Wo + x) * C + c;
+        store4<TAct>(out_act + o, r);
+        if (out_raw) store4<TRaw>(out_raw + o, v);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, int B, int dim,
+                                          const float* __restrict__ freqs, float* __restrict__ out) {
+  const int half = dim / 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * dim) return;
+  const int b = idx / dim, j = idx % dim;
+  float v = 0.f;
+  if (j < 2 * half) {
+    const int i = j < half ? j : j - half;
+    // freqs[] is computed on the host with the reference's own fp32 op sequence (a 1-ulp difference in
+    // exp() would be amplified ~1000x by t before the cos/sin).
+    const float arg = __fmul_rn((float)t[b], freqs[i]);
+    v = j < half ? cosf(arg) : sinf(arg);
+  }
+  out[idx] = v;
+}
+
+__global__ void embedding_add_kernel(float* __restrict__ emb, const float* __restrict__ table,
+                                     const int64_t* __restrict__ idx, int B, int E) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * E) return;
+  const int b = i / E, j = i % E;
+  emb[i] += table[idx[b] * E + j];
+}
+
+__global__ void ddim_step_kernel(const float* __restrict__ x, const float* __restrict__ eps,
+                                 const float* __restrict__ grad, const int64_t* __restrict__ t,
+                                 const float* __restrict__ tA, const float* __restrict__ tB,
+                                 const float* __restrict__ tS, const float* __restrict__ tab,
+                                 float* __restrict__ out, long long per_sample, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per_sample);
+    const int64_t tb = t[b];
+    const float A = tA[tb], Bm = tB[tb], abar = tab[tb];
+    float e = eps[i];
+    if (grad) e = __fsub_rn(e, __fmul_rn(tS[tb], grad[i]));
+    const float ax = __fmul_rn(A, x[i]);
+    float x0 = __fsub_rn(ax, __fmul_rn(Bm, e));
+    x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+    const float e2 = __fdiv_rn(__fsub_rn(ax, x0), Bm);
+    out[i] = __fadd_rn(__fmul_rn(x0, sqrtf(abar)), __fmul_rn(sqrtf(__fsub_rn(1.0f, abar)), e2));
+  }
+}
+
+__global__ void q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
+                                const int64_t* __restrict__ t, const float* __restrict__ c1,
+                                const float* __restrict__ c2, float* __restrict__ out, long long per_sample,
+                                long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int64_t tb = t[i / per_sample];
+    out[i] = __fadd_rn(__fmul_rn(c1[tb], x0[i]), __fmul_rn(c2[tb], noise[i]));
+  }
+}
+
+__global__ void noise_p_sample_kernel(const float* __restrict__ x, const float* __restrict__ eps,
+                                      const float* __restrict__ noise, const float* __restrict__ lr,
+                                      const int64_t* __restrict__ t, const float* __restrict__ cx,
+                                      const float* __restrict__ ce, const float* __restrict__ logvar,
+                                      const float* __restrict__ logbeta, float* __restrict__ out,
+                                      long long per_sample, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int64_t tb = t[i / per_sample];
+    const float mean = __fsub_rn(__fmul_rn(cx[tb], x[i]), __fmul_rn(ce[tb], eps[i]));
+    float lv = logvar[tb];
+    if (lr) {
+      const float frac = __fmul_rn(__fadd_rn(lr[i], 1.0f), 0.5f);
+      lv = __fadd_rn(lv, __fmul_rn(frac, __fsub_rn(logbeta[tb], lv)));
+    }
+    const float mask = tb == 0 ? 0.0f : 1.0f;
+    out[i] = __fadd_rn(mean, __fmul_rn(__fmul_rn(mask, expf(__fmul_rn(0.5f, lv))), noise[i]));
+  }
+}
+
+// one CTA per row: y = act(LN(h*(1+cond)))
+__global__ void __launch_bounds__(256) mlp_mod_ln_act_kernel(const float* __restrict__ h, const float* __restrict__ cond,
+                                                             const float* __restrict__ lw, const float* __restrict__ lb,
+                                                             float eps, int silu, float* __restrict__ out, int out_ld,
+                                                             int N) {
+  __shared__ float red[2][8];
+  const int b = blockIdx.x;
+  const float* hr = h + (long long)b * N;
+  const float* cr = cond ? cond + (long long)b * N : nullptr;
+  float s = 0.f, q = 0.f;
+  for (int j = threadIdx.x; j < N; j += 256) {
+    float v = hr[j];
+    if (cr) v = v * (1.0f + cr[j]);
+    s += v;
+    q = fmaf(v, v, q);
+  }
+  float mean = 0.f, rstd = 1.f;
+  if (lw) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = q; }
+    __syncthreads();
+    double ds = 0.0, dq = 0.0;
+    for (int w = 0; w < 8; ++w) { ds += red[0][w]; dq += red[1][w]; }
+    const double m = ds / N;
+    double var = dq / N - m * m;
+    var = var < 0.0 ? 0.0 : var;
+    mean = (float)m;
+    rstd = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  for (int j = threadIdx.x; j < N; j += 256) {
+    float v = hr[j];
+    if (cr) v = v * (1.0f + cr[j]);
+    if (lw) v = (v - mean) * rstd * lw[j] + lb[j];
+    if (silu) v = silu_f(v);
+    out[(long long)b * out_ld + j] = v;
+  }
+}
+
+__global__ void copy_cols_kernel(const float* __restrict__ src, float* __restrict__ dst, int dst_ld, int col0, int B,
+                                 int N) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * N) return;
+  const int b = (int)(i / N), j = (int)(i % N);
+  dst[(long long)b * dst_ld + col0 + j] = src[i];
+}
+
+}  // namespace pdae
+
+using namespace pdae;
+
+extern "C" const char* pdae_last_error(void) { return g_err; }
+extern "C" int pdae_abi_version(void) { return 1; }
+extern "C" int pdae_device_check(void) {
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    set_error("no CUDA device available");
+    return PDAE_ENODEV;
+  }
+  if (prop.major != 10) {
+    set_error("device is sm_%d%d; pdae_b200 is built for sm_100a only", prop.major, prop.minor);
+    return PDAE_ENODEV;
+  }
+  return PDAE_OK;
+}
+
+extern "C" int pdae_gn_stats(const float* src1, int C1, const float* src2, int C2, int B, int HW, double* sums,
+                             pdae_stream_t stream) {
+  PDAE_REQUIRE(src1 && sums, "gn_stats: null pointer");
+  if (!src2) C2 = 0;
+  const int C = C1 + C2;
+  PDAE_REQUIRE(C1 % 4 == 0 && C2 % 4 == 0 && C % 32 == 0 && C > 0, "gn_stats: C1=%d C2=%d unsupported", C1, C2);
+  PDAE_REQUIRE((size_t)2 * C * sizeof(float) <= 48 * 1024, "gn_stats: C too large");
+  cudaStream_t s = (cudaStream_t)stream;
+  PDAE_CUDA(cudaMemsetAsync(sums, 0, (size_t)B * 32 * 2 * sizeof(double), s));
+  dim3 grid(cdiv(HW, STATS_PIX), B);
+  gn_stats_kernel<<<grid, 256, 2 * C * sizeof(float), s>>>(src1, C1, src2, C2, HW, sums);
+  PDAE_LAUNCH_CHECK("gn_stats_kernel");
+  return PDAE_OK;
+}
+
+extern "C" int pdae_gn_coef(const double* sums, const float* gamma, const float* beta, int B, int C, int HW, float eps,
+                            const float* emb, int emb_ld, const float* embz, int embz_ld, float* ab,
+                            pdae_stream_t stream) {
+  PDAE_REQUIRE(sums && gamma && beta && ab, "gn_coef: null pointer");
+  PDAE_REQUIRE(C % 32 == 0, "gn_coef: C %% 32 != 0");
+  gn_coef_kernel<<<B, C < 1024 ? C : 1024, 0, (cudaStream_t)stream>>>(sums, gamma, beta, C, HW, eps, emb, emb_ld, embz,
+                                                                      embz_ld, ab);
+  PDAE_LAUNCH_CHECK("gn_coef_kernel");
+  return PDAE_OK;
+}
+
+template <typename TAct, typename TRaw>
+static int launch_apply(const float* s1, int C1, const float* s2, int C2, const float* ab, int silu, int resample, int B,
+                        int H, int W, void* out_act, void* out_raw, cudaStream_t s) {
+  const int L = (C1 + C2) / 4;
+  const int Hi = resample == PDAE_RESAMPLE_DOWN2 ? H / 2 : H, Wi = resample == PDAE_RESAMPLE_DOWN2 ? W / 2 : W;
+  const long long items = (long long)Hi * Wi * L;
+  int gx = cdiv(items, 256);
+  if (gx > 148 * 16) gx = 148 * 16;
+  dim3 grid(gx, B);
+  TAct* oa = (TAct*)out_act;
+  TRaw* orw = (TRaw*)out_raw;
+  if (resample == PDAE_RESAMPLE_NONE)
+    gn_apply_kernel<TAct, TRaw, PDAE_RESAMPLE_NONE><<<grid, 256, 0, s>>>(s1, C1, s2, C2, ab, silu, H, W, oa, orw);
+  else if (resample == PDAE_RESAMPLE_UP2)
+    gn_apply_kernel<TAct, TRaw, PDAE_RESAMPLE_UP2><<<grid, 256, 0, s>>>(s1, C1, s2, C2, ab, silu, H, W, oa, orw);
+  else
+    gn_apply_kernel<TAct, TRaw, PDAE_RESAMPLE_DOWN2><<<grid, 256, 0, s>>>(s1, C1, s2, C2, ab, silu, H, W, oa, orw);
+  PDAE_LAUNCH_CHECK("gn_apply_kernel");
+  return PDAE_OK;
+}
+
+extern "C" int pdae_gn_apply(const float* src1, int C1, const float* src2, int C2, const float* ab, int silu,
+                             int resample, int B, int H, int W, void* out_act, int act_dtype, void* out_raw,
+                             int raw_dtype, pdae_stream_t stream) {
+  PDAE_REQUIRE(src1 && out_act, "gn_apply: null pointer");
+  if (!src2) C2 = 0;
+  PDAE_REQUIRE(C1 % 4 == 0 && C2 % 4 == 0 && C1 + C2 > 0, "gn_apply: C1=%d C2=%d unsupported", C1, C2);
+  PDAE_REQUIRE(resample >= 0 && resample <= 2, "gn_apply: bad resample mode");
+  PDAE_REQUIRE(resample != PDAE_RESAMPLE_DOWN2 || (H % 2 == 0 && W % 2 == 0), "gn_apply: odd dims for DOWN2");
+  cudaStream_t s = (cudaStream_t)stream;
+  typedef __nv_bfloat16 bf;
+  if (act_dtype == PDAE_F32 && raw_dtype == PDAE_F32)
+    return launch_apply<float, float>(src1, C1, src2, C2, ab, silu, resample, B, H, W, out_act, out_raw, s);
+  if (act_dtype == PDAE_BF16 && raw_dtype == PDAE_F32)
+    return launch_apply<bf, float>(src1, C1, src2, C2, ab, silu, resample, B, H, W, out_act, out_raw, s);
+  if (act_dtype == PDAE_BF16 && raw_dtype == PDAE_BF16)
+    return launch_apply<bf, bf>(src1, C1, src2, C2, ab, silu, resample, B, H, W, out_act, out_raw, s);
+  PDAE_REQUIRE(false, "gn_apply: unsupported dtype combination act=%d raw=%d", act_dtype, raw_dtype);
+}
+
+extern "C" int pdae_timestep_embedding(const int64_t* t, int B, int dim, const float* freqs, float* out,
+                                       pdae_stream_t stream) {
+  PDAE_REQUIRE(t && out && freqs && B > 0 && dim > 0, "timestep_embedding: bad args");
+  timestep_embedding_kernel<<<cdiv((long long)B * dim, 256), 256, 0, (cudaStream_t)stream>>>(t, B, dim, freqs, out);
+  PDAE_LAUNCH_CHECK("timestep_embedding_kernel");
+  return PDAE_OK;
+}
+
+extern "C" int pdae_embedding_add(float* emb, const float* table, const int64_t* idx, int B, int E,
+                                  pdae_stream_t stream) {
+  PDAE_REQUIRE(emb && table && idx, "embedding_add: null pointer");
+  embedding_add_kernel<<<cdiv((long long)B * E, 256), 256, 0, (cudaStream_t)stream>>>(emb, table, idx, B, E);
+  PDAE_LAUNCH_CHECK("embedding_add_kernel");
+  return PDAE_OK;
+}
+
+static inline int ew_grid(long long total) {
+  int g = cdiv(total, 256);
+  return g > 148 * 16 ? 148 * 16 : g;
+}
+
+extern "C" int pdae_ddim_step(const float* x, const float* eps, const float* grad, const int64_t* t, const float* tab_A,
+                              const float* tab_Bm, const float* tab_s1m, const float* tab_ab, float* out, int B,
+                              int64_t per_sample, pdae_stream_t stream) {
+  PDAE_REQUIRE(x && eps && t && tab_A && tab_Bm && tab_ab && out, "ddim_step: null pointer");
+  PDAE_REQUIRE(!grad || tab_s1m, "ddim_step: grad given without sqrt_one_minus_alphas_cumprod table");
+  const long long total = (long long)B * per_sample;
+  ddim_step_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(x, eps, grad, t, tab_A, tab_Bm, tab_s1m, tab_ab, out,
+                                                                    per_sample, total);
+  PDAE_LAUNCH_CHECK("ddim_step_kernel");
+  return PDAE_OK;
+}
+
+extern "C" int pdae_q_sample(const float* x0, const float* noise, const int64_t* t, const float* tab_c1,
+                             const float* tab_c2, float* out, int B, int64_t per_sample, pdae_stream_t stream) {
+  PDAE_REQUIRE(x0 && noise && t && tab_c1 && tab_c2 && out, "q_sample: null pointer");
+  const long long total = (long long)B * per_sample;
+  q_sample_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(x0, noise, t, tab_c1, tab_c2, out, per_sample, total);
+  PDAE_LAUNCH_CHECK("q_sample_kernel");
+  return PDAE_OK;
+}
+
+extern "C" int pdae_noise_p_sample(const float* x, const float* eps, const float* noise, const float* learned_range,
+                                   const int64_t* t, const float* tab_cx, const float* tab_ce, const float* tab_logvar,
+                                   const float* tab_logbeta, float* out, int B, int64_t per_sample,
+                                   pdae_stream_t stream) {
+  PDAE_REQUIRE(x && eps && noise && t && tab_cx && tab_ce && tab_logvar && out, "noise_p_sample: null pointer");
+  PDAE_REQUIRE(!learned_range || tab_logbeta, "noise_p_sample: learned_range needs log(betas)");
+  const long long total = (long long)B * per_sample;
+  noise_p_sample_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(x, eps, noise, learned_range, t, tab_cx, tab_ce,
+                                                                         tab_logvar, tab_logbeta, out, per_sample, total);
+  PDAE_LAUNCH_CHECK("noise_p_sample_kernel");
+  return PDAE_OK;
+}
+
+extern "C" int pdae_mlp_mod_ln_act(const float* h, const float* cond, const float* ln_w, const float* ln_b, float eps,
+                                   int silu, float* out, int out_ld, int B, int N, pdae_stream_t stream) {
+  PDAE_REQUIRE(h && out && B > 0 && N > 0 && out_ld >= N, "mlp_mod_ln_act: bad args");
+  PDAE_REQUIRE(!ln_w || ln_b, "mlp_mod_ln_act: LayerNorm weight without bias");
+  mlp_mod_ln_act_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(h, cond, ln_w, ln_b, eps, silu, out, out_ld, N);
+  PDAE_LAUNCH_CHECK("mlp_mod_ln_act_kernel");
+  return PDAE_OK;
+}
+
+extern "C" int pdae_copy_cols(const float* src, float* dst, int dst_ld, int col0, int B, int N, pdae_stream_t stream) {
+  PDAE_REQUIRE(src && dst && col0 >= 0 && col0 + N <= dst_ld, "copy_cols: bad args");
+  copy_cols_kernel<<<cdiv((long long)B * N, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, dst_ld, col0, B, N);
+  PDAE_LAUNCH_CHECK("copy_cols_kernel");
+  return PDAE_OK;
+}

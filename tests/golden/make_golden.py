@@ -1,0 +1,202 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the REAL reference (ckczzj/PDAE at /root/reference).
+
+Run only in the build container (the GPU box has no /root/reference):
+    python tests/golden/make_golden.py
+Each fixture stores the config (JSON), the input seeds and the reference outputs.  Weights are NOT
+stored: both sides regenerate them with pdae_b200.utils.synth (numpy PCG64 keyed by parameter
+name), so a fixture is a few KB.  The oracle (oracle/pdae_oracle.py) and the CUDA path are both
+checked against these files.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+from pdae_b200.utils.synth import fill_module_, synth_images, synth_normal  # noqa: E402
+
+import model.module as rm  # noqa: E402  (reference)
+from model.unet import UNet  # noqa: E402
+from model.shift_unet import ShiftUNet  # noqa: E402
+from model.mlp_skip_net import MLPSkipNet  # noqa: E402
+from model.representation_learning.encoder import CELEBA64Encoder, FFHQEncoder  # noqa: E402
+from diffusion.gaussian_diffusion import GaussianDiffusion  # noqa: E402
+from diffusion.ddim import DDIM  # noqa: E402
+
+torch.set_grad_enabled(False)
+torch.set_num_threads(8)
+
+TINY_UNET = dict(input_channel=3, base_channel=32, channel_multiplier=[1, 2, 2],
+                 num_residual_blocks_of_a_block=1, attention_resolutions=[2], num_heads=1, head_channel=-1,
+                 use_new_attention_order=False, dropout=0.0)
+TINY_UNET_NEW = dict(TINY_UNET, use_new_attention_order=True, num_heads=2, attention_resolutions=[2, 4])
+TINY_UNET_HC = dict(TINY_UNET, head_channel=32, learn_sigma=True)
+TINY_UNET_CLS = dict(TINY_UNET, num_class=10, input_channel=1, attention_resolutions=[])
+TINY_SHIFT = dict(TINY_UNET, latent_dim=64)
+TINY_SHIFT2 = dict(input_channel=3, base_channel=64, channel_multiplier=[1, 2], num_residual_blocks_of_a_block=2,
+                   attention_resolutions=[2], num_heads=1, head_channel=-1, use_new_attention_order=False,
+                   dropout=0.0, latent_dim=512)
+TINY_MLP = dict(input_channel=64, model_channel=128, num_layers=4, time_emb_channel=32, use_norm=True, dropout=0.0)
+DIFF = {"timesteps": 1000, "betas_type": "linear"}
+
+
+def save(name, cfg, **arrays):
+    out = {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in arrays.items()}
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), cfg=np.array(json.dumps(cfg)), **out)
+    print("wrote", name, {k: v.shape for k, v in out.items()})
+
+
+def block_cases():
+    B, E = 2, 128
+    emb = synth_normal((B, E), 11)
+    embz = synth_normal((B, E), 12)
+    for name, kw, shift in [
+        ("res_same", dict(channels=64), False), ("res_widen", dict(channels=32, out_channels=64), False),
+        ("res_narrow", dict(channels=96, out_channels=32), False), ("res_up", dict(channels=32, up=True), False),
+        ("res_down", dict(channels=32, down=True), False), ("shift_same", dict(channels=64), True),
+        ("shift_narrow", dict(channels=96, out_channels=32), True), ("shift_up", dict(channels=32, up=True), True),
+    ]:
+        cls = rm.ResBlockShift if shift else rm.ResBlock
+        m = fill_module_(cls(emb_channels=E, dropout=0.0, **kw), seed=3).eval()
+        x = synth_normal((B, kw["channels"], 8, 8), 13)
+        y = m(x, emb, embz) if shift else m(x, emb)
+        save("block_" + name, dict(kind="resblock", shift=shift, emb_channels=E, **kw), y=y)
+    for name, C, heads, new in [("attn_legacy_h1", 64, 1, False), ("attn_legacy_h4", 128, 4, False),
+                                ("attn_new_h1", 64, 1, True), ("attn_new_h4", 128, 4, True)]:
+        m = fill_module_(rm.AttentionBlock(C, heads, -1, new), seed=4).eval()
+        x = synth_normal((B, C, 8, 8), 14)
+        save("block_" + name, dict(kind="attention", channels=C, heads=heads, new_order=new), y=m(x))
+    t = torch.tensor([0, 1, 17, 999], dtype=torch.long)
+    save("timestep_embedding", dict(kind="temb"), t=t, e64=rm.timestep_embedding(t, 64), e33=rm.timestep_embedding(t, 33))
+
+
+def model_cases():
+    t = torch.tensor([3, 977], dtype=torch.long)
+    for name, cfg, size in [("unet_tiny", TINY_UNET, 16), ("unet_new_order", TINY_UNET_NEW, 16),
+                            ("unet_headch_sigma", TINY_UNET_HC, 16)]:
+        m = fill_module_(UNet(**cfg), seed=5).eval()
+        x = synth_normal((2, cfg["input_channel"], size, size), 15)
+        save("model_" + name, dict(kind="unet", cfg=cfg, size=size), t=t, y=m(x, t))
+    m = fill_module_(UNet(**TINY_UNET_CLS), seed=5).eval()
+    x = synth_normal((2, 1, 32, 32), 15)
+    cond = torch.tensor([1, 7], dtype=torch.long)
+    save("model_unet_class", dict(kind="unet", cfg=TINY_UNET_CLS, size=32), t=t, cond=cond, y=m(x, t, cond))
+    for name, cfg, size in [("shiftunet_tiny", TINY_SHIFT, 16), ("shiftunet_b64", TINY_SHIFT2, 16)]:
+        m = fill_module_(ShiftUNet(**cfg), seed=6).eval()
+        x = synth_normal((2, 3, size, size), 16)
+        z = synth_normal((2, cfg["latent_dim"]), 17)
+        eps, grad = m(x, t, z)
+        save("model_" + name, dict(kind="shiftunet", cfg=cfg, size=size), t=t, eps=eps, grad=grad)
+    for name, cls, size in [("encoder_celeba64", CELEBA64Encoder, 64), ("encoder_ffhq128", FFHQEncoder, 128)]:
+        m = fill_module_(cls(latent_dim=512), seed=7).eval()
+        save("model_" + name, dict(kind="encoder", size=size), z=m(synth_images(2, 3, size, 18)))
+    m = fill_module_(MLPSkipNet(**TINY_MLP), seed=8).eval()
+    save("model_mlp_skip", dict(kind="mlp", cfg=TINY_MLP), t=t, y=m(synth_normal((2, 64), 19), t))
+
+
+def diffusion_cases():
+    for bt in ("linear", "cosine"):
+        gd = GaussianDiffusion({"timesteps": 1000, "betas_type": bt}, "cpu")
+        tabs = {k: v for k, v in vars(gd).items() if isinstance(v, torch.Tensor)}
+        save("diffusion_tables_" + bt, dict(kind="tables", betas_type=bt), **tabs)
+    gd = GaussianDiffusion(DIFF, "cpu")
+    arrs = {}
+    for style in ("ddim10", "ddim100", "ddim200", "ddim500", "ddim1000"):
+        nb, tmap = gd.get_ddim_betas_and_timestep_map(style, gd.alphas_cumprod.cpu().numpy())
+        arrs[style + "_betas"] = nb
+        arrs[style + "_map"] = tmap
+        if style in ("ddim10", "ddim100"):
+            d = DDIM(nb, tmap, "cpu")
+            for k, v in vars(d).items():
+                if isinstance(v, torch.Tensor) and k != "timestep_map":
+                    arrs[f"{style}_{k}"] = v
+    save("diffusion_ddim_maps", dict(kind="ddim_maps"), **arrs)
+
+    # elementwise steps
+    x0 = synth_images(4, 3, 8, 21)
+    noise = synth_normal((4, 3, 8, 8), 22)
+    t = torch.tensor([0, 1, 500, 999], dtype=torch.long)
+    torch.manual_seed(1234)
+    eps = synth_normal((4, 3, 8, 8), 23)
+    ps = gd.noise_p_sample(x0, t, eps)          # draws torch.randn(shape) internally
+    torch.manual_seed(1234)
+    ps_noise = torch.randn(x0.shape)
+    lr = synth_normal((4, 3, 8, 8), 24).clamp(-1, 1)
+    torch.manual_seed(1234)
+    ps_lr = gd.noise_p_sample(x0, t, eps, lr)
+    save("diffusion_steps", dict(kind="steps"), t=t, q=gd.q_sample(x0, t, noise), p_sample=ps, p_noise=ps_noise,
+         p_sample_lr=ps_lr)
+
+    # loops on tiny nets
+    unet = fill_module_(UNet(**TINY_UNET), seed=5).eval()
+    xT = synth_normal((2, 3, 16, 16), 25)
+    x0 = synth_images(2, 3, 16, 26)
+    save("loop_unet_ddim10", dict(kind="loop_unet", cfg=TINY_UNET, size=16),
+         sample=gd.ddim_sample("ddim10", unet, xT), encode=gd.ddim_encode("ddim10", unet, x0))
+    dec = fill_module_(ShiftUNet(**TINY_SHIFT), seed=6).eval()
+    z = synth_normal((2, 64), 27)
+    save("loop_shift_ddim10", dict(kind="loop_shift", cfg=TINY_SHIFT, size=16),
+         sample=gd.representation_learning_ddim_sample("ddim10", None, dec, None, xT, z),
+         sample_stop30=gd.representation_learning_ddim_sample("ddim10", None, dec, None, xT, z, stop_percent=0.3),
+         encode=gd.representation_learning_ddim_encode("ddim10", None, dec, x0, z))
+
+    # full autoencoding with a real encoder (64 px) -- the benchmark workload in miniature
+    cfg = dict(TINY_SHIFT, latent_dim=512)
+    dec = fill_module_(ShiftUNet(**cfg), seed=6).eval()
+    enc = fill_module_(CELEBA64Encoder(latent_dim=512), seed=7).eval()
+    x0 = synth_images(2, 3, 64, 28)
+    save("loop_autoencode_ddim10", dict(kind="autoencode", cfg=cfg, size=64),
+         recon=gd.representation_learning_autoencoding("ddim10", "ddim10", enc, dec, x0))
+
+    # latent sampling loop
+    mlp = fill_module_(MLPSkipNet(**TINY_MLP), seed=8).eval()
+    lat = gd.latent_diffusion_config["alphas_cumprod"]
+    nb, tmap = gd.get_ddim_betas_and_timestep_map("ddim10", lat.cpu().numpy())
+    zT = synth_normal((2, 64), 29).clamp(-1, 1)
+    save("loop_latent_ddim10", dict(kind="latent_loop", cfg=TINY_MLP), z=DDIM(nb, tmap, "cpu").latent_ddim_sample_loop(mlp, zT))
+
+
+def training_cases():
+    torch.set_grad_enabled(True)
+    gd = GaussianDiffusion(DIFF, "cpu")
+    cfg = dict(TINY_SHIFT, latent_dim=512)
+    dec = fill_module_(ShiftUNet(**cfg), seed=6)
+    enc = fill_module_(CELEBA64Encoder(latent_dim=512), seed=7)
+    x0 = synth_images(2, 3, 64, 31)
+    torch.manual_seed(777)
+    loss = gd.representation_learning_train_one_batch(enc, dec, x0)["prediction_loss"]
+    loss.backward()
+    torch.manual_seed(777)
+    t = torch.randint(0, 1000, (2,), dtype=torch.long)
+    noise = torch.randn_like(x0)
+    grads = {"g_" + k.replace(".", "_"): p.grad for k, p in list(dec.named_parameters()) + [("enc." + k, p) for k, p in enc.named_parameters()]
+             if p.grad is not None and k.endswith(("label_emb.weight", "shift_out.2.weight", "shift_middle_block.0.in_layers.2.weight",
+                                                    "shift_output_blocks.0.0.emb_z_layers.1.weight", "encoder.0.weight", "encoder.14.weight"))}
+    n_grad = sum(1 for p in list(dec.parameters()) + list(enc.parameters()) if p.grad is not None)
+    save("train_representation_learning", dict(kind="train_rl", cfg=cfg, size=64, n_params_with_grad=n_grad),
+         t=t, noise=noise, loss=loss.detach(),
+         **{k: v.detach().flatten()[:512] for k, v in grads.items()},
+         **{"n" + k: v.detach().double().norm().float() for k, v in grads.items()})
+    unet = fill_module_(UNet(**TINY_UNET), seed=5)
+    x0 = synth_images(2, 3, 16, 32)
+    torch.manual_seed(778)
+    loss = gd.regular_train_one_batch(unet, x0)["prediction_loss"]
+    torch.manual_seed(778)
+    t = torch.randint(0, 1000, (2,), dtype=torch.long)
+    noise = torch.randn_like(x0)
+    save("train_regular", dict(kind="train_regular", cfg=TINY_UNET, size=16), t=t, noise=noise, loss=loss.detach())
+    torch.set_grad_enabled(False)
+
+
+if __name__ == "__main__":
+    block_cases()
+    model_cases()
+    diffusion_cases()
+    training_cases()
