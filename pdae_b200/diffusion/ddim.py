@@ -1,0 +1,154 @@
+"""Respaced deterministic DDIM (reference surface: diffusion/ddim.py:7-207) on native kernels.
+
+Same constructor (``DDIM(betas, timestep_map, device)``) and method names.  The per-step arithmetic
+(23 ATen launches in the reference) is ONE fused kernel, ``pdae_ddim_step``; when the network is a
+pdae_b200 ShiftUNet/UNet the loop drives the network's static plan buffers directly (no per-step
+allocation, no host sync, no tqdm).
+"""
+from __future__ import annotations
+
+import ctypes
+from functools import partial
+
+import numpy as np
+import torch
+
+from .. import _native
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+class DDIM:
+    def __init__(self, betas, timestep_map, device):
+        self.device = device
+        self.timestep_map = timestep_map.to(self.device)
+        self.timesteps = betas.shape[0] - 1
+        # fp64 schedule algebra on the host, fp32 tables on the device -- exactly ddim.py:15-33
+        acp = np.cumprod(1.0 - betas, axis=0)
+        f32 = partial(torch.tensor, dtype=torch.float32, device=self.device)
+        self.alphas_cumprod_prev = f32(np.append(1.0, acp[:-1]))
+        self.alphas_cumprod_next = f32(np.append(acp[1:], 0.0))
+        self.sqrt_one_minus_alphas_cumprod = f32(np.sqrt(1.0 - acp))
+        self.sqrt_recip_alphas_cumprod = f32(np.sqrt(1.0 / acp))
+        self.sqrt_recip_alphas_cumprod_m1 = f32(np.sqrt(1.0 / acp - 1.0))
+
+    @staticmethod
+    def extract_coef_at_t(schedule, t, x_shape):
+        return torch.gather(schedule, -1, t).reshape([x_shape[0]] + [1] * (len(x_shape) - 1))
+
+    def t_transform(self, t):
+        return self.timestep_map[t]
+
+    # ---- the fused update ---------------------------------------------------------------------------
+    def _update(self, x_t, t, eps, grad, direction, out=None):
+        if not x_t.is_cuda:
+            raise _native.NativeError("DDIM: CUDA tensors required (no CPU fallback)")
+        x_t, eps = x_t.contiguous(), eps.contiguous()
+        grad = grad.contiguous() if grad is not None else None
+        t = t.to(torch.int64).contiguous()
+        out = torch.empty_like(x_t) if out is None else out
+        B = x_t.shape[0]
+        tab = self.alphas_cumprod_prev if direction == "sample" else self.alphas_cumprod_next
+        rc = _native.lib().pdae_ddim_step(_ptr(x_t), _ptr(eps), _ptr(grad), _ptr(t), _ptr(self.sqrt_recip_alphas_cumprod),
+                                          _ptr(self.sqrt_recip_alphas_cumprod_m1), _ptr(self.sqrt_one_minus_alphas_cumprod),
+                                          _ptr(tab), _ptr(out), B, x_t.numel() // B, _stream(x_t.device))
+        _native.check(rc, "pdae_ddim_step")
+        return out
+
+    # ---- single steps (ddim.py:43-55, 66-79, 91-107, 123-138) -----------------------------------------
+    def ddim_sample(self, denoise_fn, x_t, t, condition=None):
+        return self._update(x_t, t, denoise_fn(x_t, self.t_transform(t), condition), None, "sample")
+
+    def ddim_encode(self, denoise_fn, x_t, t, condition=None):
+        return self._update(x_t, t, denoise_fn(x_t, self.t_transform(t), condition), None, "encode")
+
+    def shift_ddim_sample(self, decoder, z, x_t, t, use_shift=True):
+        eps, grad = decoder(x_t, self.t_transform(t), z)
+        return self._update(x_t, t, eps, grad if use_shift else None, "sample")
+
+    def shift_ddim_encode(self, decoder, z, x_t, t):
+        eps, grad = decoder(x_t, self.t_transform(t), z)
+        return self._update(x_t, t, eps, grad, "encode")
+
+    # ---- loops (ddim.py:57-64, 81-88, 110-120, 140-147) -----------------------------------------------
+    def _steps(self, direction):
+        return reversed(range(1, self.timesteps + 1)) if direction == "sample" else range(0, self.timesteps)
+
+    def _loop(self, net, x, cond, direction, shift, stop_step=0):
+        from ..model.shift_unet import ShiftUNet
+        from ..model.unet import UNet
+        B = x.shape[0]
+        fast = isinstance(net, (ShiftUNet, UNet)) and x.is_cuda and x.dim() == 4 and not torch.is_grad_enabled()
+        ts = torch.arange(0, self.timesteps + 1, device=self.device, dtype=torch.int64)
+        if not fast:
+            img = x
+            for i in self._steps(direction):
+                t = ts[i].expand(B).contiguous()
+                if shift:
+                    eps, grad = net(img, self.t_transform(t), cond)
+                    img = self._update(img, t, eps, grad if (direction == "encode" or (i - 1) >= stop_step) else None,
+                                       direction)
+                else:
+                    img = self._update(img, t, net(img, self.t_transform(t), cond), None, direction)
+            return img
+        # fast path: drive the network's static plan buffers in place
+        H, W = x.shape[2], x.shape[3]
+        if isinstance(net, ShiftUNet):
+            plan, (x_in, t_in, z_in, eps, grad) = net.plan_for(B, H, W)
+            z_in.tensor.copy_(cond)
+        else:
+            plan, (x_in, t_in, c_in, eps) = net._get_plan(("unet", B, H, W), lambda P: net._build(P, B, H, W))
+            grad = None
+            if c_in is not None:
+                c_in.tensor.copy_(cond)
+        x_in.tensor.copy_(x)
+        t_loc = torch.empty(B, device=self.device, dtype=torch.int64)
+        eps_t = eps.tensor
+        C = x.shape[1]
+        eps_used = eps_t if eps_t.shape[1] == C else None
+        for i in self._steps(direction):
+            t_loc.fill_(i)
+            torch.index_select(self.timestep_map, 0, t_loc, out=t_in.tensor)
+            plan.run()
+            e = eps_used if eps_used is not None else eps_t[:, :C].contiguous()
+            g = grad.tensor if (shift and (direction == "encode" or (i - 1) >= stop_step)) else None
+            self._update(x_in.tensor, t_loc, e, g, direction, out=x_in.tensor)
+        return x_in.tensor.clone()
+
+    def ddim_sample_loop(self, denoise_fn, x_T, condition=None):
+        return self._loop(denoise_fn, x_T, condition, "sample", shift=False)
+
+    def ddim_encode_loop(self, denoise_fn, x_0, condition=None):
+        return self._loop(denoise_fn, x_0, condition, "encode", shift=False)
+
+    def shift_ddim_sample_loop(self, decoder, z, x_T, stop_percent=0.0):
+        return self._loop(decoder, x_T, z, "sample", shift=True, stop_step=int(stop_percent * self.timesteps))
+
+    def shift_ddim_encode_loop(self, decoder, z, x_0):
+        return self._loop(decoder, x_0, z, "encode", shift=True)
+
+    def shift_ddim_trajectory_interpolation(self, decoder, z_1, z_2, x_T, alpha):
+        """ddim.py:149-174: two decoder calls per step, gradient = (1-alpha) g1 + alpha g2, epsilon from the first."""
+        B = x_T.shape[0]
+        x_t = x_T
+        for i in reversed(range(1, self.timesteps + 1)):
+            t = torch.full((B,), i, device=self.device, dtype=torch.long)
+            eps, g1 = decoder(x_t, self.t_transform(t), z_1)
+            _, g2 = decoder(x_t, self.t_transform(t), z_2)
+            x_t = self._update(x_t, t, eps, (1.0 - alpha) * g1 + alpha * g2, "sample")
+        return x_t
+
+    def latent_ddim_sample_loop(self, latent_denoise_fn, z_T):
+        """ddim.py:200-207 -- NB calls ddim_sample, i.e. WITH the clamp of the predicted z_0."""
+        B = z_T.shape[0]
+        z = z_T
+        for i in reversed(range(1, self.timesteps + 1)):
+            t = torch.full((B,), i, device=self.device, dtype=torch.long)
+            z = self.ddim_sample(latent_denoise_fn, z, t)
+        return z

@@ -1,0 +1,343 @@
+"""Static launch plans over the C-ABI kernels.
+
+A ``Plan`` is recorded once per (module, input shape, precision): a flat list of native calls on
+pre-assigned device buffers (liveness-based reuse of one arena), so a forward pass is a tight loop of
+ctypes calls on the current CUDA stream -- no allocation, no host sync, legal under CUDA-graph capture.
+PyTorch is used here only for device memory and streams.
+
+Precision modes
+  * ``fp32``: every contraction on CUDA cores in fp32 (pdae_conv2d_simt / pdae_attention_simt).  This is
+    the mode that holds rtol 1e-3 / atol 1e-4 against the CPU oracle.
+  * ``bf16``: convolutions whose shape allows it run on the tcgen05 tensor-core kernel with bf16 operands
+    and fp32 accumulation (pdae_conv_tc_*); the residual stream, GroupNorm statistics, embeddings and
+    the DDIM update stay fp32.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _native
+from ._native import PDAE_BF16, PDAE_F32, RESAMPLE_DOWN2, RESAMPLE_NONE, RESAMPLE_UP2
+
+_DT = {torch.float32: PDAE_F32, torch.bfloat16: PDAE_BF16}
+_STREAM = object()  # placeholder replaced by the current stream at run time
+
+_default_precision = "bf16"
+
+
+def set_default_precision(p: str) -> None:
+    global _default_precision
+    if p not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    _default_precision = p
+
+
+def get_default_precision() -> str:
+    return _default_precision
+
+
+class Buf:
+    """A device buffer known to a plan: either plan-owned (arena) or fixed (parameter / caller tensor)."""
+    __slots__ = ("shape", "dtype", "tensor", "first", "last", "fixed", "keep", "name", "_block")
+
+    def __init__(self, shape, dtype, tensor=None, name=""):
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = dtype
+        self.tensor = tensor
+        self.fixed = tensor is not None
+        self.first = None
+        self.last = None
+        self.keep = False
+        self.name = name
+
+    @property
+    def nbytes(self) -> int:
+        n = torch.empty((), dtype=self.dtype).element_size()
+        for s in self.shape:
+            n *= s
+        return n
+
+    def at(self, elem_offset: int) -> "BufView":
+        return BufView(self, elem_offset)
+
+
+class BufView:
+    __slots__ = ("buf", "off")
+
+    def __init__(self, buf: Buf, off: int):
+        self.buf, self.off = buf, int(off)
+
+
+class Packed:
+    """A derived (re-laid-out / converted) copy of parameters, refreshed when a source changes."""
+
+    def __init__(self, sources: Sequence[torch.Tensor], fn: Callable[[], torch.Tensor]):
+        self.sources = list(sources)
+        self.fn = fn
+        self.tensor = fn().contiguous()
+        self.stamp = self._stamp()
+
+    def _stamp(self):
+        return tuple((s.data_ptr(), s._version) for s in self.sources)
+
+    def refresh(self) -> None:
+        st = self._stamp()
+        if st != self.stamp:
+            with torch.inference_mode(False), torch.no_grad():
+                self.tensor.copy_(self.fn())
+            self.stamp = st
+
+
+class Plan:
+    def __init__(self, device: torch.device, precision: Optional[str] = None):
+        _native.require_device()
+        self.device = device
+        self.precision = precision or _default_precision
+        self.tc = self.precision == "bf16"
+        self.L = _native.lib()
+        self.ops: List[Tuple[str, list]] = []
+        self.bufs: List[Buf] = []
+        self.packed: List[Packed] = []
+        self.params: List[Tuple[torch.Tensor, int]] = []
+        self._pack_cache: Dict[tuple, Buf] = {}
+        self._compiled = None
+        self._tc_handles: List[ctypes.c_void_p] = []
+        self.n_launch = 0
+        self.flops: List[float] = []  # algorithmic FLOPs (2*MACs) per recorded op, 0 for non-contraction ops
+
+    # ---- buffers ----------------------------------------------------------------------------
+    def new(self, shape, dtype=torch.float32, name="") -> Buf:
+        b = Buf(shape, dtype, None, name)
+        self.bufs.append(b)
+        return b
+
+    def fixed(self, t: torch.Tensor) -> Buf:
+        assert t.is_cuda and t.is_contiguous(), "plan tensors must be contiguous CUDA tensors"
+        return Buf(t.shape, t.dtype, t)
+
+    def param(self, p: Optional[torch.Tensor]) -> Optional[Buf]:
+        """A parameter consumed in place (fp32, contiguous); tracked so a moved parameter invalidates the plan."""
+        if p is None:
+            return None
+        if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+            raise _native.NativeError("pdae_b200 modules need contiguous fp32 CUDA parameters (no CPU fallback)")
+        self.params.append((p, p.data_ptr()))
+        return Buf(p.shape, p.dtype, p.detach())
+
+    def pack(self, key: tuple, sources: Sequence[torch.Tensor], fn: Callable[[], torch.Tensor]) -> Buf:
+        if key in self._pack_cache:
+            return self._pack_cache[key]
+        for s in sources:
+            if not s.is_cuda:
+                raise _native.NativeError("pdae_b200 modules need CUDA parameters (no CPU fallback)")
+        with torch.inference_mode(False), torch.no_grad():  # never create inference tensors: plans outlive the caller's mode
+            pk = Packed([s for s in sources], fn)
+        self.packed.append(pk)
+        b = Buf(pk.tensor.shape, pk.tensor.dtype, pk.tensor)
+        self._pack_cache[key] = b
+        return b
+
+    # ---- recording --------------------------------------------------------------------------
+    def call(self, fn: str, *args, flops: float = 0.0) -> None:
+        idx = len(self.ops)
+        self.flops.append(float(flops))
+        for a in args:
+            b = a.buf if isinstance(a, BufView) else a
+            if isinstance(b, Buf) and not b.fixed:
+                if b.first is None:
+                    b.first = idx
+                b.last = idx
+        self.ops.append((fn, list(args)))
+
+    # ---- finalisation -----------------------------------------------------------------------
+    def finalize(self) -> "Plan":
+        with torch.inference_mode(False):
+            return self._finalize()
+
+    def _finalize(self) -> "Plan":
+        starts: Dict[int, List[Buf]] = {}
+        ends: Dict[int, List[Buf]] = {}
+        for b in self.bufs:
+            if b.first is None:
+                continue
+            starts.setdefault(b.first, []).append(b)
+            if not b.keep:
+                ends.setdefault(b.last, []).append(b)
+        free: List[torch.Tensor] = []
+        self.arena_bytes = 0
+        for i in range(len(self.ops)):
+            for b in starts.get(i, []):
+                need = max(b.nbytes, 16)
+                best = None
+                for j, blk in enumerate(free):
+                    if blk.numel() >= need and (best is None or blk.numel() < free[best].numel()):
+                        best = j
+                if best is not None and free[best].numel() <= 2 * need + 4096:
+                    blk = free.pop(best)
+                else:
+                    blk = torch.empty(need, dtype=torch.uint8, device=self.device)
+                    self.arena_bytes += need
+                b.tensor = blk[: b.nbytes].view(b.dtype).view(b.shape)
+                b._block = blk  # type: ignore[attr-defined]
+            for b in ends.get(i, []):
+                free.append(b._block)  # type: ignore[attr-defined]
+        compiled = []
+        for fn, args in self.ops:
+            if fn == "conv_tc":
+                compiled.append(self._compile_tc(args))
+                continue
+            cargs = []
+            sidx = -1
+            for k, a in enumerate(args):
+                if a is _STREAM:
+                    sidx = k
+                    cargs.append(None)
+                else:
+                    cargs.append(self._resolve(a))
+            compiled.append((getattr(self.L, "pdae_" + fn), cargs, sidx, fn))
+        self._compiled = compiled
+        self.n_launch = sum(_LAUNCHES.get(fn, 1) for fn, _ in self.ops)
+        return self
+
+    @staticmethod
+    def _resolve(a):
+        if isinstance(a, Buf):
+            return ctypes.c_void_p(a.tensor.data_ptr())
+        if isinstance(a, BufView):
+            return ctypes.c_void_p(a.buf.tensor.data_ptr() + a.off * a.buf.tensor.element_size())
+        return a
+
+    def _compile_tc(self, args):
+        x, w, bias, resid, out, B, H, W, Cin, Cout, k = args
+        h = ctypes.c_void_p()
+        rc = self.L.pdae_conv_tc_create(ctypes.byref(h), self._resolve(x), self._resolve(w), self._resolve(bias),
+                                        self._resolve(resid), self._resolve(out), B, H, W, Cin, Cout, k)
+        _native.check(rc, "pdae_conv_tc_create")
+        self._tc_handles.append(h)
+        return (self.L.pdae_conv_tc_run, [h, None], 1, "conv_tc")
+
+    def __del__(self):
+        try:
+            for h in self._tc_handles:
+                self.L.pdae_conv_tc_destroy(h)
+        except Exception:
+            pass
+
+    # ---- execution --------------------------------------------------------------------------
+    def stale(self) -> bool:
+        return any(p.data_ptr() != ptr for p, ptr in self.params)
+
+    def run(self) -> None:
+        for pk in self.packed:
+            pk.refresh()
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        for cfn, cargs, sidx, name in self._compiled:
+            cargs[sidx] = stream
+            rc = cfn(*cargs)
+            if rc != 0:
+                _native.check(rc, "pdae_" + name)
+
+    def profile(self, reps: int = 3) -> Dict[str, Dict[str, float]]:
+        """Per-kernel-kind device time (CUDA events on the launching stream) and algorithmic FLOPs of one replay.
+        Measurement aid for bench.py / profiles; not used on the product path."""
+        for pk in self.packed:
+            pk.refresh()
+        st = torch.cuda.current_stream(self.device)
+        stream = ctypes.c_void_p(st.cuda_stream)
+        n = len(self._compiled)
+        acc = [0.0] * n
+        for _ in range(reps):
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+            evs[0].record(st)
+            for i, (cfn, cargs, sidx, name) in enumerate(self._compiled):
+                cargs[sidx] = stream
+                _native.check(cfn(*cargs), "pdae_" + name)
+                evs[i + 1].record(st)
+            st.synchronize()
+            for i in range(n):
+                acc[i] += evs[i].elapsed_time(evs[i + 1]) / reps
+        out: Dict[str, Dict[str, float]] = {}
+        for i, (_, _, _, name) in enumerate(self._compiled):
+            d = out.setdefault(name, {"ms": 0.0, "flops": 0.0, "launches": 0})
+            d["ms"] += acc[i]
+            d["flops"] += self.flops[i]
+            d["launches"] += 1
+        return out
+
+    # ---- emitters: thin typed wrappers that pick kernels ------------------------------------------
+    def use_tc(self, Cin: int, Cout: int, k: int, stride: int, H: int, W: int) -> bool:
+        if not self.tc or stride != 1 or k not in (1, 3) or Cin % 64 or Cout % 64:
+            return False
+        tw = 1
+        while tw * 2 <= 128 and W % (tw * 2) == 0:
+            tw *= 2
+        th = 1
+        while th * 2 <= 128 // tw and H % (th * 2) == 0:
+            th *= 2
+        return W % tw == 0 and H % th == 0 and 128 % (tw * th) == 0
+
+    def conv(self, x: Buf, weight: torch.Tensor, bias: Optional[torch.Tensor], out: Buf, *, B, H, W, Cin, Cout, k=3,
+             stride=1, pad=None, residual: Optional[Buf] = None, in_nchw=False, out_nchw=False, a_silu=False,
+             wkey=None) -> None:
+        """weight: nn-style [Cout, Cin, k, k] / [Cout, Cin, 1] / [Cout, Cin] parameter."""
+        pad = k // 2 if pad is None else pad
+        bias_b = self.param(bias)
+        wkey = wkey or id(weight)
+        if x.dtype == torch.bfloat16 and self.use_tc(Cin, Cout, k, stride, H, W) and not (in_nchw or out_nchw or a_silu):
+            wp = self.pack((wkey, "tc"), [weight],
+                           lambda: weight.detach().reshape(Cout, Cin, k * k).permute(2, 0, 1).to(torch.bfloat16))
+            self.call("conv_tc", x, wp, bias_b, residual, out, B, H, W, Cin, Cout, k, flops=2.0 * B * H * W * Cout * Cin * k * k)
+            return
+        wp = self.pack((wkey, "simt"), [weight], lambda: weight.detach().reshape(Cout, Cin, k * k).permute(2, 1, 0).float())
+        Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        self.call("conv2d_simt", x, _DT[x.dtype], int(in_nchw), wp, bias_b, residual, out, int(out_nchw), B, H, W, Cin, Cout,
+                  k, stride, pad, int(a_silu), _STREAM, flops=2.0 * B * Ho * Wo * Cout * Cin * k * k)
+
+    def linear(self, x: Buf, weight: torch.Tensor, bias: Optional[torch.Tensor], out: Buf, *, B, Cin, Cout, a_silu=False,
+               wkey=None) -> None:
+        self.conv(x, weight, bias, out, B=B, H=1, W=1, Cin=Cin, Cout=Cout, k=1, a_silu=a_silu, wkey=wkey)
+
+    def linear_packed(self, x: Buf, wp: Buf, bias: Optional[Buf], out: Buf, *, B, Cin, Cout, a_silu=False) -> None:
+        """Linear with an already packed fp32 [Cin][Cout] weight (e.g. all blocks' emb layers concatenated)."""
+        self.call("conv2d_simt", x, PDAE_F32, 0, wp, bias, None, out, 0, B, 1, 1, Cin, Cout, 1, 1, 0, int(a_silu), _STREAM,
+                  flops=2.0 * B * Cin * Cout)
+
+    def head_conv(self, x: Buf, weight: torch.Tensor, bias: torch.Tensor, out_nchw: Buf, *, B, H, W, Cin, Cout) -> None:
+        """3x3 conv to a few image channels (unet.py:171-175): bandwidth kernel for Cout <= 4."""
+        if Cout <= 4 and Cin % 4 == 0:
+            def pack4():
+                w = weight.detach().reshape(Cout, Cin, 9).permute(2, 1, 0).float()
+                z = torch.zeros(9, Cin, 4, device=w.device, dtype=torch.float32)
+                z[:, :, :Cout] = w
+                return z
+            wp = self.pack((id(weight), "small4"), [weight], pack4)
+            self.call("conv3x3_smalln", x, _DT[x.dtype], wp, self.param(bias), out_nchw, B, H, W, Cin, Cout, _STREAM,
+                      flops=2.0 * B * H * W * Cout * Cin * 9)
+        else:
+            self.conv(x, weight, bias, out_nchw, B=B, H=H, W=W, Cin=Cin, Cout=Cout, k=3, out_nchw=True)
+
+    def gn_coef(self, src1: Buf, C1: int, src2: Optional[Buf], C2: int, gamma, beta, *, B, HW, emb=None, emb_ld=0,
+                embz=None, embz_ld=0) -> Buf:
+        C = C1 + C2
+        sums = self.new((B, 32, 2), torch.float64, "gn_sums")
+        self.call("gn_stats", src1, C1, src2, C2, B, HW, sums, _STREAM)
+        ab = self.new((B, 2, C), torch.float32, "gn_ab")
+        self.call("gn_coef", sums, self.param(gamma), self.param(beta), B, C, HW, ctypes.c_float(1e-5), emb, emb_ld, embz,
+                  embz_ld, ab, _STREAM)
+        return ab
+
+    def gn_apply(self, src1: Buf, C1: int, src2: Optional[Buf], C2: int, ab: Optional[Buf], *, silu: bool, resample: int,
+                 B, H, W, act_dtype, raw_dtype=None) -> Tuple[Buf, Optional[Buf]]:
+        C = C1 + C2
+        Ho, Wo = (2 * H, 2 * W) if resample == RESAMPLE_UP2 else ((H // 2, W // 2) if resample == RESAMPLE_DOWN2 else (H, W))
+        act = self.new((B, Ho, Wo, C), act_dtype, "act")
+        raw = self.new((B, Ho, Wo, C), raw_dtype, "raw") if raw_dtype is not None else None
+        self.call("gn_apply", src1, C1, src2, C2, ab, int(silu), resample, B, H, W, act, _DT[act_dtype], raw,
+                  _DT[raw_dtype] if raw_dtype is not None else PDAE_F32, _STREAM)
+        return act, raw
+
+
+_LAUNCHES = {"gn_stats": 1, "attention_simt": 3}

@@ -1,0 +1,431 @@
+"""Building blocks with the reference's parameter names, executed by the native kernels.
+
+Same class names, constructor arguments, attribute names and ``state_dict`` keys as the reference's
+``model/module.py`` (ResBlock :205-297, ResBlockShift :299-384, AttentionBlock :387-428, Upsample/Downsample
+:143-202, TimestepSequential :131-140, timestep_embedding :66-84) -- but the modules here only *hold*
+parameters; ``forward`` records/replays a launch plan over libpdae_b200 (pdae_b200.engine).  There is no
+PyTorch-op fallback: a forward on a CPU tensor, or without the built library, raises.
+
+Layout: parameters stay nn-style fp32 (NCHW conv weights) so checkpoints, DDP, Adam and EMA code written
+against the reference keep working; activations inside a plan are NHWC.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import _native
+from ..engine import Buf, Plan, RESAMPLE_DOWN2, RESAMPLE_NONE, RESAMPLE_UP2, _STREAM, get_default_precision
+
+
+# --------------------------------------------------------------------------------------------------
+# parameter holders
+# --------------------------------------------------------------------------------------------------
+class Slots(nn.Module):
+    """Children registered under explicit integer names -- reproduces the key numbering of the reference's
+    nn.Sequential containers (whose parameter-free members such as SiLU/Dropout leave gaps)."""
+
+    def __init__(self, members: Dict[int, nn.Module]):
+        super().__init__()
+        for i, m in members.items():
+            self.add_module(str(i), m)
+
+    def __getitem__(self, i: int) -> nn.Module:
+        return self._modules[str(i)]
+
+    def __iter__(self):
+        return iter(self._modules.values())
+
+    def __len__(self):
+        return len(self._modules)
+
+
+def conv_nd(dims, *args, **kwargs):
+    if dims == 1:
+        return nn.Conv1d(*args, **kwargs)
+    if dims == 2:
+        return nn.Conv2d(*args, **kwargs)
+    raise ValueError(f"pdae_b200 supports dims in (1, 2), got {dims}")
+
+
+def linear(*args, **kwargs):
+    return nn.Linear(*args, **kwargs)
+
+
+def normalization(channels):
+    """GroupNorm(32, C) parameters (model/module.py:56-63)."""
+    return nn.GroupNorm(32, channels)
+
+
+def zero_module(module):
+    for p in module.parameters():
+        p.detach().zero_()
+    return module
+
+
+class View(nn.Module):
+    def __init__(self, size):
+        super().__init__()
+        self.size = size
+
+
+_FREQ_CACHE: Dict[Tuple[int, str], torch.Tensor] = {}
+
+
+def timestep_freqs(dim: int, device, max_period: int = 10000) -> torch.Tensor:
+    """exp(-ln(max_period) * i / half), evaluated on the host with the reference's fp32 op order
+    (model/module.py:75-79) and cached on the device."""
+    key = (dim, str(device), max_period)
+    if key not in _FREQ_CACHE:
+        half = dim // 2
+        f = torch.exp(-math.log(max_period) * torch.arange(start=0, end=half, dtype=torch.float32) / half)
+        _FREQ_CACHE[key] = f.to(device)
+    return _FREQ_CACHE[key]
+
+
+def timestep_embedding(timesteps: torch.Tensor, dim: int, max_period: int = 10000) -> torch.Tensor:
+    """Sinusoidal embedding [N, dim] (cos | sin | zero pad) computed by pdae_timestep_embedding."""
+    if not timesteps.is_cuda:
+        raise _native.NativeError("timestep_embedding: CUDA tensor required (no CPU fallback)")
+    t = timesteps.to(torch.int64).contiguous()
+    out = torch.empty(t.shape[0], dim, device=t.device, dtype=torch.float32)
+    L = _native.lib()
+    import ctypes
+    rc = L.pdae_timestep_embedding(ctypes.c_void_p(t.data_ptr()), t.shape[0], dim,
+                                   ctypes.c_void_p(timestep_freqs(dim, t.device, max_period).data_ptr()),
+                                   ctypes.c_void_p(out.data_ptr()),
+                                   ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream))
+    _native.check(rc, "pdae_timestep_embedding")
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# plan plumbing shared by every module
+# --------------------------------------------------------------------------------------------------
+class Src:
+    """An NHWC fp32 activation, possibly the virtual channel-concat of two tensors (skip connections are
+    never materialised: unet.py:199-200 / shift_unet.py:276-281 ``torch.cat([h, hs.pop()], 1)``)."""
+    __slots__ = ("b1", "C1", "b2", "C2", "B", "H", "W")
+
+    def __init__(self, b1: Buf, C1: int, B: int, H: int, W: int, b2: Optional[Buf] = None, C2: int = 0):
+        self.b1, self.C1, self.b2, self.C2, self.B, self.H, self.W = b1, C1, b2, C2, B, H, W
+
+    @property
+    def C(self) -> int:
+        return self.C1 + self.C2
+
+    def cat(self, other: "Src") -> "Src":
+        assert self.b2 is None and other.b2 is None and (self.B, self.H, self.W) == (other.B, other.H, other.W)
+        return Src(self.b1, self.C1, self.B, self.H, self.W, other.b1, other.C1)
+
+
+class PlannedModule(nn.Module):
+    """Caches one plan per (input signature, precision, train flag); re-records if parameters moved."""
+
+    precision: Optional[str] = None  # None -> engine default
+
+    def _plans(self) -> dict:
+        d = self.__dict__.get("_plan_cache")
+        if d is None:
+            d = {}
+            self.__dict__["_plan_cache"] = d
+        return d
+
+    def _get_plan(self, key, builder):
+        prec = self.precision or get_default_precision()
+        key = (key, prec)
+        plans = self._plans()
+        ent = plans.get(key)
+        if ent is None or ent[0].stale():
+            plan = Plan(self._device(), prec)
+            io = builder(plan)
+            plan.finalize()
+            ent = (plan, io)
+            plans[key] = ent
+        return ent
+
+    def _device(self) -> torch.device:
+        p = next(self.parameters())
+        if not p.is_cuda:
+            raise _native.NativeError(f"{type(self).__name__}: parameters are on {p.device}; pdae_b200 runs on CUDA "
+                                      "(sm_100) only -- there is no CPU fallback")
+        return p.device
+
+    def __deepcopy__(self, memo):
+        # plans hold raw device pointers: never copy them (copy.deepcopy(decoder) is how the trainers make EMA nets)
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        import copy
+        for k, v in self.__dict__.items():
+            if k == "_plan_cache":
+                continue
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
+
+    def _check_no_grad(self, *tensors):
+        """Forward-only for now: refuse (loudly) to run where autograd would expect a graph."""
+        if not torch.is_grad_enabled():
+            return
+        if any(t is not None and t.requires_grad for t in tensors) or any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("pdae_b200: backward kernels are not built yet -- run under torch.no_grad() / "
+                                      "inference_mode() (forward/sampling path)")
+
+
+# --------------------------------------------------------------------------------------------------
+# blocks
+# --------------------------------------------------------------------------------------------------
+class TimestepBlock(nn.Module):
+    pass
+
+
+class TimestepContextBlock(nn.Module):
+    pass
+
+
+class Upsample(nn.Module):
+    """Parameter-free marker (the reference only ever builds it with use_conv=False, module.py:248-252)."""
+
+    def __init__(self, channels, use_conv, dims=2, out_channels=None):
+        super().__init__()
+        assert not use_conv, "pdae_b200: Upsample(use_conv=True) is never constructed by the reference models"
+        self.channels, self.out_channels, self.use_conv, self.dims = channels, out_channels or channels, use_conv, dims
+
+
+class Downsample(nn.Module):
+    def __init__(self, channels, use_conv, dims=2, out_channels=None):
+        super().__init__()
+        assert not use_conv, "pdae_b200: Downsample(use_conv=True) is never constructed by the reference models"
+        self.channels, self.out_channels, self.use_conv, self.dims = channels, out_channels or channels, use_conv, dims
+
+
+class _ResBase(PlannedModule):
+    has_z = False
+
+    def __init__(self, channels, emb_channels, dropout, out_channels=None, use_conv=False, dims=2, up=False, down=False):
+        super().__init__()
+        assert dims == 2, "only dims=2 is exercised by the reference configs"
+        self.channels = channels
+        self.emb_channels = emb_channels
+        self.dropout = dropout
+        self.out_channels = out_channels or channels
+        self.use_conv = use_conv
+        self.up, self.down = up, down
+        self.updown = up or down
+        co = self.out_channels
+        self.in_layers = Slots({0: normalization(channels), 2: conv_nd(dims, channels, co, 3, padding=1)})
+        if up:
+            self.h_upd, self.x_upd = Upsample(channels, False, dims), Upsample(channels, False, dims)
+        elif down:
+            self.h_upd, self.x_upd = Downsample(channels, False, dims), Downsample(channels, False, dims)
+        else:
+            self.h_upd = self.x_upd = nn.Identity()
+        self.emb_layers = Slots({1: linear(emb_channels, 2 * co)})
+        if self.has_z:
+            self.emb_z_layers = Slots({1: linear(emb_channels, 2 * co)})
+        self.out_layers = Slots({0: normalization(co), 3: zero_module(conv_nd(dims, co, co, 3, padding=1))})
+        if co == channels:
+            self.skip_connection = nn.Identity()
+        else:
+            self.skip_connection = conv_nd(dims, channels, co, 3 if use_conv else 1, padding=1 if use_conv else 0)
+
+    # ---- plan emission --------------------------------------------------------------------------
+    def emit(self, P: Plan, x: Src, emb: Tuple[Buf, int, int], embz: Optional[Tuple[Buf, int, int]] = None) -> Src:
+        """emb / embz = (buffer, element offset of this block's [scale|shift] row slice, leading dim)."""
+        if self.training and self.dropout > 0:
+            raise NotImplementedError("pdae_b200: dropout>0 in train mode needs the training kernels (not built yet)")
+        assert x.C == self.channels, f"expected {self.channels} channels, got {x.C}"
+        B, H, W, C, Co = x.B, x.H, x.W, x.C, self.out_channels
+        rs = RESAMPLE_UP2 if self.up else (RESAMPLE_DOWN2 if self.down else RESAMPLE_NONE)
+        H2, W2 = (2 * H, 2 * W) if self.up else ((H // 2, W // 2) if self.down else (H, W))
+        conv1, conv2 = self.in_layers[2], self.out_layers[3]
+        gn1, gn2 = self.in_layers[0], self.out_layers[0]
+        ident = isinstance(self.skip_connection, nn.Identity)
+
+        ab1 = P.gn_coef(x.b1, x.C1, x.b2, x.C2, gn1.weight, gn1.bias, B=B, HW=H * W)
+        tc1 = P.use_tc(C, Co, 3, 1, H2, W2)
+        # raw (un-normalised) copy of the possibly concatenated / resampled input for the skip path
+        raw_dtype = None
+        if ident:
+            if self.updown or x.b2 is not None:
+                raw_dtype = torch.float32
+        else:
+            ks = self.skip_connection.kernel_size[0]
+            tcs = P.use_tc(C, Co, ks, 1, H2, W2)
+            if tcs:
+                raw_dtype = torch.bfloat16
+            elif self.updown or x.b2 is not None:
+                raw_dtype = torch.float32
+        act1, raw = P.gn_apply(x.b1, x.C1, x.b2, x.C2, ab1, silu=True, resample=rs, B=B, H=H, W=W,
+                               act_dtype=torch.bfloat16 if tc1 else torch.float32, raw_dtype=raw_dtype)
+        h = P.new((B, H2, W2, Co), torch.float32, "res_h")
+        P.conv(act1, conv1.weight, conv1.bias, h, B=B, H=H2, W=W2, Cin=C, Cout=Co, k=3)
+
+        eb, eoff, eld = emb
+        zb = zoff = zld = None
+        if self.has_z:
+            zb, zoff, zld = embz
+        ab2 = P.gn_coef(h, Co, None, 0, gn2.weight, gn2.bias, B=B, HW=H2 * W2, emb=eb.at(eoff), emb_ld=eld,
+                        embz=zb.at(zoff) if zb is not None else None, embz_ld=zld or 0)
+        tc2 = P.use_tc(Co, Co, 3, 1, H2, W2)
+        act2, _ = P.gn_apply(h, Co, None, 0, ab2, silu=True, resample=RESAMPLE_NONE, B=B, H=H2, W=W2,
+                             act_dtype=torch.bfloat16 if tc2 else torch.float32)
+        if ident:
+            resid = raw if raw is not None else x.b1
+        else:
+            sk_in = raw if raw is not None else x.b1
+            resid = P.new((B, H2, W2, Co), torch.float32, "res_skip")
+            P.conv(sk_in, self.skip_connection.weight, self.skip_connection.bias, resid, B=B, H=H2, W=W2, Cin=C, Cout=Co,
+                   k=self.skip_connection.kernel_size[0])
+        out = P.new((B, H2, W2, Co), torch.float32, "res_out")
+        P.conv(act2, conv2.weight, conv2.bias, out, B=B, H=H2, W=W2, Cin=Co, Cout=Co, k=3, residual=resid)
+        return Src(out, Co, B, H2, W2)
+
+    def emit_emb(self, P: Plan, emb: Buf, B: int, which: str = "t") -> Tuple[Buf, int, int]:
+        """This block's own Linear(SiLU(emb)) -> [B, 2*Cout] (used when the block runs stand-alone)."""
+        lin = self.emb_layers[1] if which == "t" else self.emb_z_layers[1]
+        out = P.new((B, 2 * self.out_channels), torch.float32, "emb_out")
+        P.linear(emb, lin.weight, lin.bias, out, B=B, Cin=self.emb_channels, Cout=2 * self.out_channels, a_silu=True)
+        return out, 0, 2 * self.out_channels
+
+    # ---- stand-alone forward (NCHW in / NCHW out like the reference) ---------------------------------
+    def _forward(self, x, emb, emb_z=None):
+        self._check_no_grad(x, emb, emb_z)
+        B, C, H, W = x.shape
+        key = ("res", B, C, H, W, self.training)
+
+        def build(P: Plan):
+            xin = P.new((B, H, W, C), torch.float32, "x_in")
+            xin.keep = True
+            e = P.new((B, self.emb_channels), torch.float32, "emb_in")
+            e.keep = True
+            ez = None
+            if self.has_z:
+                ez = P.new((B, self.emb_channels), torch.float32, "embz_in")
+                ez.keep = True
+            # touch inputs so they are allocated before the first op
+            y = self.emit(P, Src(xin, C, B, H, W), self.emit_emb(P, e, B, "t"),
+                          self.emit_emb(P, ez, B, "z") if self.has_z else None)
+            y.b1.keep = True
+            return xin, e, ez, y
+
+        plan, (xin, e, ez, y) = self._get_plan(key, build)
+        xin.tensor.copy_(x.permute(0, 2, 3, 1))
+        e.tensor.copy_(emb)
+        if self.has_z:
+            ez.tensor.copy_(emb_z)
+        plan.run()
+        return y.b1.tensor.permute(0, 3, 1, 2).contiguous()
+
+
+class ResBlock(_ResBase, TimestepBlock):
+    """model/module.py:205-297."""
+    has_z = False
+
+    def forward(self, x, emb):
+        return self._forward(x, emb)
+
+
+class ResBlockShift(_ResBase, TimestepContextBlock):
+    """model/module.py:299-384: ResBlock + z-conditioned scale/shift ``(1+zs)*(GN(h)*(1+s)+sh)+zsh``."""
+    has_z = True
+
+    def forward(self, x, emb, emb_z):
+        return self._forward(x, emb, emb_z)
+
+
+class QKVAttentionLegacy(nn.Module):
+    """Marker for the heads-first channel split (model/module.py:431-457)."""
+
+    def __init__(self, n_heads):
+        super().__init__()
+        self.n_heads = n_heads
+
+
+class QKVAttention(nn.Module):
+    """Marker for the qkv-first channel split (model/module.py:460-488)."""
+
+    def __init__(self, n_heads):
+        super().__init__()
+        self.n_heads = n_heads
+
+
+class AttentionBlock(PlannedModule):
+    """model/module.py:387-428: GN -> qkv 1x1 -> softmax(QK^T ch^-1/2) V -> proj 1x1 -> + x."""
+
+    def __init__(self, channels, num_heads=1, num_head_channels=-1, use_new_attention_order=False):
+        super().__init__()
+        self.channels = channels
+        if num_head_channels == -1:
+            self.num_heads = num_heads
+        else:
+            assert channels % num_head_channels == 0, \
+                f"q,k,v channels {channels} is not divisible by num_head_channels {num_head_channels}"
+            self.num_heads = channels // num_head_channels
+        self.norm = normalization(channels)
+        self.qkv = conv_nd(1, channels, channels * 3, 1)
+        self.attention = QKVAttention(self.num_heads) if use_new_attention_order else QKVAttentionLegacy(self.num_heads)
+        self.proj_out = zero_module(conv_nd(1, channels, channels, 1))
+
+    def emit(self, P: Plan, x: Src) -> Src:
+        assert x.b2 is None and x.C == self.channels
+        B, H, W, C = x.B, x.H, x.W, x.C
+        T = H * W
+        legacy = isinstance(self.attention, QKVAttentionLegacy)
+        ab = P.gn_coef(x.b1, C, None, 0, self.norm.weight, self.norm.bias, B=B, HW=T)
+        tcq = P.use_tc(C, 3 * C, 1, 1, H, W)
+        xn, _ = P.gn_apply(x.b1, C, None, 0, ab, silu=False, resample=RESAMPLE_NONE, B=B, H=H, W=W,
+                           act_dtype=torch.bfloat16 if tcq else torch.float32)
+        qkv = P.new((B, T, 3 * C), torch.float32, "qkv")
+        P.conv(xn, self.qkv.weight, self.qkv.bias, qkv, B=B, H=H, W=W, Cin=C, Cout=3 * C, k=1)
+        att = P.new((B, T, C), torch.float32, "att")
+        scratch = P.new((B * self.num_heads, T, T), torch.float32, "att_scores")
+        P.call("attention_simt", qkv, att, scratch, B, T, C, self.num_heads, int(legacy), _STREAM, flops=4.0 * B * T * T * C)
+        tcp = P.use_tc(C, C, 1, 1, H, W)
+        if tcp:
+            att, _ = P.gn_apply(att, C, None, 0, None, silu=False, resample=RESAMPLE_NONE, B=B, H=H, W=W,
+                                act_dtype=torch.bfloat16)
+        out = P.new((B, H, W, C), torch.float32, "attn_out")
+        P.conv(att, self.proj_out.weight, self.proj_out.bias, out, B=B, H=H, W=W, Cin=C, Cout=C, k=1, residual=x.b1)
+        return Src(out, C, B, H, W)
+
+    def forward(self, x):
+        self._check_no_grad(x)
+        shape = x.shape
+        B, C = shape[0], shape[1]
+        T = 1
+        for s in shape[2:]:
+            T *= s
+        H, W = (shape[2], shape[3]) if len(shape) == 4 else (1, T)
+        key = ("attn", B, C, H, W)
+
+        def build(P: Plan):
+            xin = P.new((B, H, W, C), torch.float32, "x_in")
+            xin.keep = True
+            y = self.emit(P, Src(xin, C, B, H, W))
+            y.b1.keep = True
+            return xin, y
+
+        plan, (xin, y) = self._get_plan(key, build)
+        xin.tensor.copy_(x.reshape(B, C, H, W).permute(0, 2, 3, 1))
+        plan.run()
+        return y.b1.tensor.permute(0, 3, 1, 2).reshape(shape).contiguous()
+
+
+class TimestepSequential(nn.Sequential, TimestepBlock, TimestepContextBlock):
+    """model/module.py:131-140 (dispatch by block type), in plan-emission form."""
+
+    def emit(self, P: Plan, x, emb_of, embz_of=None) -> Src:
+        for layer in self:
+            if isinstance(layer, ResBlockShift):
+                x = layer.emit(P, x, emb_of(layer), embz_of(layer))
+            elif isinstance(layer, ResBlock):
+                x = layer.emit(P, x, emb_of(layer))
+            elif isinstance(layer, AttentionBlock):
+                x = layer.emit(P, x)
+            else:
+                raise TypeError(f"unexpected layer {type(layer).__name__} in TimestepSequential")
+        return x

@@ -1,0 +1,54 @@
+"""Rebuild, from a golden fixture's config, the pdae_b200 module + the seeded inputs that
+tests/golden/make_golden.py fed to the real reference.  Used by the CPU oracle tests and the GPU parity tests."""
+import torch
+
+from pdae_b200.model import module as pm
+from pdae_b200.model.mlp_skip_net import MLPSkipNet
+from pdae_b200.model.representation_learning.encoder import CELEBA64Encoder, FFHQEncoder
+from pdae_b200.model.shift_unet import ShiftUNet
+from pdae_b200.model.unet import UNet
+from pdae_b200.utils.synth import fill_module_, synth_images, synth_normal
+
+DIFF = {"timesteps": 1000, "betas_type": "linear"}
+
+
+def block_case(cfg):
+    """-> (module, inputs dict).  Seeds: weights 3/4, emb 11, embz 12, x 13/14 (make_golden.block_cases)."""
+    B, E = 2, 128
+    if cfg["kind"] == "resblock":
+        kw = {k: cfg[k] for k in ("channels", "out_channels", "up", "down") if k in cfg}
+        cls = pm.ResBlockShift if cfg["shift"] else pm.ResBlock
+        m = fill_module_(cls(emb_channels=E, dropout=0.0, **kw), seed=3).eval()
+        inp = {"x": synth_normal((B, cfg["channels"], 8, 8), 13), "emb": synth_normal((B, E), 11)}
+        if cfg["shift"]:
+            inp["emb_z"] = synth_normal((B, E), 12)
+        return m, inp
+    if cfg["kind"] == "attention":
+        m = fill_module_(pm.AttentionBlock(cfg["channels"], cfg["heads"], -1, cfg["new_order"]), seed=4).eval()
+        return m, {"x": synth_normal((B, cfg["channels"], 8, 8), 14)}
+    raise KeyError(cfg["kind"])
+
+
+def model_case(cfg):
+    """-> (module, inputs dict, oracle kind).  Seeds per make_golden.model_cases."""
+    kind = cfg["kind"]
+    if kind == "unet":
+        c = cfg["cfg"]
+        m = fill_module_(UNet(**c), seed=5).eval()
+        return m, {"x": synth_normal((2, c["input_channel"], cfg["size"], cfg["size"]), 15)}
+    if kind == "shiftunet":
+        c = cfg["cfg"]
+        m = fill_module_(ShiftUNet(**c), seed=6).eval()
+        return m, {"x": synth_normal((2, 3, cfg["size"], cfg["size"]), 16), "z": synth_normal((2, c["latent_dim"]), 17)}
+    if kind == "encoder":
+        cls = CELEBA64Encoder if cfg["size"] == 64 else FFHQEncoder
+        m = fill_module_(cls(latent_dim=512), seed=7).eval()
+        return m, {"x": synth_images(2, 3, cfg["size"], 18)}
+    if kind == "mlp":
+        m = fill_module_(MLPSkipNet(**cfg["cfg"]), seed=8).eval()
+        return m, {"x": synth_normal((2, 64), 19)}
+    raise KeyError(kind)
+
+
+def sd_of(module):
+    return {k: v.detach().float().cpu().clone() for k, v in module.state_dict().items()}

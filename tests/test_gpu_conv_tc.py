@@ -1,0 +1,106 @@
+"""tcgen05/TMA convolution vs the fp32 CUDA-core kernel on identical (bf16-rounded) operands, plus the
+CUDA-core kernel vs torch's CPU conv2d (the oracle's arithmetic).  Differences between the two GPU kernels can
+only come from accumulation order, so the tolerance is tight."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_conv(x, w, bias, resid, precision, k):
+    from pdae_b200.engine import Plan
+    B, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    P = Plan(x.device, precision)
+    out = P.new((B, H, W, Cout), torch.float32)
+    out.keep = True
+    P.conv(P.fixed(x), w, bias, out, B=B, H=H, W=W, Cin=Cin, Cout=Cout, k=k,
+           residual=P.fixed(resid) if resid is not None else None)
+    P.finalize()
+    P.run()
+    torch.cuda.synchronize()
+    kinds = [op[0] for op in P.ops]
+    return out.tensor.clone(), kinds
+
+
+SHAPES = [
+    # B, H, W, Cin, Cout, k, bias, residual
+    (2, 16, 16, 64, 64, 3, True, False),
+    (2, 16, 16, 64, 128, 3, True, True),
+    (1, 32, 32, 128, 128, 3, True, True),
+    (2, 8, 8, 128, 256, 3, True, False),     # tile spans 2 images
+    (8, 4, 4, 256, 256, 3, True, True),      # tile spans 8 images
+    (3, 8, 8, 64, 64, 3, True, True),        # batch not a multiple of the images-per-tile -> masked rows
+    (2, 64, 64, 64, 64, 3, False, False),
+    (1, 128, 128, 64, 128, 3, True, False),  # one tile = one image row
+    (2, 16, 16, 192, 64, 1, True, True),     # 1x1 (skip / qkv / proj)
+    (2, 16, 16, 64, 192, 1, True, False),
+    (1, 16, 16, 1024, 512, 3, True, True),   # long K loop (144 k-blocks): pipeline wrap-around
+    (2, 32, 16, 128, 64, 3, True, False),    # non-square
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s[:6])))
+def test_tc_conv_matches_simt(shape):
+    B, H, W, Cin, Cout, k, has_bias, has_res = shape
+    g = torch.Generator(device="cpu").manual_seed(hash(shape) % (2 ** 31))
+    x = torch.randn(B, H, W, Cin, generator=g).cuda().to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(torch.bfloat16).float().cuda()
+    bias = torch.randn(Cout, generator=g).cuda() if has_bias else None
+    resid = torch.randn(B, H, W, Cout, generator=g).cuda() if has_res else None
+    y_tc, kinds = _run_conv(x, w, bias, resid, "bf16", k)
+    assert kinds == ["conv_tc"], kinds
+    y_ref, kinds = _run_conv(x, w, bias, resid, "fp32", k)
+    assert kinds == ["conv2d_simt"], kinds
+    assert_close(y_tc, y_ref, rtol=2e-3, atol=2e-3, what=f"tc vs simt {shape}")
+    # and both against torch (CPU fp32, the oracle's arithmetic)
+    y_cpu = F.conv2d(x.float().cpu().permute(0, 3, 1, 2), w.cpu(), bias.cpu() if has_bias else None, padding=k // 2)
+    y_cpu = y_cpu.permute(0, 2, 3, 1)
+    if has_res:
+        y_cpu = y_cpu + resid.cpu()
+    assert_close(y_ref, y_cpu, rtol=1e-4, atol=1e-4, what=f"simt vs torch-cpu {shape}")
+
+
+@pytest.mark.parametrize("cfg", [(2, 3, 16, 16, 32, 3, 1, True), (2, 64, 16, 16, 128, 3, 2, False), (1, 128, 8, 8, 3, 3, 1, False),
+                                 (4, 96, 1, 1, 200, 1, 1, False)])
+def test_simt_conv_general(cfg):
+    """stem (NCHW in, Cin=3), stride-2 encoder conv, tiny-N, Linear (H=W=1) with SiLU on the input."""
+    from pdae_b200.engine import Plan
+    B, Cin, H, W, Cout, k, stride, nchw = cfg
+    g = torch.Generator(device="cpu").manual_seed(7)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    a_silu = (H == 1)
+    ref = F.conv2d(F.silu(x) if a_silu else x, w, b, stride=stride, padding=k // 2)
+    P = Plan(torch.device("cuda"), "fp32")
+    xin = x.cuda().contiguous() if nchw else x.permute(0, 2, 3, 1).contiguous().cuda()
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    out = P.new((B, Ho, Wo, Cout), torch.float32)
+    out.keep = True
+    P.conv(P.fixed(xin), w.cuda(), b.cuda(), out, B=B, H=H, W=W, Cin=Cin, Cout=Cout, k=k, stride=stride, in_nchw=nchw,
+           a_silu=a_silu)
+    P.finalize()
+    P.run()
+    assert_close(out.tensor.permute(0, 3, 1, 2), ref, rtol=1e-4, atol=1e-4, what=str(cfg))
+
+
+def test_head_conv_smalln():
+    from pdae_b200.engine import Plan
+    g = torch.Generator(device="cpu").manual_seed(9)
+    for dt in (torch.float32, torch.bfloat16):
+        x = torch.randn(2, 16, 16, 128, generator=g).to(dt)
+        w = torch.randn(3, 128, 3, 3, generator=g) / 34.0
+        b = torch.randn(3, generator=g)
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), w, b, padding=1)
+        P = Plan(torch.device("cuda"), "fp32")
+        out = P.new((2, 3, 16, 16), torch.float32)
+        out.keep = True
+        P.head_conv(P.fixed(x.cuda()), w.cuda(), b.cuda(), out, B=2, H=16, W=16, Cin=128, Cout=3)
+        P.finalize()
+        P.run()
+        assert [o[0] for o in P.ops] == ["conv3x3_smalln"]
+        assert_close(out.tensor, ref, rtol=1e-4, atol=1e-4, what=f"smalln {dt}")

@@ -1,0 +1,116 @@
+"""Per-step diffusion arithmetic and the DDIM loops on the GPU vs the reference fixtures."""
+import pytest
+import torch
+
+from tests import cases
+from tests.util import assert_close, load_golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def gd():
+    from pdae_b200.diffusion.gaussian_diffusion import GaussianDiffusion
+    return GaussianDiffusion(cases.DIFF, torch.device("cuda"))
+
+
+def test_tables_bit_exact():
+    for bt in ("linear", "cosine"):
+        from pdae_b200.diffusion.gaussian_diffusion import GaussianDiffusion
+        _, g = load_golden("diffusion_tables_" + bt)
+        d = GaussianDiffusion({"timesteps": 1000, "betas_type": bt}, torch.device("cuda"))
+        for k, v in g.items():
+            assert torch.equal(getattr(d, k).cpu(), v), (bt, k)
+
+
+def test_elementwise_steps():
+    from pdae_b200.utils.synth import synth_images, synth_normal
+    _, g = load_golden("diffusion_steps")
+    d = gd()
+    x0, noise, eps = synth_images(4, 3, 8, 21).cuda(), synth_normal((4, 3, 8, 8), 22).cuda(), synth_normal((4, 3, 8, 8), 23).cuda()
+    lr = synth_normal((4, 3, 8, 8), 24).clamp(-1, 1).cuda()
+    t = g["t"].cuda()
+    assert_close(d.q_sample(x0, t, noise), g["q"], rtol=0, atol=0, what="q_sample (bit exact)")
+    assert_close(d.noise_p_sample(x0, t, eps, noise=g["p_noise"].cuda()), g["p_sample"], rtol=1e-6, atol=1e-6, what="p_sample")
+    assert_close(d.noise_p_sample(x0, t, eps, lr, noise=g["p_noise"].cuda()), g["p_sample_lr"], rtol=1e-6, atol=1e-6, what="p_lr")
+
+
+def test_ddim_update_matches_oracle_bitwise():
+    from oracle import pdae_oracle as O
+    from pdae_b200.utils.synth import synth_normal
+    d = gd()._ddim("ddim100")
+    D = O.DiffusionOracle(cases.DIFF)
+    tabs, tmap, S = D._ddim("ddim100")
+    assert torch.equal(tmap, d.timestep_map.cpu()) and S == d.timesteps
+    x, eps, grad = (synth_normal((6, 3, 8, 8), s) for s in (51, 52, 53))
+    t = torch.tensor([0, 1, 50, 99, 100, 37])
+    for direction, tt in (("sample", t.clamp(min=1)), ("encode", t.clamp(max=99))):
+        for g_ in (grad, None):
+            ref = O.ddim_update(tabs, x, tt, eps, g_, direction)
+            got = d._update(x.cuda(), tt.cuda(), eps.cuda(), g_.cuda() if g_ is not None else None, direction)
+            assert_close(got, ref, rtol=1e-6, atol=1e-6, what=f"ddim {direction} shift={g_ is not None}")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_loops(precision):
+    from pdae_b200.utils.synth import synth_images, synth_normal
+    tol = dict(rtol=1e-3, atol=2e-4) if precision == "fp32" else None
+    d = gd()
+    xT, x0 = synth_normal((2, 3, 16, 16), 25).cuda(), synth_images(2, 3, 16, 26).cuda()
+
+    def check(got, want, what):
+        if tol:
+            assert_close(got, want, what=what, **tol)
+        else:
+            assert rel_l2(got, want) < 5e-2, (what, rel_l2(got, want))
+
+    cfg, g = load_golden("loop_unet_ddim10")
+    m, _ = cases.model_case({"kind": "unet", "cfg": cfg["cfg"], "size": 16})
+    m = m.cuda()
+    m.precision = precision
+    with torch.no_grad():
+        check(d.ddim_sample("ddim10", m, xT), g["sample"], "unet sample")
+        check(d.ddim_encode("ddim10", m, x0), g["encode"], "unet encode")
+    cfg, g = load_golden("loop_shift_ddim10")
+    m, _ = cases.model_case({"kind": "shiftunet", "cfg": cfg["cfg"], "size": 16})
+    m = m.cuda()
+    m.precision = precision
+    z = synth_normal((2, 64), 27).cuda()
+    with torch.no_grad():
+        check(d.representation_learning_ddim_sample("ddim10", None, m, None, xT, z), g["sample"], "shift sample")
+        check(d.representation_learning_ddim_sample("ddim10", None, m, None, xT, z, stop_percent=0.3), g["sample_stop30"], "stop30")
+        check(d.representation_learning_ddim_encode("ddim10", None, m, x0, z), g["encode"], "shift encode")
+        # generic (black-box callable) path must agree with the fast in-place path
+        slow = d._ddim("ddim10")._loop(lambda a, b, c: m(a, b, c), xT, z, "sample", shift=True)
+        fast = d.representation_learning_ddim_sample("ddim10", None, m, None, xT, z)
+        assert_close(slow, fast, rtol=1e-5, atol=1e-6, what="generic vs fast loop")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_autoencoding_and_latent(precision):
+    from pdae_b200.utils.synth import synth_images, synth_normal
+    d = gd()
+    cfg, g = load_golden("loop_autoencode_ddim10")
+    dec, _ = cases.model_case({"kind": "shiftunet", "cfg": cfg["cfg"], "size": 64})
+    enc, _ = cases.model_case({"kind": "encoder", "size": 64})
+    dec, enc = dec.cuda(), enc.cuda()
+    dec.precision = enc.precision = precision
+    x0 = synth_images(2, 3, 64, 28).cuda()
+    with torch.no_grad():
+        rec = d.representation_learning_autoencoding("ddim10", "ddim10", enc, dec, x0)
+    if precision == "fp32":
+        assert_close(rec, g["recon"], rtol=1e-3, atol=5e-4, what="autoencode")
+    else:
+        assert rel_l2(rec, g["recon"]) < 5e-2
+    # reconstruction-MSE metric of the reference (metric/utils.py:62-63, images scaled to [0,1])
+    mse = lambda a, b: float((((a.cpu() + 1) / 2 - (b.cpu() + 1) / 2) ** 2).mean())
+    assert abs(mse(rec, x0) - mse(g["recon"], x0)) < 1e-5
+
+    cfg, g = load_golden("loop_latent_ddim10")
+    m, _ = cases.model_case({"kind": "mlp", "cfg": cfg["cfg"]})
+    m = m.cuda()
+    zT = synth_normal((2, 64), 29).clamp(-1, 1).cuda()
+    nb, tmap = d.get_ddim_betas_and_timestep_map("ddim10", d.latent_diffusion_config["alphas_cumprod"].cpu().numpy())
+    from pdae_b200.diffusion.ddim import DDIM
+    with torch.no_grad():
+        out = DDIM(nb, tmap, torch.device("cuda")).latent_ddim_sample_loop(m, zT)
+    assert_close(out, g["z"], rtol=1e-3, atol=1e-4, what="latent loop")

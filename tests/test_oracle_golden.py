@@ -1,0 +1,147 @@
+"""Pin the CPU oracle (oracle/pdae_oracle.py) against the fixtures recorded from the REAL reference
+(tests/golden/make_golden.py).  CPU only; this is what makes the oracle trustworthy on the GPU box, where
+/root/reference does not exist."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pdae_oracle as O
+from tests import cases
+from tests.util import assert_close, golden_names, load_golden
+
+TOL = dict(rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", golden_names("block_"))
+def test_blocks(name):
+    cfg, g = load_golden(name)
+    m, inp = cases.block_case(cfg)
+    sd = {"blk." + k: v for k, v in cases.sd_of(m).items()}
+    if cfg["kind"] == "resblock":
+        y = O.resblock(sd, "blk", inp["x"], inp["emb"], inp.get("emb_z"), up=cfg.get("up", False), down=cfg.get("down", False))
+    else:
+        y = O.attention_block(sd, "blk", inp["x"], cfg["heads"], cfg["new_order"])
+    assert_close(y, g["y"], what=name, **TOL)
+
+
+def test_timestep_embedding():
+    _, g = load_golden("timestep_embedding")
+    assert_close(O.timestep_embedding(g["t"], 64), g["e64"], rtol=0, atol=0, what="e64")
+    assert_close(O.timestep_embedding(g["t"], 33), g["e33"], rtol=0, atol=0, what="e33")
+
+
+@pytest.mark.parametrize("name", golden_names("model_"))
+def test_models(name):
+    cfg, g = load_golden(name)
+    m, inp = cases.model_case(cfg)
+    sd = cases.sd_of(m)
+    if cfg["kind"] == "unet":
+        assert_close(O.unet_forward(sd, cfg["cfg"], inp["x"], g["t"], g.get("cond")), g["y"], what=name, **TOL)
+    elif cfg["kind"] == "shiftunet":
+        eps, grad = O.shiftunet_forward(sd, cfg["cfg"], inp["x"], g["t"], inp["z"])
+        assert_close(eps, g["eps"], what=name + ".eps", **TOL)
+        assert_close(grad, g["grad"], what=name + ".grad", **TOL)
+    elif cfg["kind"] == "encoder":
+        assert_close(O.encoder_forward(sd, "celeba64" if cfg["size"] == 64 else "ffhq128", inp["x"]), g["z"], what=name, **TOL)
+    else:
+        assert_close(O.mlp_skip_net_forward(sd, cfg["cfg"], inp["x"], g["t"]), g["y"], what=name, **TOL)
+
+
+@pytest.mark.parametrize("bt", ["linear", "cosine"])
+def test_schedule_tables(bt):
+    _, g = load_golden("diffusion_tables_" + bt)
+    tabs = O.gaussian_tables({"timesteps": 1000, "betas_type": bt})
+    for k, v in g.items():
+        assert torch.equal(tabs[k], v), k
+
+
+def test_ddim_maps_and_tables():
+    _, g = load_golden("diffusion_ddim_maps")
+    ac = O.gaussian_tables(cases.DIFF)["alphas_cumprod"].numpy()
+    for style, n in (("ddim10", 11), ("ddim100", 101), ("ddim200", 201), ("ddim500", 501), ("ddim1000", 1000)):
+        nb, tmap = O.ddim_betas_and_timestep_map(style, ac)
+        assert tmap.shape[0] == n
+        assert torch.equal(tmap, g[style + "_map"])
+        np.testing.assert_array_equal(nb, g[style + "_betas"].numpy())
+        if style in ("ddim10", "ddim100"):
+            for k, v in O.ddim_tables(nb).items():
+                assert torch.equal(v, g[f"{style}_{k}"]), (style, k)
+
+
+def test_elementwise_steps():
+    from pdae_b200.utils.synth import synth_images, synth_normal
+    _, g = load_golden("diffusion_steps")
+    D = O.DiffusionOracle(cases.DIFF)
+    x0, noise, eps = synth_images(4, 3, 8, 21), synth_normal((4, 3, 8, 8), 22), synth_normal((4, 3, 8, 8), 23)
+    lr = synth_normal((4, 3, 8, 8), 24).clamp(-1, 1)
+    assert_close(D.q_sample(x0, g["t"], noise), g["q"], rtol=0, atol=0, what="q_sample")
+    assert_close(D.noise_p_sample(x0, g["t"], eps, g["p_noise"]), g["p_sample"], rtol=1e-6, atol=1e-6, what="p_sample")
+    assert_close(D.noise_p_sample(x0, g["t"], eps, g["p_noise"], lr), g["p_sample_lr"], rtol=1e-6, atol=1e-6, what="p_lr")
+
+
+def test_loops():
+    from pdae_b200.utils.synth import synth_images, synth_normal
+    D = O.DiffusionOracle(cases.DIFF)
+    cfg, g = load_golden("loop_unet_ddim10")
+    m, _ = cases.model_case({"kind": "unet", "cfg": cfg["cfg"], "size": 16})
+    sd = cases.sd_of(m)
+    fn = lambda x, t, c: O.unet_forward(sd, cfg["cfg"], x, t, c)
+    xT, x0 = synth_normal((2, 3, 16, 16), 25), synth_images(2, 3, 16, 26)
+    assert_close(D.ddim_sample("ddim10", fn, xT), g["sample"], what="unet sample", **TOL)
+    assert_close(D.ddim_encode("ddim10", fn, x0), g["encode"], what="unet encode", **TOL)
+
+    cfg, g = load_golden("loop_shift_ddim10")
+    m, _ = cases.model_case({"kind": "shiftunet", "cfg": cfg["cfg"], "size": 16})
+    sd = cases.sd_of(m)
+    dec = lambda x, t, z: O.shiftunet_forward(sd, cfg["cfg"], x, t, z)
+    z = synth_normal((2, 64), 27)
+    assert_close(D.representation_learning_ddim_sample("ddim10", dec, xT, z), g["sample"], what="shift sample", **TOL)
+    assert_close(D.representation_learning_ddim_sample("ddim10", dec, xT, z, 0.3), g["sample_stop30"], what="stop30", **TOL)
+    assert_close(D.representation_learning_ddim_encode("ddim10", dec, x0, z), g["encode"], what="shift encode", **TOL)
+
+
+def test_autoencoding_and_latent_loop():
+    from pdae_b200.utils.synth import synth_images, synth_normal
+    D = O.DiffusionOracle(cases.DIFF)
+    cfg, g = load_golden("loop_autoencode_ddim10")
+    dec_m, _ = cases.model_case({"kind": "shiftunet", "cfg": cfg["cfg"], "size": 64})
+    enc_m, _ = cases.model_case({"kind": "encoder", "size": 64})
+    dsd, esd = cases.sd_of(dec_m), cases.sd_of(enc_m)
+    rec = D.representation_learning_autoencoding(
+        "ddim10", "ddim10", lambda x: O.encoder_forward(esd, "celeba64", x),
+        lambda x, t, z: O.shiftunet_forward(dsd, cfg["cfg"], x, t, z), synth_images(2, 3, 64, 28))
+    assert_close(rec, g["recon"], what="autoencode", rtol=1e-3, atol=1e-4)
+
+    cfg, g = load_golden("loop_latent_ddim10")
+    m, _ = cases.model_case({"kind": "mlp", "cfg": cfg["cfg"]})
+    sd = cases.sd_of(m)
+    zT = synth_normal((2, 64), 29).clamp(-1, 1)
+    out = D.latent_ddim_sample("ddim10", lambda z, t: O.mlp_skip_net_forward(sd, cfg["cfg"], z, t), zT)
+    assert_close(out, g["z"], what="latent loop", **TOL)
+
+
+def test_training_losses():
+    from pdae_b200.utils.synth import synth_images
+    D = O.DiffusionOracle(cases.DIFF)
+    cfg, g = load_golden("train_representation_learning")
+    dec_m, _ = cases.model_case({"kind": "shiftunet", "cfg": cfg["cfg"], "size": 64})
+    enc_m, _ = cases.model_case({"kind": "encoder", "size": 64})
+    dsd = {k: v.requires_grad_(k.startswith(("label_emb", "shift_"))) for k, v in cases.sd_of(dec_m).items()}
+    esd = {k: v.requires_grad_(True) for k, v in cases.sd_of(enc_m).items()}
+    loss = D.representation_learning_loss(lambda x: O.encoder_forward(esd, "celeba64", x),
+                                          lambda x, t, z: O.shiftunet_forward(dsd, cfg["cfg"], x, t, z),
+                                          synth_images(2, 3, 64, 31), g["t"], g["noise"])
+    assert_close(loss, g["loss"], what="rl loss", rtol=1e-5, atol=1e-7)
+    loss.backward()
+    n_grad = sum(1 for v in list(dsd.values()) + list(esd.values()) if v.grad is not None)
+    assert n_grad == cfg["n_params_with_grad"]
+    for key, ref in (("label_emb.weight", "g_label_emb_weight"), ("shift_out.2.weight", "g_shift_out_2_weight")):
+        assert_close(dsd[key].grad.flatten()[:512], g[ref], what=key, rtol=1e-3, atol=1e-7)
+        assert_close(dsd[key].grad.double().norm().float(), g["n" + ref], what=key + " norm", rtol=1e-4, atol=0)
+    assert_close(esd["encoder.0.weight"].grad.flatten()[:512], g["g_enc_encoder_0_weight"], what="enc grad", rtol=1e-3, atol=1e-7)
+
+    cfg, g = load_golden("train_regular")
+    m, _ = cases.model_case({"kind": "unet", "cfg": cfg["cfg"], "size": 16})
+    sd = cases.sd_of(m)
+    loss = D.regular_loss(lambda x, t, c: O.unet_forward(sd, cfg["cfg"], x, t, c), synth_images(2, 3, 16, 32), g["t"], g["noise"])
+    assert_close(loss, g["loss"], what="regular loss", rtol=1e-5, atol=1e-7)
