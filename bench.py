@@ -113,7 +113,8 @@ def cpu_sample(cfg, size, enc_kind, enc_size, S, batch, n_steps, warm=1):
     + 1 encoder forward per image (every step is identical work)."""
     from pdae_b200.utils.synth import synth_images, synth_normal
     enc, dec, O = oracle_models(cfg, enc_kind)
-    cores = os.cpu_count() or 1
+    from pdae_b200.utils.host import host_cores
+    cores = host_cores()  # affinity and cgroup quota: the box exposes 128 logical CPUs but grants a 16-CPU quota
     torch.set_num_threads(cores)
     D = O.DiffusionOracle(DIFFUSION)
     tabs, tmap, _ = D._ddim(f"ddim{S}")

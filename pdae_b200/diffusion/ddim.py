@@ -8,6 +8,7 @@ allocation, no host sync, no tqdm).
 from __future__ import annotations
 
 import ctypes
+import os
 from functools import partial
 
 import numpy as np
@@ -25,6 +26,9 @@ def _stream(dev):
 
 
 class DDIM:
+    # replay each network step as one CUDA graph in the native fast path (PDAE_NO_GRAPH=1 disables, e.g. under ncu)
+    use_cuda_graph = os.environ.get("PDAE_NO_GRAPH", "0") != "1"
+
     def __init__(self, betas, timestep_map, device):
         self.device = device
         self.timestep_map = timestep_map.to(self.device)
@@ -107,6 +111,8 @@ class DDIM:
             grad = None
             if c_in is not None:
                 c_in.tensor.copy_(cond)
+        if self.use_cuda_graph:
+            plan.capture_graph()
         x_in.tensor.copy_(x)
         t_loc = torch.empty(B, device=self.device, dtype=torch.int64)
         eps_t = eps.tensor

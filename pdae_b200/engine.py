@@ -92,8 +92,9 @@ class Packed:
 
 
 class Plan:
-    def __init__(self, device: torch.device, precision: Optional[str] = None):
-        _native.require_device()
+    def __init__(self, device: torch.device, precision: Optional[str] = None, check_device: bool = True):
+        if check_device:  # False only in CPU unit tests of the recording / buffer-assignment logic (a plan cannot run there)
+            _native.require_device()
         self.device = device
         self.precision = precision or _default_precision
         self.tc = self.precision == "bf16"
@@ -106,6 +107,7 @@ class Plan:
         self._compiled = None
         self._tc_handles: List[ctypes.c_void_p] = []
         self.n_launch = 0
+        self.graph = None
         self.flops: List[float] = []  # algorithmic FLOPs (2*MACs) per recorded op, 0 for non-contraction ops
 
     # ---- buffers ----------------------------------------------------------------------------
@@ -115,7 +117,7 @@ class Plan:
         return b
 
     def fixed(self, t: torch.Tensor) -> Buf:
-        assert t.is_cuda and t.is_contiguous(), "plan tensors must be contiguous CUDA tensors"
+        assert t.is_contiguous(), "plan tensors must be contiguous"
         return Buf(t.shape, t.dtype, t)
 
     def param(self, p: Optional[torch.Tensor]) -> Optional[Buf]:
@@ -168,8 +170,17 @@ class Plan:
                 ends.setdefault(b.last, []).append(b)
         free: List[torch.Tensor] = []
         self.arena_bytes = 0
+        # `keep` buffers are the plan's inputs/outputs: the caller writes/reads them OUTSIDE the op sequence, so their
+        # live range is the whole plan -- they get private storage and never touch the recycling pool.
+        for b in self.bufs:
+            if b.keep and b.first is not None:
+                b.tensor = torch.empty(max(b.nbytes, 16), dtype=torch.uint8, device=self.device)[: b.nbytes].view(
+                    b.dtype).view(b.shape)
+                self.arena_bytes += b.nbytes
         for i in range(len(self.ops)):
             for b in starts.get(i, []):
+                if b.keep:
+                    continue
                 need = max(b.nbytes, 16)
                 best = None
                 for j, blk in enumerate(free):
@@ -230,15 +241,36 @@ class Plan:
     def stale(self) -> bool:
         return any(p.data_ptr() != ptr for p, ptr in self.params)
 
-    def run(self) -> None:
-        for pk in self.packed:
-            pk.refresh()
+    def _launch_all(self) -> None:
         stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         for cfn, cargs, sidx, name in self._compiled:
             cargs[sidx] = stream
             rc = cfn(*cargs)
             if rc != 0:
                 _native.check(rc, "pdae_" + name)
+
+    def run(self) -> None:
+        for pk in self.packed:
+            pk.refresh()
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._launch_all()
+
+    def capture_graph(self) -> "Plan":
+        """Record the whole launch list into a CUDA graph (all buffers are static, nothing allocates), so a replay costs
+        one launch instead of hundreds of ctypes calls.  Idempotent."""
+        if self.graph is not None:
+            return self
+        for pk in self.packed:
+            pk.refresh()
+        self._launch_all()  # warm-up outside capture (lazy module loading, cudaFuncSetAttribute, ...)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._launch_all()
+        self.graph = g
+        return self
 
     def profile(self, reps: int = 3) -> Dict[str, Dict[str, float]]:
         """Per-kernel-kind device time (CUDA events on the launching stream) and algorithmic FLOPs of one replay.

@@ -145,3 +145,20 @@ def test_training_losses():
     sd = cases.sd_of(m)
     loss = D.regular_loss(lambda x, t, c: O.unet_forward(sd, cfg["cfg"], x, t, c), synth_images(2, 3, 16, 32), g["t"], g["noise"])
     assert_close(loss, g["loss"], what="regular loss", rtol=1e-5, atol=1e-7)
+
+
+def test_loop_sensitivity():
+    """How much a 10-step shift-DDIM loop on random weights amplifies an input perturbation (justifies the stated
+    bf16 loop tolerance in tests/test_gpu_diffusion.py): 1e-5 in -> between 1e-5 and 1e-2 out, no sign flips."""
+    from pdae_b200.utils.synth import synth_normal
+    D = O.DiffusionOracle(cases.DIFF)
+    cfg, g = load_golden("loop_shift_ddim10")
+    m, _ = cases.model_case({"kind": "shiftunet", "cfg": cfg["cfg"], "size": 16})
+    sd = cases.sd_of(m)
+    dec = lambda x, t, z: O.shiftunet_forward(sd, cfg["cfg"], x, t, z)
+    z, xT = synth_normal((2, 64), 27), synth_normal((2, 3, 16, 16), 25)
+    with torch.no_grad():
+        a = D.representation_learning_ddim_sample("ddim10", dec, xT, z)
+        b = D.representation_learning_ddim_sample("ddim10", dec, xT + 1e-5 * synth_normal((2, 3, 16, 16), 99), z)
+    amp = float((a - b).abs().max()) / 1e-5
+    assert 1.0 < amp < 1e3, amp
