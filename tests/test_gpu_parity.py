@@ -80,7 +80,9 @@ def test_repeat_calls_and_weight_update_refresh_packed_weights():
     with torch.no_grad():
         e1, g1 = m(i["x"], t, i["z"])
         e2, g2 = m(i["x"], t, i["z"])
-        assert torch.equal(e1, e2) and torch.equal(g1, g2)
+        # GroupNorm statistics are accumulated with atomics -> run-to-run differences at the 1e-7 level are expected
+        assert_close(e2, e1, rtol=1e-5, atol=1e-6, what="repeat eps")
+        assert_close(g2, g1, rtol=1e-5, atol=1e-6, what="repeat grad")
         sd = {k: v.clone() for k, v in m.state_dict().items()}
         m.shift_out[2].weight.mul_(2.0)
         m.shift_out[2].bias.mul_(2.0)
@@ -88,7 +90,7 @@ def test_repeat_calls_and_weight_update_refresh_packed_weights():
         assert_close(g3, 2.0 * g1, rtol=1e-5, atol=1e-6, what="scaled head")
         m.load_state_dict(sd)
         _, g4 = m(i["x"], t, i["z"])
-        assert torch.equal(g4, g1)
+        assert_close(g4, g1, rtol=1e-5, atol=1e-6, what="restored weights")
 
 
 def test_oracle_agrees_on_gpu_inputs_at_larger_shape():
