@@ -1,0 +1,51 @@
+"""Data-parallel plumbing of the sampling path: contiguous batch shards, one all-gather of results.
+
+The hot path shards over independent images: no collective inside the DDIM loop; the reference
+collects results with ``all_gather_object`` of ``.tolist()``-ed images (trainer/base_trainer.py:156-159,
+sampler/base_sampler.py:53-56) -- here it is ONE tensor all-gather (NCCL on GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """[start, end) of rank's contiguous shard; like dispatch_num_samples_for_process (sampler/base_sampler.py:40-50)
+    every rank gets n // world items and the LAST rank also takes the remainder."""
+    per = n // world
+    start = rank * per
+    end = n if rank == world - 1 else start + per
+    return start, end
+
+
+def all_gather_images(local: torch.Tensor, n_total: int) -> torch.Tensor:
+    """Gather per-rank shards (possibly ragged: the last rank may hold the remainder) into [n_total, ...] on every rank
+    with a single equal-count all-gather (shards are padded to the largest count)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local
+    world, rank = dist.get_world_size(), dist.get_rank()
+    counts = [shard_range(n_total, r, world) for r in range(world)]
+    cmax = max(e - s for s, e in counts)
+    pad = local
+    if local.shape[0] < cmax:
+        pad = torch.cat([local, local.new_zeros((cmax - local.shape[0],) + tuple(local.shape[1:]))], 0)
+    out = local.new_empty((world * cmax,) + tuple(local.shape[1:]))
+    dist.all_gather_into_tensor(out, pad.contiguous())
+    parts: List[torch.Tensor] = [out[r * cmax: r * cmax + (e - s)] for r, (s, e) in enumerate(counts)]
+    return torch.cat(parts, 0)
+
+
+def sharded_autoencode(gd, encoder, decoder, x0_all: torch.Tensor, enc_style: str = "ddim100", dec_style: str = "ddim100",
+                       device=None) -> torch.Tensor:
+    """Autoencode a global batch: every rank runs the hot path on its shard, then one all-gather."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    s, e = shard_range(x0_all.shape[0], rank, world)
+    x = x0_all[s:e]
+    if device is not None:
+        x = x.to(device)
+    rec = gd.representation_learning_autoencoding(enc_style, dec_style, encoder, decoder, x)
+    return all_gather_images(rec, x0_all.shape[0])
