@@ -76,9 +76,18 @@ int pdae_gn_coef(const double* sums, const float* gamma, const float* beta, int 
 /* out_act = resample( f(a*x+b) ) over the virtual concat; f = SiLU if silu.  ab == NULL -> a=1,b=0.
  * out_raw (optional) = resample(x) (the un-normalised input, for the skip path).  H, W are the SOURCE
  * dims; outputs are [B][H'][W'][C1+C2] with H' = 2H (UP2), H/2 (DOWN2) or H.                          */
-int pdae_gn_apply(const float* src1, int C1, const float* src2, int C2, const float* ab, int silu, int resample,
-                  int B, int H, int W, void* out_act, int act_dtype, void* out_raw, int raw_dtype,
+int pdae_gn_apply(const void* src1, int src1_dtype, int C1, const float* src2, int C2, const float* ab, int silu,
+                  int resample, int B, int H, int W, void* out_act, int act_dtype, void* out_raw, int raw_dtype,
                   pdae_stream_t stream);
+
+/* Per-channel variant of the statistics (what the tensor-core conv epilogue accumulates): chs[b][c] = (sum, sum^2)
+ * in fp32.  pdae_ch_stats fills it for a tensor that no conv epilogue produced; pdae_gn_coef_ch forms the 32 group
+ * statistics over the virtual concat [chs1 | chs2] (groups may straddle the seam) and folds the affine / AdaGN terms. */
+int pdae_zero(void* ptr, int64_t bytes, pdae_stream_t stream);
+int pdae_ch_stats(const float* src, int B, int HW, int C, float* chs, pdae_stream_t stream);
+int pdae_gn_coef_ch(const float* chs1, int C1, const float* chs2, int C2, const float* gamma, const float* beta, int B,
+                    int HW, float eps, const float* emb, int emb_ld, const float* embz, int embz_ld, float* ab,
+                    pdae_stream_t stream);
 
 /* ---- attention (model/module.py:422-488) ---------------------------------------------------------
  * qkv: fp32 [B][T][3C] token-major.  legacy != 0: per-head channel blocks [q|k|v] (QKVAttentionLegacy);
@@ -127,6 +136,18 @@ int pdae_conv_tc_create(pdae_conv_tc_plan** plan, const void* in_bf16, const voi
                         const float* residual, float* out, int B, int H, int W, int Cin, int Cout, int ksize);
 int pdae_conv_tc_run(const pdae_conv_tc_plan* plan, pdae_stream_t stream);
 void pdae_conv_tc_destroy(pdae_conv_tc_plan* plan);
+
+
+/* v2: persistent CTAs, double-buffered TMEM accumulators (epilogue overlaps the next tile's main loop), TMA-store
+ * epilogue.  out_dtype PDAE_F32|PDAE_BF16; ch_stats (optional) fp32 [B][Cout][2] accumulates per-channel (sum, sum^2)
+ * of the stored values (zero it first); residual needs an fp32 output.  cout_valid > 0 selects the image-head variant:
+ * Cout must be 16 (weights zero-padded), `out` is NCHW fp32 [B][cout_valid][H][W].  bn_override: 0 = auto.              */
+typedef struct pdae_conv_tc2_plan pdae_conv_tc2_plan;
+int pdae_conv_tc2_create(pdae_conv_tc2_plan** plan, const void* in_bf16, const void* w_bf16, const float* bias,
+                         const float* residual, void* out, int out_dtype, float* ch_stats, int B, int H, int W, int Cin,
+                         int Cout, int ksize, int cout_valid, int bn_override);
+int pdae_conv_tc2_run(const pdae_conv_tc2_plan* plan, pdae_stream_t stream);
+void pdae_conv_tc2_destroy(pdae_conv_tc2_plan* plan);
 
 #ifdef __cplusplus
 }

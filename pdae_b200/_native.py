@@ -16,7 +16,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libpdae_b200.so")
-SOURCES = ["conv_simt.cu", "norm_elementwise.cu", "attention_simt.cu", "conv_tc.cu"]
+SOURCES = ["conv_simt.cu", "norm_elementwise.cu", "attention_simt.cu", "conv_tc.cu", "conv_tc2.cu"]
 
 PDAE_F32, PDAE_BF16 = 0, 1
 RESAMPLE_NONE, RESAMPLE_UP2, RESAMPLE_DOWN2 = 0, 1, 2
@@ -58,7 +58,10 @@ _SIGS = {
     "pdae_conv3x3_smalln": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "pdae_gn_stats": (c_int, [_P, c_int, _P, c_int, c_int, c_int, _P, _P]),
     "pdae_gn_coef": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_float, _P, c_int, _P, c_int, _P, _P]),
-    "pdae_gn_apply": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, _P]),
+    "pdae_gn_apply": (c_int, [_P, c_int, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, _P]),
+    "pdae_zero": (c_int, [_P, c_int64, _P]),
+    "pdae_ch_stats": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
+    "pdae_gn_coef_ch": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_float, _P, c_int, _P, c_int, _P, _P]),
     "pdae_attention_simt": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "pdae_timestep_embedding": (c_int, [_P, c_int, c_int, _P, _P, _P]),
     "pdae_embedding_add": (c_int, [_P, _P, _P, c_int, c_int, _P]),
@@ -70,6 +73,10 @@ _SIGS = {
     "pdae_conv_tc_create": (c_int, [POINTER(c_void_p), _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int]),
     "pdae_conv_tc_run": (c_int, [_P, _P]),
     "pdae_conv_tc_destroy": (None, [_P]),
+    "pdae_conv_tc2_create": (c_int, [POINTER(c_void_p), _P, _P, _P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int,
+                                     c_int, c_int]),
+    "pdae_conv_tc2_run": (c_int, [_P, _P]),
+    "pdae_conv_tc2_destroy": (None, [_P]),
 }
 EXPORTS = tuple(_SIGS.keys())
 

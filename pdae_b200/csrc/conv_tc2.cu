@@ -1,0 +1,558 @@
+// conv_tc v2 -- persistent, warp-specialised tensor-core implicit-GEMM convolution for sm_100a.
+//
+//   warp 0   : TMA producer  (4-D activation boxes with OOB zero fill = conv padding, 3-D weight boxes)
+//   warp 1   : tcgen05.mma issuer; accumulators are DOUBLE-BUFFERED in TMEM (2 x BN columns), so
+//   warps 2-5: the epilogue of tile i overlaps the main loop of tile i+1:
+//              tcgen05.ld -> +bias (+fp32 residual fetched by TMA) -> 128B-swizzled staging tile in smem ->
+//              per-channel GroupNorm partial sums (sum, sum^2) -> TMA store (fp32 or bf16 NHWC).
+// One CTA per SM, static round-robin tile schedule (tile = blockIdx.x + i * gridDim.x; all CTAs sweep the same
+// weight tile at the same time, so it stays hot in L2).
+//
+// The BN=16 instantiation is the UNet image head (Cout=3 zero-padded to 16): it skips the TMA store and writes the
+// first `cout_valid` columns as NCHW fp32 planes (coalesced along x).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace pdae {
+
+constexpr int T2_BM = 128;
+constexpr int T2_BK = 64;
+constexpr int T2_A_BYTES = T2_BM * T2_BK * 2;  // 16 KB
+constexpr int T2_STG_BYTES = 128 * 128;        // staging tile: 128 rows x 128 B
+constexpr int T2_MAX_STAGES = 8;
+constexpr int T2_THREADS = 192;
+constexpr int T2_EPI_THREADS = 128;
+
+struct ConvTc2Args {
+  const float* bias;
+  float* ch_stats;    // [B][Cout][2] fp32 partial (sum, sum^2) accumulators or nullptr
+  float* out_nchw;    // BN==16 head: NCHW fp32 output
+  int B, H, W, Cout;
+  int tw, th, tn;
+  int tiles_x, tiles_y, tiles_b, tiles_m, tiles_total;
+  int taps, ksize, kblocks;
+  int stages;
+  int has_res, out_bf16, cout_valid;
+};
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mb_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mb_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000LL) __trap();  // a protocol bug must trap, never hang the GPU
+  }
+}
+__device__ __forceinline__ void tma_ld4(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_ld3(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_st4(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(m), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(a), "l"(b), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_to(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// byte offset of (row, 16-byte chunk) inside a 128-row x 128-byte SWIZZLE_128B staging tile
+__device__ __forceinline__ uint32_t swz(int row, int chunk16) { return (uint32_t)(row * 128 + ((chunk16 ^ (row & 7)) << 4)); }
+
+template <int BN>
+__global__ void __launch_bounds__(T2_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, ConvTc2Args p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[T2_MAX_STAGES], bar_empty[T2_MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2], bar_res[2];
+  __shared__ uint32_t tmem_slot;
+
+  constexpr int B_BYTES = BN * T2_BK * 2;
+  constexpr int STAGE_BYTES = T2_A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
+  constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  const uint32_t smem0 = (s_u32(smem_raw) + 1023u) & ~1023u;
+  const int S = p.stages;
+  const uint32_t stg_out = smem0 + (uint32_t)S * STAGE_BYTES;   // 2 x 16 KB output staging
+  const uint32_t stg_res = stg_out + 2u * T2_STG_BYTES;         // 2 x 16 KB residual staging (only if has_res)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_k = p.taps * p.kblocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mb_init(s_u32(&bar_full[s]), 1);
+      mb_init(s_u32(&bar_empty[s]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mb_init(s_u32(&bar_acc_full[i]), 1);
+      mb_init(s_u32(&bar_acc_empty[i]), 1);
+      mb_init(s_u32(&bar_res[i]), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_slot)), "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= TMA producer =================
+      int it_g = 0;
+      for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
+        const int nt = tile / p.tiles_m;
+        int mt = tile - nt * p.tiles_m;
+        const int tx = mt % p.tiles_x;
+        mt /= p.tiles_x;
+        const int ty = mt % p.tiles_y;
+        const int bt = mt / p.tiles_y;
+        const int x0 = tx * p.tw, y0 = ty * p.th, b0 = bt * p.tn, n0 = nt * BN;
+        for (int it = 0; it < total_k; ++it, ++it_g) {
+          const int s = it_g % S;
+          const uint32_t ph = (uint32_t)((it_g / S) & 1);
+          mb_wait(s_u32(&bar_empty[s]), ph ^ 1u);
+          const uint32_t full = s_u32(&bar_full[s]);
+          mb_expect_tx(full, T2_A_BYTES + B_BYTES);
+          const int tap = it / p.kblocks, kb = it - tap * p.kblocks;
+          const int dy = p.ksize == 3 ? tap / 3 - 1 : 0, dx = p.ksize == 3 ? tap % 3 - 1 : 0;
+          const uint32_t sa = smem0 + (uint32_t)s * STAGE_BYTES;
+          tma_ld4(sa, &tmA, full, kb * T2_BK, x0 + dx, y0 + dy, b0);
+          tma_ld3(sa + T2_A_BYTES, &tmB, full, kb * T2_BK, n0, tap);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================= MMA issuer =================
+      constexpr uint32_t IDESC =
+          (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24);
+      int it_g = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++tl) {
+        const int ab = tl & 1;
+        mb_wait(s_u32(&bar_acc_empty[ab]), (uint32_t)(((tl >> 1) & 1) ^ 1));  // epilogue drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_d = tmem_base + (uint32_t)(ab * BN);
+        for (int it = 0; it < total_k; ++it, ++it_g) {
+          const int s = it_g % S;
+          mb_wait(s_u32(&bar_full[s]), (uint32_t)((it_g / S) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem0 + (uint32_t)s * STAGE_BYTES;
+          const uint64_t ad = sw128_desc(sa), bd = sw128_desc(sa + T2_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < T2_BK / 16; ++k)
+            umma(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), IDESC, (uint32_t)((it | k) != 0));
+          umma_commit_to(s_u32(&bar_empty[s]));
+        }
+        umma_commit_to(s_u32(&bar_acc_full[ab]));
+      }
+    }
+  } else {
+    // ================= epilogue (128 threads) =================
+    const int et = threadIdx.x - 64;           // 0..127
+    const bool elected = et == 0;
+    const int q = warp & 3;                    // TMEM lane quadrant of this warp
+    const int r = q * 32 + lane;               // accumulator row = pixel index in the tile
+    const int ppi = p.th * p.tw;               // pixels per image inside a tile
+    int tl = 0, sc = 0, rc = 0;                // tile / staging-buffer / residual-buffer counters
+    for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++tl) {
+      const int nt = tile / p.tiles_m;
+      int mt = tile - nt * p.tiles_m;
+      const int tx = mt % p.tiles_x;
+      mt /= p.tiles_x;
+      const int ty = mt % p.tiles_y;
+      const int bt = mt / p.tiles_y;
+      const int x0 = tx * p.tw, y0 = ty * p.th, b0 = bt * p.tn, n0 = nt * BN;
+      const int ab = tl & 1;
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(ab * BN) + ((uint32_t)(q * 32) << 16);
+      mb_wait(s_u32(&bar_acc_full[ab]), (uint32_t)((tl >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+      if constexpr (BN == 16) {
+        // ---- image head: first cout_valid columns -> NCHW fp32 planes ----
+        uint32_t v[16];
+        tmem_ld16(tmem_acc, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int ni = r / ppi, rem = r - ni * ppi;
+        const int yy = rem / p.tw, xx = rem - yy * p.tw;
+        const int b = b0 + ni;
+        if (b < p.B) {
+          const long long hw = (long long)p.H * p.W;
+          float* o = p.out_nchw + (long long)b * p.cout_valid * hw + (long long)(y0 + yy) * p.W + (x0 + xx);
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < p.cout_valid) o[j * hw] = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + j) : 0.f);
+        }
+      } else {
+        const int CW = p.out_bf16 ? 64 : 32;  // accumulator columns per staging tile (128-byte rows)
+        const int nch = BN / CW;
+        if (p.has_res && elected) {            // residual chunk 0 of this tile
+          const uint32_t rb = s_u32(&bar_res[rc & 1]);
+          mb_expect_tx(rb, T2_STG_BYTES);
+          tma_ld4(stg_res + (uint32_t)(rc & 1) * T2_STG_BYTES, &tmR, rb, n0, x0, y0, b0);
+        }
+        for (int c = 0; c < nch; ++c) {
+          float val[64];
+          {
+            uint32_t v[32];
+            tmem_ld32(tmem_acc + (uint32_t)(c * CW), v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(v[j]);
+            if (p.out_bf16) {
+              tmem_ld32(tmem_acc + (uint32_t)(c * CW + 32), v);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+              for (int j = 0; j < 32; ++j) val[32 + j] = __uint_as_float(v[j]);
+            }
+          }
+          if (p.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c * CW);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (j * 4 < CW) {
+                const float4 bv = __ldg(bp + j);
+                val[4 * j + 0] += bv.x; val[4 * j + 1] += bv.y; val[4 * j + 2] += bv.z; val[4 * j + 3] += bv.w;
+              }
+            }
+          }
+          if (p.has_res) {                      // fp32 output only (CW == 32)
+            if (elected && c + 1 < nch) {
+              const uint32_t rb = s_u32(&bar_res[(rc + 1) & 1]);
+              mb_expect_tx(rb, T2_STG_BYTES);
+              tma_ld4(stg_res + (uint32_t)((rc + 1) & 1) * T2_STG_BYTES, &tmR, rb, n0 + (c + 1) * 32, x0, y0, b0);
+            }
+            mb_wait(s_u32(&bar_res[rc & 1]), (uint32_t)((rc >> 1) & 1));
+            const uint32_t rbuf = stg_res + (uint32_t)(rc & 1) * T2_STG_BYTES;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 rv;
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(rv.x), "=f"(rv.y), "=f"(rv.z), "=f"(rv.w)
+                           : "r"(rbuf + swz(r, j)));
+              val[4 * j + 0] += rv.x; val[4 * j + 1] += rv.y; val[4 * j + 2] += rv.z; val[4 * j + 3] += rv.w;
+            }
+            ++rc;
+          }
+          // staging buffer (sc & 1) must no longer be read by the TMA store issued two chunks ago
+          if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          epi_bar();
+          const uint32_t obuf = stg_out + (uint32_t)(sc & 1) * T2_STG_BYTES;
+          if (p.out_bf16) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint32_t w[4];
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(val[8 * j + 2 * h], val[8 * j + 2 * h + 1]);
+                w[h] = *reinterpret_cast<uint32_t*>(&b2);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(obuf + swz(r, j)), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                           "r"(w[3])
+                           : "memory");
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(obuf + swz(r, j)), "f"(val[4 * j]), "f"(val[4 * j + 1]),
+                           "f"(val[4 * j + 2]), "f"(val[4 * j + 3])
+                           : "memory");
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          epi_bar();
+          if (elected) {
+            tma_st4(&tmO, obuf, n0 + c * CW, x0, y0, b0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          if (p.ch_stats) {
+            // per-channel partial sums over this tile's rows, read back from the staged (rounded) values:
+            // thread -> column (et % CW), rows [(et / CW) * CW, +CW)
+            const int col = et % CW, r0 = (et / CW) * CW;
+            float s = 0.f, qq = 0.f;
+            int cur = r0 / ppi;
+            for (int rr = r0; rr < r0 + CW; ++rr) {
+              const int img = rr / ppi;
+              if (img != cur) {
+                if (b0 + cur < p.B) {
+                  float* dst = p.ch_stats + ((long long)(b0 + cur) * p.Cout + n0 + c * CW + col) * 2;
+                  atomicAdd(dst, s);
+                  atomicAdd(dst + 1, qq);
+                }
+                s = qq = 0.f;
+                cur = img;
+              }
+              float x;
+              if (p.out_bf16) {
+                unsigned short h;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(obuf + swz(rr, col >> 3) + (uint32_t)((col & 7) * 2)));
+                x = __uint_as_float(((uint32_t)h) << 16);
+              } else {
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(obuf + swz(rr, col >> 2) + (uint32_t)((col & 3) * 4)));
+              }
+              s += x;
+              qq = fmaf(x, x, qq);
+            }
+            if (b0 + cur < p.B) {
+              float* dst = p.ch_stats + ((long long)(b0 + cur) * p.Cout + n0 + c * CW + col) * 2;
+              atomicAdd(dst, s);
+              atomicAdd(dst + 1, qq);
+            }
+          }
+          ++sc;
+        }
+      }
+      // accumulator buffer fully read by every epilogue thread -> hand it back to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      epi_bar();
+      if (elected) mb_arrive(s_u32(&bar_acc_empty[ab]));
+    }
+    if (elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn2 encode_fn2() {
+  static EncodeTiledFn2 fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  fn = (EncodeTiledFn2)sym;
+  return fn;
+}
+
+static int pow2_tile(int W, int cap) {
+  int t = 1;
+  while (t * 2 <= cap && W % (t * 2) == 0) t *= 2;
+  return t;
+}
+
+template <int BN>
+static cudaError_t launch_tc2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& r,
+                              const ConvTc2Args& args, int grid, size_t smem, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  conv_tc2_kernel<BN><<<grid, T2_THREADS, smem, s>>>(a, b, o, r, args);
+  return cudaPeekAtLastError();
+}
+
+}  // namespace pdae
+
+using namespace pdae;
+
+struct pdae_conv_tc2_plan {
+  CUtensorMap tmA, tmB, tmO, tmR;
+  ConvTc2Args args;
+  int BN, grid;
+  size_t smem;
+};
+
+static int g_num_sms = 0;
+
+extern "C" int pdae_conv_tc2_create(pdae_conv_tc2_plan** plan_out, const void* in_bf16, const void* w_bf16, const float* bias,
+                                    const float* residual, void* out, int out_dtype, float* ch_stats, int B, int H, int W,
+                                    int Cin, int Cout, int ksize, int cout_valid, int bn_override) {
+  PDAE_REQUIRE(plan_out && in_bf16 && w_bf16 && out, "conv_tc2_create: null pointer");
+  PDAE_REQUIRE(ksize == 1 || ksize == 3, "conv_tc2_create: ksize must be 1 or 3");
+  PDAE_REQUIRE(Cin % T2_BK == 0, "conv_tc2_create: Cin=%d not a multiple of 64", Cin);
+  const bool head = cout_valid > 0;
+  PDAE_REQUIRE(head ? (Cout == 16 && cout_valid <= 16 && out_dtype == PDAE_F32 && !residual && !ch_stats) : (Cout % 64 == 0),
+               "conv_tc2_create: unsupported Cout=%d (cout_valid=%d)", Cout, cout_valid);
+  PDAE_REQUIRE(out_dtype == PDAE_F32 || out_dtype == PDAE_BF16, "conv_tc2_create: bad out dtype");
+  PDAE_REQUIRE(!(residual && out_dtype != PDAE_F32), "conv_tc2_create: a residual needs an fp32 output");
+  PDAE_REQUIRE(((uintptr_t)in_bf16 & 15) == 0 && ((uintptr_t)w_bf16 & 15) == 0 && ((uintptr_t)out & 15) == 0 &&
+                   ((uintptr_t)residual & 15) == 0 && ((uintptr_t)bias & 15) == 0,
+               "conv_tc2_create: pointers must be 16-byte aligned");
+  EncodeTiledFn2 enc = encode_fn2();
+  PDAE_REQUIRE(enc != nullptr, "conv_tc2_create: cuTensorMapEncodeTiled unavailable (no driver)");
+  if (g_num_sms == 0) {
+    int dev = 0;
+    PDAE_CUDA(cudaGetDevice(&dev));
+    PDAE_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  pdae_conv_tc2_plan* pl = new pdae_conv_tc2_plan();
+  ConvTc2Args& a = pl->args;
+  a.bias = bias; a.ch_stats = ch_stats; a.out_nchw = head ? (float*)out : nullptr;
+  a.B = B; a.H = H; a.W = W; a.Cout = Cout;
+  a.tw = pow2_tile(W, T2_BM);
+  a.th = pow2_tile(H, T2_BM / a.tw);
+  a.tn = T2_BM / (a.tw * a.th);
+  if (W % a.tw != 0 || H % a.th != 0 || a.tw * a.th * a.tn != T2_BM || a.tn > 256) {
+    delete pl;
+    PDAE_REQUIRE(false, "conv_tc2_create: H=%d W=%d cannot be tiled into 128-pixel boxes", H, W);
+  }
+  a.tiles_x = W / a.tw; a.tiles_y = H / a.th; a.tiles_b = (B + a.tn - 1) / a.tn;
+  a.tiles_m = a.tiles_x * a.tiles_y * a.tiles_b;
+  a.taps = ksize * ksize; a.ksize = ksize; a.kblocks = Cin / T2_BK;
+  a.has_res = residual != nullptr; a.out_bf16 = out_dtype == PDAE_BF16; a.cout_valid = cout_valid;
+  int BN;
+  if (head) BN = 16;
+  else if (bn_override == 64 || bn_override == 128 || bn_override == 256) BN = bn_override;
+  else BN = (Cout % 128 == 0) ? 128 : 64;
+  if (!head && Cout % BN != 0) {
+    delete pl;
+    PDAE_REQUIRE(false, "conv_tc2_create: Cout=%d not a multiple of BN=%d", Cout, BN);
+  }
+  pl->BN = BN;
+  a.tiles_total = a.tiles_m * (head ? 1 : Cout / BN);
+  const int b_bytes = ((BN * T2_BK * 2 + 1023) / 1024) * 1024;
+  const int stage_bytes = T2_A_BYTES + b_bytes;
+  const int staging = head ? 0 : (a.has_res ? 4 : 2) * T2_STG_BYTES;
+  int stages = (220 * 1024 - 1024 - staging) / stage_bytes;
+  if (stages > T2_MAX_STAGES) stages = T2_MAX_STAGES;
+  if (stages > a.taps * a.kblocks) stages = a.taps * a.kblocks;
+  if (stages < 2) stages = 2;
+  a.stages = stages;
+  pl->smem = (size_t)stages * stage_bytes + staging + 1024;
+  pl->grid = a.tiles_total < g_num_sms ? a.tiles_total : g_num_sms;
+
+  auto fail = [&](const char* what, int code) {
+    delete pl;
+    set_error("conv_tc2_create: cuTensorMapEncodeTiled(%s) failed with %d", what, code);
+    return PDAE_EINVAL;
+  };
+  cuuint32_t estr4[4] = {1, 1, 1, 1};
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)T2_BK, (cuuint32_t)a.tw, (cuuint32_t)a.th, (cuuint32_t)a.tn};
+    CUresult r = enc(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in_bf16), dims, strides, box, estr4,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("A", (int)r);
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)a.taps};
+    cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
+    cuuint32_t box[3] = {(cuuint32_t)T2_BK, (cuuint32_t)BN, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&pl->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_bf16), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("W", (int)r);
+  }
+  pl->tmO = pl->tmA;
+  pl->tmR = pl->tmA;
+  if (!head) {
+    const int esz = a.out_bf16 ? 2 : 4;
+    cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)Cout * esz, (cuuint64_t)W * Cout * esz, (cuuint64_t)H * W * Cout * esz};
+    cuuint32_t box[4] = {(cuuint32_t)(a.out_bf16 ? 64 : 32), (cuuint32_t)a.tw, (cuuint32_t)a.th, (cuuint32_t)a.tn};
+    CUresult r = enc(&pl->tmO, a.out_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, dims,
+                     strides, box, estr4, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("O", (int)r);
+    if (a.has_res) {
+      cuuint64_t rstr[3] = {(cuuint64_t)Cout * 4, (cuuint64_t)W * Cout * 4, (cuuint64_t)H * W * Cout * 4};
+      cuuint32_t rbox[4] = {32, (cuuint32_t)a.tw, (cuuint32_t)a.th, (cuuint32_t)a.tn};
+      r = enc(&pl->tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(residual), dims, rstr, rbox, estr4,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail("R", (int)r);
+    }
+  }
+  *plan_out = pl;
+  return PDAE_OK;
+}
+
+extern "C" int pdae_conv_tc2_run(const pdae_conv_tc2_plan* pl, pdae_stream_t stream) {
+  PDAE_REQUIRE(pl, "conv_tc2_run: null plan");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e;
+  switch (pl->BN) {
+    case 16: e = launch_tc2<16>(pl->tmA, pl->tmB, pl->tmO, pl->tmR, pl->args, pl->grid, pl->smem, s); break;
+    case 64: e = launch_tc2<64>(pl->tmA, pl->tmB, pl->tmO, pl->tmR, pl->args, pl->grid, pl->smem, s); break;
+    case 128: e = launch_tc2<128>(pl->tmA, pl->tmB, pl->tmO, pl->tmR, pl->args, pl->grid, pl->smem, s); break;
+    default: e = launch_tc2<256>(pl->tmA, pl->tmB, pl->tmO, pl->tmR, pl->args, pl->grid, pl->smem, s); break;
+  }
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    set_error("launch of conv_tc2_kernel<%d> failed: %s", pl->BN, cudaGetErrorString(e));
+    return PDAE_ECUDA;
+  }
+  return PDAE_OK;
+}
+
+extern "C" void pdae_conv_tc2_destroy(pdae_conv_tc2_plan* pl) { delete pl; }

@@ -61,6 +61,82 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
   }
 }
 
+// per-channel (sum, sum^2) fp32 accumulators [B][C][2] -- the form the tensor-core conv epilogue produces
+__global__ void __launch_bounds__(256) ch_stats_kernel(const float* __restrict__ src, int C, int HW, float* __restrict__ chs) {
+  extern __shared__ float sh[];  // [2][C]
+  const int L = C >> 2;
+  const int Lb = L < 256 ? L : 256;
+  const int R = 256 / Lb;
+  const int tid = threadIdx.x;
+  const int lane = tid % Lb, row = tid / Lb;
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * STATS_PIX;
+  const int p1 = min(HW, p0 + STATS_PIX);
+  for (int i = tid; i < 2 * C; i += 256) sh[i] = 0.f;
+  __syncthreads();
+  if (row < R) {
+    for (int cq = lane; cq < L; cq += Lb) {
+      const int c = cq * 4;
+      const float* base = src + (long long)b * HW * C + c;
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+      for (int p = p0 + row; p < p1; p += R) {
+        const float4 v = *reinterpret_cast<const float4*>(base + (long long)p * C);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+      }
+      atomicAdd(&sh[c + 0], s.x); atomicAdd(&sh[c + 1], s.y); atomicAdd(&sh[c + 2], s.z); atomicAdd(&sh[c + 3], s.w);
+      atomicAdd(&sh[C + c + 0], q.x); atomicAdd(&sh[C + c + 1], q.y); atomicAdd(&sh[C + c + 2], q.z); atomicAdd(&sh[C + c + 3], q.w);
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += 256) {
+    atomicAdd(&chs[((long long)b * C + c) * 2 + 0], sh[c]);
+    atomicAdd(&chs[((long long)b * C + c) * 2 + 1], sh[C + c]);
+  }
+}
+
+// GroupNorm coefficients from per-channel sums of a virtual concat [chs1 (C1) | chs2 (C2)]
+__global__ void gn_coef_ch_kernel(const float* __restrict__ chs1, int C1, const float* __restrict__ chs2, int C2,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta, int HW, float eps,
+                                  const float* __restrict__ emb, int emb_ld, const float* __restrict__ embz, int embz_ld,
+                                  float* __restrict__ ab) {
+  __shared__ double gs[32][2];
+  const int b = blockIdx.x;
+  const int C = C1 + C2, cpg = C / 32;
+  if (threadIdx.x < 64) {
+    const int g = threadIdx.x & 31, which = threadIdx.x >> 5;
+    double a = 0.0;
+    for (int j = 0; j < cpg; ++j) {
+      const int c = g * cpg + j;
+      a += (double)(c < C1 ? chs1[((long long)b * C1 + c) * 2 + which] : chs2[((long long)b * C2 + (c - C1)) * 2 + which]);
+    }
+    gs[g][which] = a;
+  }
+  __syncthreads();
+  const double n = (double)HW * cpg;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const double mean = gs[g][0] / n;
+    double var = gs[g][1] / n - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    float a = gamma[c] * rstd;
+    float bb = beta[c] - (float)mean * a;
+    if (emb) {
+      const float s = 1.0f + emb[(long long)b * emb_ld + c], shv = emb[(long long)b * emb_ld + C + c];
+      a *= s;
+      bb = bb * s + shv;
+    }
+    if (embz) {
+      const float s = 1.0f + embz[(long long)b * embz_ld + c], shv = embz[(long long)b * embz_ld + C + c];
+      a *= s;
+      bb = bb * s + shv;
+    }
+    ab[((long long)b * 2 + 0) * C + c] = a;
+    ab[((long long)b * 2 + 1) * C + c] = bb;
+  }
+}
+
 __global__ void gn_coef_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
                                const float* __restrict__ beta, int C, int HW, float eps,
                                const float* __restrict__ emb, int emb_ld, const float* __restrict__ embz, int embz_ld,
@@ -100,8 +176,8 @@ __device__ __forceinline__ float4 affine_act(float4 v, float4 a, float4 b, int s
   return r;
 }
 
-template <typename TAct, typename TRaw, int RS>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ s1, int C1,
+template <typename TSrc, typename TAct, typename TRaw, int RS>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const TSrc* __restrict__ s1, int C1,
                                                        const float* __restrict__ s2, int C2,
                                                        const float* __restrict__ ab, int silu, int H, int W,
                                                        TAct* __restrict__ out_act, TRaw* __restrict__ out_raw) {
@@ -117,10 +193,13 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
     const long long pix = it / L;
     const int x = (int)(pix % Wi), y = (int)(pix / Wi);
     const int c = cq * 4;
-    const float* base;
-    int cs, cc;
-    if (c < C1) { base = s1; cs = C1; cc = c; } else { base = s2; cs = C2; cc = c - C1; }
-    base += (long long)b * H * W * cs + cc;
+    // source 1 may be bf16 (a conv output kept in bf16); source 2 (a skip tensor) is always fp32
+    const bool first = c < C1;
+    const int cs = first ? C1 : C2, cc = first ? c : c - C1;
+    const long long boff = (long long)b * H * W * cs + cc;
+    auto ld = [&](long long pixoff) -> float4 {
+      return first ? load4<TSrc>(s1 + boff + pixoff * cs) : load4<float>(s2 + boff + pixoff * cs);
+    };
     float4 a = make_float4(1.f, 1.f, 1.f, 1.f), bb = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ab) {
       a = *reinterpret_cast<const float4*>(ab + ((long long)b * 2 + 0) * C + c);
@@ -132,7 +211,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
       for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 2; ++dx) {
-          const float4 v = *reinterpret_cast<const float4*>(base + ((long long)(2 * y + dy) * W + 2 * x + dx) * cs);
+          const float4 v = ld((long long)(2 * y + dy) * W + 2 * x + dx);
           const float4 r = affine_act(v, a, bb, silu);
           accA.x += r.x; accA.y += r.y; accA.z += r.z; accA.w += r.w;
           accR.x += v.x; accR.y += v.y; accR.z += v.z; accR.w += v.w;
@@ -141,7 +220,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
       store4<TAct>(out_act + o, make_float4(accA.x * 0.25f, accA.y * 0.25f, accA.z * 0.25f, accA.w * 0.25f));
       if (out_raw) store4<TRaw>(out_raw + o, make_float4(accR.x * 0.25f, accR.y * 0.25f, accR.z * 0.25f, accR.w * 0.25f));
     } else {
-      const float4 v = *reinterpret_cast<const float4*>(base + ((long long)y * W + x) * cs);
+      const float4 v = ld((long long)y * W + x);
       const float4 r = affine_act(v, a, bb, silu);
       if (RS == PDAE_RESAMPLE_UP2) {
 #pragma unroll
@@ -335,9 +414,40 @@ extern "C" int pdae_gn_coef(const double* sums, const float* gamma, const float*
   return PDAE_OK;
 }
 
-template <typename TAct, typename TRaw>
-static int launch_apply(const float* s1, int C1, const float* s2, int C2, const float* ab, int silu, int resample, int B,
+extern "C" int pdae_zero(void* ptr, int64_t bytes, pdae_stream_t stream) {
+  PDAE_REQUIRE(ptr && bytes >= 0, "zero: bad args");
+  PDAE_CUDA(cudaMemsetAsync(ptr, 0, (size_t)bytes, (cudaStream_t)stream));
+  return PDAE_OK;
+}
+
+extern "C" int pdae_ch_stats(const float* src, int B, int HW, int C, float* chs, pdae_stream_t stream) {
+  PDAE_REQUIRE(src && chs, "ch_stats: null pointer");
+  PDAE_REQUIRE(C % 4 == 0 && C > 0 && (size_t)2 * C * sizeof(float) <= 48 * 1024, "ch_stats: C=%d unsupported", C);
+  cudaStream_t s = (cudaStream_t)stream;
+  PDAE_CUDA(cudaMemsetAsync(chs, 0, (size_t)B * C * 2 * sizeof(float), s));
+  dim3 grid(cdiv(HW, STATS_PIX), B);
+  ch_stats_kernel<<<grid, 256, 2 * C * sizeof(float), s>>>(src, C, HW, chs);
+  PDAE_LAUNCH_CHECK("ch_stats_kernel");
+  return PDAE_OK;
+}
+
+extern "C" int pdae_gn_coef_ch(const float* chs1, int C1, const float* chs2, int C2, const float* gamma, const float* beta,
+                               int B, int HW, float eps, const float* emb, int emb_ld, const float* embz, int embz_ld,
+                               float* ab, pdae_stream_t stream) {
+  PDAE_REQUIRE(chs1 && gamma && beta && ab, "gn_coef_ch: null pointer");
+  if (!chs2) C2 = 0;
+  const int C = C1 + C2;
+  PDAE_REQUIRE(C % 32 == 0, "gn_coef_ch: C %% 32 != 0");
+  gn_coef_ch_kernel<<<B, C < 1024 ? (C < 64 ? 64 : C) : 1024, 0, (cudaStream_t)stream>>>(chs1, C1, chs2, C2, gamma, beta, HW,
+                                                                                          eps, emb, emb_ld, embz, embz_ld, ab);
+  PDAE_LAUNCH_CHECK("gn_coef_ch_kernel");
+  return PDAE_OK;
+}
+
+template <typename TSrc, typename TAct, typename TRaw>
+static int launch_apply(const void* s1v, int C1, const float* s2, int C2, const float* ab, int silu, int resample, int B,
                         int H, int W, void* out_act, void* out_raw, cudaStream_t s) {
+  const TSrc* s1 = (const TSrc*)s1v;
   const int L = (C1 + C2) / 4;
   const int Hi = resample == PDAE_RESAMPLE_DOWN2 ? H / 2 : H, Wi = resample == PDAE_RESAMPLE_DOWN2 ? W / 2 : W;
   const long long items = (long long)Hi * Wi * L;
@@ -347,16 +457,16 @@ static int launch_apply(const float* s1, int C1, const float* s2, int C2, const 
   TAct* oa = (TAct*)out_act;
   TRaw* orw = (TRaw*)out_raw;
   if (resample == PDAE_RESAMPLE_NONE)
-    gn_apply_kernel<TAct, TRaw, PDAE_RESAMPLE_NONE><<<grid, 256, 0, s>>>(s1, C1, s2, C2, ab, silu, H, W, oa, orw);
+    gn_apply_kernel<TSrc, TAct, TRaw, PDAE_RESAMPLE_NONE><<<grid, 256, 0, s>>>(s1, C1, s2, C2, ab, silu, H, W, oa, orw);
   else if (resample == PDAE_RESAMPLE_UP2)
-    gn_apply_kernel<TAct, TRaw, PDAE_RESAMPLE_UP2><<<grid, 256, 0, s>>>(s1, C1, s2, C2, ab, silu, H, W, oa, orw);
+    gn_apply_kernel<TSrc, TAct, TRaw, PDAE_RESAMPLE_UP2><<<grid, 256, 0, s>>>(s1, C1, s2, C2, ab, silu, H, W, oa, orw);
   else
-    gn_apply_kernel<TAct, TRaw, PDAE_RESAMPLE_DOWN2><<<grid, 256, 0, s>>>(s1, C1, s2, C2, ab, silu, H, W, oa, orw);
+    gn_apply_kernel<TSrc, TAct, TRaw, PDAE_RESAMPLE_DOWN2><<<grid, 256, 0, s>>>(s1, C1, s2, C2, ab, silu, H, W, oa, orw);
   PDAE_LAUNCH_CHECK("gn_apply_kernel");
   return PDAE_OK;
 }
 
-extern "C" int pdae_gn_apply(const float* src1, int C1, const float* src2, int C2, const float* ab, int silu,
+extern "C" int pdae_gn_apply(const void* src1, int src1_dtype, int C1, const float* src2, int C2, const float* ab, int silu,
                              int resample, int B, int H, int W, void* out_act, int act_dtype, void* out_raw,
                              int raw_dtype, pdae_stream_t stream) {
   PDAE_REQUIRE(src1 && out_act, "gn_apply: null pointer");
@@ -366,12 +476,17 @@ extern "C" int pdae_gn_apply(const float* src1, int C1, const float* src2, int C
   PDAE_REQUIRE(resample != PDAE_RESAMPLE_DOWN2 || (H % 2 == 0 && W % 2 == 0), "gn_apply: odd dims for DOWN2");
   cudaStream_t s = (cudaStream_t)stream;
   typedef __nv_bfloat16 bf;
+  if (src1_dtype == PDAE_BF16) {
+    PDAE_REQUIRE(act_dtype == PDAE_BF16 && !out_raw, "gn_apply: a bf16 source supports a bf16 activation output only");
+    return launch_apply<bf, bf, float>(src1, C1, src2, C2, ab, silu, resample, B, H, W, out_act, nullptr, s);
+  }
+  PDAE_REQUIRE(src1_dtype == PDAE_F32, "gn_apply: bad source dtype");
   if (act_dtype == PDAE_F32 && raw_dtype == PDAE_F32)
-    return launch_apply<float, float>(src1, C1, src2, C2, ab, silu, resample, B, H, W, out_act, out_raw, s);
+    return launch_apply<float, float, float>(src1, C1, src2, C2, ab, silu, resample, B, H, W, out_act, out_raw, s);
   if (act_dtype == PDAE_BF16 && raw_dtype == PDAE_F32)
-    return launch_apply<bf, float>(src1, C1, src2, C2, ab, silu, resample, B, H, W, out_act, out_raw, s);
+    return launch_apply<float, bf, float>(src1, C1, src2, C2, ab, silu, resample, B, H, W, out_act, out_raw, s);
   if (act_dtype == PDAE_BF16 && raw_dtype == PDAE_BF16)
-    return launch_apply<bf, bf>(src1, C1, src2, C2, ab, silu, resample, B, H, W, out_act, out_raw, s);
+    return launch_apply<float, bf, bf>(src1, C1, src2, C2, ab, silu, resample, B, H, W, out_act, out_raw, s);
   PDAE_REQUIRE(false, "gn_apply: unsupported dtype combination act=%d raw=%d", act_dtype, raw_dtype);
 }
 

@@ -15,6 +15,7 @@ Precision modes
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -98,6 +99,8 @@ class Plan:
         self.device = device
         self.precision = precision or _default_precision
         self.tc = self.precision == "bf16"
+        self.v2 = os.environ.get("PDAE_TC_V1", "0") != "1"       # persistent v2 conv kernel (default) vs the simple v1
+        self.bn_override = int(os.environ.get("PDAE_TC_BN", "0"))  # tuning aid: force the N tile of the v2 kernel
         self.L = _native.lib()
         self.ops: List[Tuple[str, list]] = []
         self.bufs: List[Buf] = []
@@ -106,6 +109,7 @@ class Plan:
         self._pack_cache: Dict[tuple, Buf] = {}
         self._compiled = None
         self._tc_handles: List[ctypes.c_void_p] = []
+        self._tc2_handles: List[ctypes.c_void_p] = []
         self.n_launch = 0
         self.graph = None
         self.flops: List[float] = []  # algorithmic FLOPs (2*MACs) per recorded op, 0 for non-contraction ops
@@ -200,6 +204,9 @@ class Plan:
             if fn == "conv_tc":
                 compiled.append(self._compile_tc(args))
                 continue
+            if fn == "conv_tc2":
+                compiled.append(self._compile_tc2(args))
+                continue
             cargs = []
             sidx = -1
             for k, a in enumerate(args):
@@ -230,10 +237,22 @@ class Plan:
         self._tc_handles.append(h)
         return (self.L.pdae_conv_tc_run, [h, None], 1, "conv_tc")
 
+    def _compile_tc2(self, args):
+        x, w, bias, resid, out, odt, stats, B, H, W, Cin, Cout, k, cout_valid, bn = args
+        h = ctypes.c_void_p()
+        rc = self.L.pdae_conv_tc2_create(ctypes.byref(h), self._resolve(x), self._resolve(w), self._resolve(bias),
+                                         self._resolve(resid), self._resolve(out), odt, self._resolve(stats), B, H, W, Cin,
+                                         Cout, k, cout_valid, bn)
+        _native.check(rc, "pdae_conv_tc2_create")
+        self._tc2_handles.append(h)
+        return (self.L.pdae_conv_tc2_run, [h, None], 1, "conv_tc2")
+
     def __del__(self):
         try:
             for h in self._tc_handles:
                 self.L.pdae_conv_tc_destroy(h)
+            for h in self._tc2_handles:
+                self.L.pdae_conv_tc2_destroy(h)
         except Exception:
             pass
 
@@ -313,20 +332,33 @@ class Plan:
 
     def conv(self, x: Buf, weight: torch.Tensor, bias: Optional[torch.Tensor], out: Buf, *, B, H, W, Cin, Cout, k=3,
              stride=1, pad=None, residual: Optional[Buf] = None, in_nchw=False, out_nchw=False, a_silu=False,
-             wkey=None) -> None:
-        """weight: nn-style [Cout, Cin, k, k] / [Cout, Cin, 1] / [Cout, Cin] parameter."""
+             wkey=None, want_stats=False, bn_override=0) -> Optional[Buf]:
+        """weight: nn-style [Cout, Cin, k, k] / [Cout, Cin, 1] / [Cout, Cin] parameter.
+        Returns the per-channel (sum, sum^2) buffer [B][Cout][2] if the tensor-core epilogue produced one."""
         pad = k // 2 if pad is None else pad
         bias_b = self.param(bias)
         wkey = wkey or id(weight)
         if x.dtype == torch.bfloat16 and self.use_tc(Cin, Cout, k, stride, H, W) and not (in_nchw or out_nchw or a_silu):
             wp = self.pack((wkey, "tc"), [weight],
                            lambda: weight.detach().reshape(Cout, Cin, k * k).permute(2, 0, 1).to(torch.bfloat16))
-            self.call("conv_tc", x, wp, bias_b, residual, out, B, H, W, Cin, Cout, k, flops=2.0 * B * H * W * Cout * Cin * k * k)
-            return
+            fl = 2.0 * B * H * W * Cout * Cin * k * k
+            if not self.v2:
+                assert out.dtype == torch.float32
+                self.call("conv_tc", x, wp, bias_b, residual, out, B, H, W, Cin, Cout, k, flops=fl)
+                return None
+            stats = None
+            if want_stats:
+                stats = self.new((B, Cout, 2), torch.float32, "chs")
+                self.call("zero", stats, ctypes.c_int64(B * Cout * 8), _STREAM)
+            self.call("conv_tc2", x, wp, bias_b, residual, out, _DT[out.dtype], stats, B, H, W, Cin, Cout, k, 0,
+                      bn_override or self.bn_override, flops=fl)
+            return stats
+        assert out.dtype == torch.float32, "CUDA-core conv writes fp32"
         wp = self.pack((wkey, "simt"), [weight], lambda: weight.detach().reshape(Cout, Cin, k * k).permute(2, 1, 0).float())
         Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
         self.call("conv2d_simt", x, _DT[x.dtype], int(in_nchw), wp, bias_b, residual, out, int(out_nchw), B, H, W, Cin, Cout,
                   k, stride, pad, int(a_silu), _STREAM, flops=2.0 * B * Ho * Wo * Cout * Cin * k * k)
+        return None
 
     def linear(self, x: Buf, weight: torch.Tensor, bias: Optional[torch.Tensor], out: Buf, *, B, Cin, Cout, a_silu=False,
                wkey=None) -> None:
@@ -338,25 +370,55 @@ class Plan:
                   flops=2.0 * B * Cin * Cout)
 
     def head_conv(self, x: Buf, weight: torch.Tensor, bias: torch.Tensor, out_nchw: Buf, *, B, H, W, Cin, Cout) -> None:
-        """3x3 conv to a few image channels (unet.py:171-175): bandwidth kernel for Cout <= 4."""
-        if Cout <= 4 and Cin % 4 == 0:
+        """3x3 conv to a few image channels (unet.py:171-175)."""
+        fl = 2.0 * B * H * W * Cout * Cin * 9
+        if self.v2 and x.dtype == torch.bfloat16 and Cout <= 16 and self.use_tc(Cin, 64, 3, 1, H, W):
+            # tensor-core head: Cout zero-padded to one 16-wide UMMA tile, NCHW fp32 planes written by the epilogue
+            def pack16():
+                w = weight.detach().reshape(Cout, Cin, 9).permute(2, 0, 1)
+                z = torch.zeros(9, 16, Cin, device=w.device, dtype=torch.bfloat16)
+                z[:, :Cout, :] = w.to(torch.bfloat16)
+                return z
+            wp = self.pack((id(weight), "tc16"), [weight], pack16)
+            self.call("conv_tc2", x, wp, self.param(bias), None, out_nchw, PDAE_F32, None, B, H, W, Cin, 16, 3, Cout, 0, flops=fl)
+        elif Cout <= 4 and Cin % 4 == 0:
             def pack4():
                 w = weight.detach().reshape(Cout, Cin, 9).permute(2, 1, 0).float()
                 z = torch.zeros(9, Cin, 4, device=w.device, dtype=torch.float32)
                 z[:, :, :Cout] = w
                 return z
             wp = self.pack((id(weight), "small4"), [weight], pack4)
-            self.call("conv3x3_smalln", x, _DT[x.dtype], wp, self.param(bias), out_nchw, B, H, W, Cin, Cout, _STREAM,
-                      flops=2.0 * B * H * W * Cout * Cin * 9)
+            self.call("conv3x3_smalln", x, _DT[x.dtype], wp, self.param(bias), out_nchw, B, H, W, Cin, Cout, _STREAM, flops=fl)
         else:
+            assert x.dtype == torch.float32
             self.conv(x, weight, bias, out_nchw, B=B, H=H, W=W, Cin=Cin, Cout=Cout, k=3, out_nchw=True)
 
+    def ch_stats(self, src: Buf, C: int, *, B, HW) -> Buf:
+        """Per-channel (sum, sum^2) of an fp32 NHWC tensor that no conv epilogue produced."""
+        chs = self.new((B, C, 2), torch.float32, "chs")
+        self.call("ch_stats", src, B, HW, C, chs, _STREAM)
+        return chs
+
+    @property
+    def fused_stats(self) -> bool:
+        return self.tc and self.v2
+
     def gn_coef(self, src1: Buf, C1: int, src2: Optional[Buf], C2: int, gamma, beta, *, B, HW, emb=None, emb_ld=0,
-                embz=None, embz_ld=0) -> Buf:
+                embz=None, embz_ld=0, stats1: Optional[Buf] = None, stats2: Optional[Buf] = None) -> Buf:
+        """GroupNorm(32) statistics -> per-(b,c) affine coefficients.  bf16/v2 mode consumes the per-channel sums the
+        conv epilogues accumulated (computing missing ones); fp32 mode keeps the fp64 two-kernel path."""
         C = C1 + C2
+        ab = self.new((B, 2, C), torch.float32, "gn_ab")
+        if self.fused_stats:
+            if stats1 is None:
+                stats1 = self.ch_stats(src1, C1, B=B, HW=HW)
+            if src2 is not None and stats2 is None:
+                stats2 = self.ch_stats(src2, C2, B=B, HW=HW)
+            self.call("gn_coef_ch", stats1, C1, stats2, C2, self.param(gamma), self.param(beta), B, HW, ctypes.c_float(1e-5),
+                      emb, emb_ld, embz, embz_ld, ab, _STREAM)
+            return ab
         sums = self.new((B, 32, 2), torch.float64, "gn_sums")
         self.call("gn_stats", src1, C1, src2, C2, B, HW, sums, _STREAM)
-        ab = self.new((B, 2, C), torch.float32, "gn_ab")
         self.call("gn_coef", sums, self.param(gamma), self.param(beta), B, C, HW, ctypes.c_float(1e-5), emb, emb_ld, embz,
                   embz_ld, ab, _STREAM)
         return ab
@@ -367,9 +429,9 @@ class Plan:
         Ho, Wo = (2 * H, 2 * W) if resample == RESAMPLE_UP2 else ((H // 2, W // 2) if resample == RESAMPLE_DOWN2 else (H, W))
         act = self.new((B, Ho, Wo, C), act_dtype, "act")
         raw = self.new((B, Ho, Wo, C), raw_dtype, "raw") if raw_dtype is not None else None
-        self.call("gn_apply", src1, C1, src2, C2, ab, int(silu), resample, B, H, W, act, _DT[act_dtype], raw,
+        self.call("gn_apply", src1, _DT[src1.dtype], C1, src2, C2, ab, int(silu), resample, B, H, W, act, _DT[act_dtype], raw,
                   _DT[raw_dtype] if raw_dtype is not None else PDAE_F32, _STREAM)
         return act, raw
 
 
-_LAUNCHES = {"gn_stats": 1, "attention_simt": 3}
+_LAUNCHES = {"gn_stats": 1, "attention_simt": 3, "zero": 0}

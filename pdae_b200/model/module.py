@@ -108,10 +108,12 @@ def timestep_embedding(timesteps: torch.Tensor, dim: int, max_period: int = 1000
 class Src:
     """An NHWC fp32 activation, possibly the virtual channel-concat of two tensors (skip connections are
     never materialised: unet.py:199-200 / shift_unet.py:276-281 ``torch.cat([h, hs.pop()], 1)``)."""
-    __slots__ = ("b1", "C1", "b2", "C2", "B", "H", "W")
+    __slots__ = ("b1", "C1", "b2", "C2", "B", "H", "W", "s1", "s2")
 
-    def __init__(self, b1: Buf, C1: int, B: int, H: int, W: int, b2: Optional[Buf] = None, C2: int = 0):
+    def __init__(self, b1: Buf, C1: int, B: int, H: int, W: int, b2: Optional[Buf] = None, C2: int = 0,
+                 s1: Optional[Buf] = None, s2: Optional[Buf] = None):
         self.b1, self.C1, self.b2, self.C2, self.B, self.H, self.W = b1, C1, b2, C2, B, H, W
+        self.s1, self.s2 = s1, s2  # per-channel (sum, sum^2) buffers accumulated by the producing conv's epilogue
 
     @property
     def C(self) -> int:
@@ -119,7 +121,7 @@ class Src:
 
     def cat(self, other: "Src") -> "Src":
         assert self.b2 is None and other.b2 is None and (self.B, self.H, self.W) == (other.B, other.H, other.W)
-        return Src(self.b1, self.C1, self.B, self.H, self.W, other.b1, other.C1)
+        return Src(self.b1, self.C1, self.B, self.H, self.W, other.b1, other.C1, self.s1, other.s1)
 
 
 class PlannedModule(nn.Module):
@@ -245,7 +247,7 @@ class _ResBase(PlannedModule):
         gn1, gn2 = self.in_layers[0], self.out_layers[0]
         ident = isinstance(self.skip_connection, nn.Identity)
 
-        ab1 = P.gn_coef(x.b1, x.C1, x.b2, x.C2, gn1.weight, gn1.bias, B=B, HW=H * W)
+        ab1 = P.gn_coef(x.b1, x.C1, x.b2, x.C2, gn1.weight, gn1.bias, B=B, HW=H * W, stats1=x.s1, stats2=x.s2)
         tc1 = P.use_tc(C, Co, 3, 1, H2, W2)
         # raw (un-normalised) copy of the possibly concatenated / resampled input for the skip path
         raw_dtype = None
@@ -261,15 +263,17 @@ class _ResBase(PlannedModule):
                 raw_dtype = torch.float32
         act1, raw = P.gn_apply(x.b1, x.C1, x.b2, x.C2, ab1, silu=True, resample=rs, B=B, H=H, W=W,
                                act_dtype=torch.bfloat16 if tc1 else torch.float32, raw_dtype=raw_dtype)
-        h = P.new((B, H2, W2, Co), torch.float32, "res_h")
-        P.conv(act1, conv1.weight, conv1.bias, h, B=B, H=H2, W=W2, Cin=C, Cout=Co, k=3)
+        # h only feeds GroupNorm-2: with the v2 kernel it is stored in bf16 and its statistics come from the epilogue
+        h_bf16 = tc1 and P.fused_stats
+        h = P.new((B, H2, W2, Co), torch.bfloat16 if h_bf16 else torch.float32, "res_h")
+        hs = P.conv(act1, conv1.weight, conv1.bias, h, B=B, H=H2, W=W2, Cin=C, Cout=Co, k=3, want_stats=True)
 
         eb, eoff, eld = emb
         zb = zoff = zld = None
         if self.has_z:
             zb, zoff, zld = embz
         ab2 = P.gn_coef(h, Co, None, 0, gn2.weight, gn2.bias, B=B, HW=H2 * W2, emb=eb.at(eoff), emb_ld=eld,
-                        embz=zb.at(zoff) if zb is not None else None, embz_ld=zld or 0)
+                        embz=zb.at(zoff) if zb is not None else None, embz_ld=zld or 0, stats1=hs)
         tc2 = P.use_tc(Co, Co, 3, 1, H2, W2)
         act2, _ = P.gn_apply(h, Co, None, 0, ab2, silu=True, resample=RESAMPLE_NONE, B=B, H=H2, W=W2,
                              act_dtype=torch.bfloat16 if tc2 else torch.float32)
@@ -281,8 +285,9 @@ class _ResBase(PlannedModule):
             P.conv(sk_in, self.skip_connection.weight, self.skip_connection.bias, resid, B=B, H=H2, W=W2, Cin=C, Cout=Co,
                    k=self.skip_connection.kernel_size[0])
         out = P.new((B, H2, W2, Co), torch.float32, "res_out")
-        P.conv(act2, conv2.weight, conv2.bias, out, B=B, H=H2, W=W2, Cin=Co, Cout=Co, k=3, residual=resid)
-        return Src(out, Co, B, H2, W2)
+        os_ = P.conv(act2, conv2.weight, conv2.bias, out, B=B, H=H2, W=W2, Cin=Co, Cout=Co, k=3, residual=resid,
+                     want_stats=True)
+        return Src(out, Co, B, H2, W2, s1=os_)
 
     def emit_emb(self, P: Plan, emb: Buf, B: int, which: str = "t") -> Tuple[Buf, int, int]:
         """This block's own Linear(SiLU(emb)) -> [B, 2*Cout] (used when the block runs stand-alone)."""
@@ -375,7 +380,7 @@ class AttentionBlock(PlannedModule):
         B, H, W, C = x.B, x.H, x.W, x.C
         T = H * W
         legacy = isinstance(self.attention, QKVAttentionLegacy)
-        ab = P.gn_coef(x.b1, C, None, 0, self.norm.weight, self.norm.bias, B=B, HW=T)
+        ab = P.gn_coef(x.b1, C, None, 0, self.norm.weight, self.norm.bias, B=B, HW=T, stats1=x.s1)
         tcq = P.use_tc(C, 3 * C, 1, 1, H, W)
         xn, _ = P.gn_apply(x.b1, C, None, 0, ab, silu=False, resample=RESAMPLE_NONE, B=B, H=H, W=W,
                            act_dtype=torch.bfloat16 if tcq else torch.float32)
@@ -389,8 +394,9 @@ class AttentionBlock(PlannedModule):
             att, _ = P.gn_apply(att, C, None, 0, None, silu=False, resample=RESAMPLE_NONE, B=B, H=H, W=W,
                                 act_dtype=torch.bfloat16)
         out = P.new((B, H, W, C), torch.float32, "attn_out")
-        P.conv(att, self.proj_out.weight, self.proj_out.bias, out, B=B, H=H, W=W, Cin=C, Cout=C, k=1, residual=x.b1)
-        return Src(out, C, B, H, W)
+        os_ = P.conv(att, self.proj_out.weight, self.proj_out.bias, out, B=B, H=H, W=W, Cin=C, Cout=C, k=1, residual=x.b1,
+                     want_stats=True)
+        return Src(out, C, B, H, W, s1=os_)
 
     def forward(self, x):
         self._check_no_grad(x)

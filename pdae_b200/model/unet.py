@@ -113,7 +113,7 @@ def emit_time_embed(P: Plan, time_embed: Slots, t: Buf, B: int, base: int, E: in
 def emit_head(P: Plan, head: Slots, x: Src, out: Buf) -> None:
     gn, conv = head[0], head[2]
     B, H, W, C = x.B, x.H, x.W, x.C
-    ab = P.gn_coef(x.b1, C, None, 0, gn.weight, gn.bias, B=B, HW=H * W)
+    ab = P.gn_coef(x.b1, C, None, 0, gn.weight, gn.bias, B=B, HW=H * W, stats1=x.s1)
     act, _ = P.gn_apply(x.b1, C, None, 0, ab, silu=True, resample=0, B=B, H=H, W=W,
                         act_dtype=torch.bfloat16 if P.tc else torch.float32)
     P.head_conv(act, conv.weight, conv.bias, out, B=B, H=H, W=W, Cin=C, Cout=conv.weight.shape[0])
@@ -169,7 +169,8 @@ class UNet(PlannedModule):
         h0 = P.new((B, H, W, stem.weight.shape[0]), torch.float32, "stem")
         P.conv(x_in, stem.weight, stem.bias, h0, B=B, H=H, W=W, Cin=self.input_channel, Cout=stem.weight.shape[0], k=3,
                in_nchw=True)
-        h = Src(h0, stem.weight.shape[0], B, H, W)
+        # the stem output is a skip tensor read by three GroupNorms: compute its per-channel sums once
+        h = Src(h0, stem.weight.shape[0], B, H, W, s1=P.ch_stats(h0, stem.weight.shape[0], B=B, HW=H * W) if P.fused_stats else None)
         hs = [h]
         for stage in list(self.input_blocks)[1:]:
             h = stage.emit(P, h, bank)

@@ -10,19 +10,25 @@ from tests.util import assert_close
 pytestmark = pytest.mark.gpu
 
 
-def _run_conv(x, w, bias, resid, precision, k):
+def _run_conv(x, w, bias, resid, precision, k, out_dtype=torch.float32, want_stats=False, bn=0, v1=False):
     from pdae_b200.engine import Plan
     B, H, W, Cin = x.shape
     Cout = w.shape[0]
     P = Plan(x.device, precision)
-    out = P.new((B, H, W, Cout), torch.float32)
+    P.v2 = not v1
+    out = P.new((B, H, W, Cout), out_dtype)
     out.keep = True
-    P.conv(P.fixed(x), w, bias, out, B=B, H=H, W=W, Cin=Cin, Cout=Cout, k=k,
-           residual=P.fixed(resid) if resid is not None else None)
+    st = P.conv(P.fixed(x), w, bias, out, B=B, H=H, W=W, Cin=Cin, Cout=Cout, k=k,
+                residual=P.fixed(resid) if resid is not None else None, want_stats=want_stats, bn_override=bn)
+    if st is not None:
+        st.keep = True
     P.finalize()
     P.run()
+    P.run()   # a second replay must give the same answer (persistent-kernel barriers / stats zeroing re-arm correctly)
     torch.cuda.synchronize()
-    kinds = [op[0] for op in P.ops]
+    kinds = [op[0] for op in P.ops if op[0] != "zero"]
+    if want_stats:
+        return out.tensor.clone(), kinds, (st.tensor.clone() if st is not None else None)
     return out.tensor.clone(), kinds
 
 
@@ -52,10 +58,29 @@ def test_tc_conv_matches_simt(shape):
     bias = torch.randn(Cout, generator=g).cuda() if has_bias else None
     resid = torch.randn(B, H, W, Cout, generator=g).cuda() if has_res else None
     y_tc, kinds = _run_conv(x, w, bias, resid, "bf16", k)
+    assert kinds == ["conv_tc2"], kinds
+    y_v1, kinds = _run_conv(x, w, bias, resid, "bf16", k, v1=True)
     assert kinds == ["conv_tc"], kinds
     y_ref, kinds = _run_conv(x, w, bias, resid, "fp32", k)
     assert kinds == ["conv2d_simt"], kinds
-    assert_close(y_tc, y_ref, rtol=2e-3, atol=2e-3, what=f"tc vs simt {shape}")
+    assert_close(y_tc, y_ref, rtol=2e-3, atol=2e-3, what=f"tc v2 vs simt {shape}")
+    assert_close(y_v1, y_ref, rtol=2e-3, atol=2e-3, what=f"tc v1 vs simt {shape}")
+    # every legal N tile of the persistent kernel
+    for bn in (64, 128, 256):
+        if Cout % bn == 0:
+            y_bn, _ = _run_conv(x, w, bias, resid, "bf16", k, bn=bn)
+            assert_close(y_bn, y_ref, rtol=2e-3, atol=2e-3, what=f"tc v2 BN={bn} {shape}")
+    # bf16 output + fused per-channel statistics (no residual allowed with a bf16 output)
+    y_b, _, st = _run_conv(x, w, bias, None, "bf16", k, out_dtype=torch.bfloat16, want_stats=True)
+    y_nores = y_ref - resid if has_res else y_ref
+    assert_close(y_b.float(), y_nores, rtol=1e-2, atol=1e-2, what=f"bf16 out {shape}")
+    yb = y_b.float().reshape(B, H * W, Cout)
+    ref_st = torch.stack([yb.sum(1), (yb * yb).sum(1)], dim=-1)
+    assert_close(st, ref_st, rtol=2e-3, atol=2e-2, what=f"fused stats {shape}")
+    # fp32 output + residual + stats
+    y_f, _, st = _run_conv(x, w, bias, resid, "bf16", k, want_stats=True)
+    yf = y_f.reshape(B, H * W, Cout)
+    assert_close(st, torch.stack([yf.sum(1), (yf * yf).sum(1)], dim=-1), rtol=2e-3, atol=2e-2, what=f"fused stats fp32 {shape}")
     # and both against torch (CPU fp32, the oracle's arithmetic)
     y_cpu = F.conv2d(x.float().cpu().permute(0, 3, 1, 2), w.cpu(), bias.cpu() if has_bias else None, padding=k // 2)
     y_cpu = y_cpu.permute(0, 2, 3, 1)
@@ -86,6 +111,26 @@ def test_simt_conv_general(cfg):
     P.finalize()
     P.run()
     assert_close(out.tensor.permute(0, 3, 1, 2), ref, rtol=1e-4, atol=1e-4, what=str(cfg))
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 128, 3), (5, 8, 8, 64, 3), (1, 64, 64, 64, 6), (2, 128, 128, 128, 3)])
+def test_head_conv_tensor_core(shape):
+    """Image head on the tensor cores (Cout zero-padded to 16, NCHW fp32 out) vs torch."""
+    from pdae_b200.engine import Plan
+    B, H, W, Cin, Cout = shape
+    g = torch.Generator(device="cpu").manual_seed(11)
+    x = torch.randn(B, H, W, Cin, generator=g).to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).to(torch.bfloat16).float()
+    b = torch.randn(Cout, generator=g)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w, b, padding=1)
+    P = Plan(torch.device("cuda"), "bf16")
+    out = P.new((B, Cout, H, W), torch.float32)
+    out.keep = True
+    P.head_conv(P.fixed(x.cuda()), w.cuda(), b.cuda(), out, B=B, H=H, W=W, Cin=Cin, Cout=Cout)
+    P.finalize()
+    P.run()
+    assert [o[0] for o in P.ops] == ["conv_tc2"]
+    assert_close(out.tensor, ref, rtol=2e-3, atol=2e-3, what=f"tc head {shape}")
 
 
 def test_head_conv_smalln():
