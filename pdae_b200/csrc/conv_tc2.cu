@@ -46,20 +46,26 @@ __device__ __forceinline__ void mb_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mb_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mb_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
+__device__ __forceinline__ uint32_t mb_try(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
+__device__ __noinline__ void mb_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
+  while (!mb_try(bar, parity))
     if (clock64() - t0 > 4000000000LL) __trap();  // a protocol bug must trap, never hang the GPU
-  }
+}
+__device__ __forceinline__ void mb_wait(uint32_t bar, uint32_t parity) {
+  if (mb_try(bar, parity)) return;   // fast path: no clock reads, no loop
+  if (mb_try(bar, parity)) return;
+  mb_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void tma_ld4(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile(
@@ -125,6 +131,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __shared__ __align__(8) uint64_t bar_full[T2_MAX_STAGES], bar_empty[T2_MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2], bar_res[2];
   __shared__ uint32_t tmem_slot;
+  __shared__ float st_acc[2][BN < 32 ? 32 : BN];  // per-channel (sum, sum^2) of the current (image, n-tile)
 
   constexpr int B_BYTES = BN * T2_BK * 2;
   constexpr int STAGE_BYTES = T2_A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
@@ -135,7 +142,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t stg_res = stg_out + 2u * T2_STG_BYTES;         // 2 x 16 KB residual staging (only if has_res)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_k = p.taps * p.kblocks;
+  // contiguous tile range per CTA: consecutive tiles of a CTA mostly belong to the same image, so the per-channel
+  // GroupNorm partial sums can be accumulated in shared memory across tiles and flushed once per image
+  const int per_cta = (p.tiles_total + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int tile_begin = (int)blockIdx.x * per_cta;
+  const int tile_end = min(p.tiles_total, tile_begin + per_cta);
 
+  for (int j = threadIdx.x; j < (BN < 32 ? 32 : BN); j += T2_THREADS) {
+    st_acc[0][j] = 0.f;
+    st_acc[1][j] = 0.f;
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mb_init(s_u32(&bar_full[s]), 1);
@@ -165,8 +181,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0) {
     if (lane == 0) {
       // ================= TMA producer =================
-      int it_g = 0;
-      for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
         const int nt = tile / p.tiles_m;
         int mt = tile - nt * p.tiles_m;
         const int tx = mt % p.tiles_x;
@@ -174,17 +191,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int ty = mt % p.tiles_y;
         const int bt = mt / p.tiles_y;
         const int x0 = tx * p.tw, y0 = ty * p.th, b0 = bt * p.tn, n0 = nt * BN;
-        for (int it = 0; it < total_k; ++it, ++it_g) {
-          const int s = it_g % S;
-          const uint32_t ph = (uint32_t)((it_g / S) & 1);
+        int tap = 0, kb = 0, dy = p.ksize == 3 ? -1 : 0, dx = dy;
+        for (int it = 0; it < total_k; ++it) {
           mb_wait(s_u32(&bar_empty[s]), ph ^ 1u);
           const uint32_t full = s_u32(&bar_full[s]);
           mb_expect_tx(full, T2_A_BYTES + B_BYTES);
-          const int tap = it / p.kblocks, kb = it - tap * p.kblocks;
-          const int dy = p.ksize == 3 ? tap / 3 - 1 : 0, dx = p.ksize == 3 ? tap % 3 - 1 : 0;
           const uint32_t sa = smem0 + (uint32_t)s * STAGE_BYTES;
           tma_ld4(sa, &tmA, full, kb * T2_BK, x0 + dx, y0 + dy, b0);
           tma_ld3(sa + T2_A_BYTES, &tmB, full, kb * T2_BK, n0, tap);
+          if (++kb == p.kblocks) {
+            kb = 0;
+            ++tap;
+            if (p.ksize == 3 && ++dx == 2) { dx = -1; ++dy; }
+          }
+          if (++s == S) { s = 0; ph ^= 1u; }
         }
       }
     }
@@ -193,15 +213,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // ================= MMA issuer =================
       constexpr uint32_t IDESC =
           (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24);
-      int it_g = 0, tl = 0;
-      for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++tl) {
+      int s = 0, tl = 0;
+      uint32_t ph = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile, ++tl) {
         const int ab = tl & 1;
         mb_wait(s_u32(&bar_acc_empty[ab]), (uint32_t)(((tl >> 1) & 1) ^ 1));  // epilogue drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_d = tmem_base + (uint32_t)(ab * BN);
-        for (int it = 0; it < total_k; ++it, ++it_g) {
-          const int s = it_g % S;
-          mb_wait(s_u32(&bar_full[s]), (uint32_t)((it_g / S) & 1));
+        for (int it = 0; it < total_k; ++it) {
+          mb_wait(s_u32(&bar_full[s]), ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem0 + (uint32_t)s * STAGE_BYTES;
           const uint64_t ad = sw128_desc(sa), bd = sw128_desc(sa + T2_A_BYTES);
@@ -209,6 +229,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int k = 0; k < T2_BK / 16; ++k)
             umma(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), IDESC, (uint32_t)((it | k) != 0));
           umma_commit_to(s_u32(&bar_empty[s]));
+          if (++s == S) { s = 0; ph ^= 1u; }
         }
         umma_commit_to(s_u32(&bar_acc_full[ab]));
       }
@@ -221,7 +242,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int r = q * 32 + lane;               // accumulator row = pixel index in the tile
     const int ppi = p.th * p.tw;               // pixels per image inside a tile
     int tl = 0, sc = 0, rc = 0;                // tile / staging-buffer / residual-buffer counters
-    for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++tl) {
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++tl) {
       const int nt = tile / p.tiles_m;
       int mt = tile - nt * p.tiles_m;
       const int tx = mt % p.tiles_x;
@@ -333,34 +354,52 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             // per-channel partial sums over this tile's rows, read back from the staged (rounded) values:
             // thread -> column (et % CW), rows [(et / CW) * CW, +CW)
             const int col = et % CW, r0 = (et / CW) * CW;
-            float s = 0.f, qq = 0.f;
-            int cur = r0 / ppi;
-            for (int rr = r0; rr < r0 + CW; ++rr) {
-              const int img = rr / ppi;
-              if (img != cur) {
-                if (b0 + cur < p.B) {
-                  float* dst = p.ch_stats + ((long long)(b0 + cur) * p.Cout + n0 + c * CW + col) * 2;
-                  atomicAdd(dst, s);
-                  atomicAdd(dst + 1, qq);
-                }
-                s = qq = 0.f;
-                cur = img;
-              }
+            const uint32_t cbyte = p.out_bf16 ? (uint32_t)((col & 7) * 2) : (uint32_t)((col & 3) * 4);
+            const int cchunk = p.out_bf16 ? (col >> 3) : (col >> 2);
+            auto ldv = [&](int rr) -> float {
               float x;
               if (p.out_bf16) {
                 unsigned short h;
-                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(obuf + swz(rr, col >> 3) + (uint32_t)((col & 7) * 2)));
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(obuf + swz(rr, cchunk) + cbyte));
                 x = __uint_as_float(((uint32_t)h) << 16);
               } else {
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(obuf + swz(rr, col >> 2) + (uint32_t)((col & 3) * 4)));
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(obuf + swz(rr, cchunk) + cbyte));
               }
-              s += x;
-              qq = fmaf(x, x, qq);
-            }
-            if (b0 + cur < p.B) {
-              float* dst = p.ch_stats + ((long long)(b0 + cur) * p.Cout + n0 + c * CW + col) * 2;
-              atomicAdd(dst, s);
-              atomicAdd(dst + 1, qq);
+              return x;
+            };
+            if (p.tn == 1) {
+              // whole tile = one image: accumulate in shared memory across this CTA's consecutive tiles
+              float s = 0.f, qq = 0.f;
+#pragma unroll 8
+              for (int rr = r0; rr < r0 + CW; ++rr) {
+                const float x = ldv(rr);
+                s += x;
+                qq = fmaf(x, x, qq);
+              }
+              atomicAdd(&st_acc[0][c * CW + col], s);
+              atomicAdd(&st_acc[1][c * CW + col], qq);
+            } else {
+              float s = 0.f, qq = 0.f;
+              int cur = r0 / ppi, nxt = (cur + 1) * ppi;  // `nxt` = first row of the next image
+              float* dst0 = p.ch_stats + ((long long)b0 * p.Cout + n0 + c * CW + col) * 2;
+              for (int rr = r0; rr < r0 + CW; ++rr) {
+                if (rr == nxt) {
+                  if (b0 + cur < p.B) {
+                    atomicAdd(dst0 + (long long)cur * p.Cout * 2, s);
+                    atomicAdd(dst0 + (long long)cur * p.Cout * 2 + 1, qq);
+                  }
+                  s = qq = 0.f;
+                  ++cur;
+                  nxt += ppi;
+                }
+                const float x = ldv(rr);
+                s += x;
+                qq = fmaf(x, x, qq);
+              }
+              if (b0 + cur < p.B) {
+                atomicAdd(dst0 + (long long)cur * p.Cout * 2, s);
+                atomicAdd(dst0 + (long long)cur * p.Cout * 2 + 1, qq);
+              }
             }
           }
           ++sc;
@@ -370,6 +409,26 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       epi_bar();
       if (elected) mb_arrive(s_u32(&bar_acc_empty[ab]));
+      if constexpr (BN != 16) {
+        if (p.ch_stats && p.tn == 1) {
+          bool flush = tile + 1 >= tile_end;
+          if (!flush) {
+            const int nt2 = (tile + 1) / p.tiles_m;
+            const int bt2 = ((tile + 1) - nt2 * p.tiles_m) / (p.tiles_x * p.tiles_y);
+            flush = nt2 != nt || bt2 != bt;
+          }
+          if (flush) {  // (the epi_bar above ordered every thread's shared-memory atomics before these reads)
+            for (int j = et; j < BN; j += 128) {
+              float* dst = p.ch_stats + ((long long)b0 * p.Cout + n0 + j) * 2;
+              atomicAdd(dst, st_acc[0][j]);
+              atomicAdd(dst + 1, st_acc[1][j]);
+              st_acc[0][j] = 0.f;
+              st_acc[1][j] = 0.f;
+            }
+            epi_bar();
+          }
+        }
+      }
     }
     if (elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -410,7 +469,7 @@ static cudaError_t launch_tc2(const CUtensorMap& a, const CUtensorMap& b, const 
                               const ConvTc2Args& args, int grid, size_t smem, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);  // + static (barriers, stats) <= 227 KB
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -470,6 +529,7 @@ extern "C" int pdae_conv_tc2_create(pdae_conv_tc2_plan** plan_out, const void* i
   int BN;
   if (head) BN = 16;
   else if (bn_override == 64 || bn_override == 128 || bn_override == 256) BN = bn_override;
+  else if (Cout % 256 == 0 && (long long)a.tiles_m * (Cout / 256) >= g_num_sms) BN = 256;  // fewer A re-reads per FLOP
   else BN = (Cout % 128 == 0) ? 128 : 64;
   if (!head && Cout % BN != 0) {
     delete pl;

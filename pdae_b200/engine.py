@@ -310,6 +310,7 @@ class Plan:
             st.synchronize()
             for i in range(n):
                 acc[i] += evs[i].elapsed_time(evs[i + 1]) / reps
+        self.last_op_ms = acc  # per recorded op, same order as self.ops
         out: Dict[str, Dict[str, float]] = {}
         for i, (_, _, _, name) in enumerate(self._compiled):
             d = out.setdefault(name, {"ms": 0.0, "flops": 0.0, "launches": 0})
@@ -382,6 +383,8 @@ class Plan:
             wp = self.pack((id(weight), "tc16"), [weight], pack16)
             self.call("conv_tc2", x, wp, self.param(bias), None, out_nchw, PDAE_F32, None, B, H, W, Cin, 16, 3, Cout, 0, flops=fl)
         elif Cout <= 4 and Cin % 4 == 0:
+            assert x.dtype in (torch.float32, torch.bfloat16)
+
             def pack4():
                 w = weight.detach().reshape(Cout, Cin, 9).permute(2, 1, 0).float()
                 z = torch.zeros(9, Cin, 4, device=w.device, dtype=torch.float32)
@@ -392,6 +395,14 @@ class Plan:
         else:
             assert x.dtype == torch.float32
             self.conv(x, weight, bias, out_nchw, B=B, H=H, W=W, Cin=Cin, Cout=Cout, k=3, out_nchw=True)
+
+    def head_act_dtype(self, Cin: int, Cout: int, H: int, W: int):
+        """dtype the normalised input of an image-head conv should be produced in (bf16 only if a bf16 kernel takes it)."""
+        if not self.tc:
+            return torch.float32
+        if (self.v2 and Cout <= 16 and self.use_tc(Cin, 64, 3, 1, H, W)) or (Cout <= 4 and Cin % 4 == 0):
+            return torch.bfloat16
+        return torch.float32
 
     def ch_stats(self, src: Buf, C: int, *, B, HW) -> Buf:
         """Per-channel (sum, sum^2) of an fp32 NHWC tensor that no conv epilogue produced."""

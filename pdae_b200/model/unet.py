@@ -115,7 +115,7 @@ def emit_head(P: Plan, head: Slots, x: Src, out: Buf) -> None:
     B, H, W, C = x.B, x.H, x.W, x.C
     ab = P.gn_coef(x.b1, C, None, 0, gn.weight, gn.bias, B=B, HW=H * W, stats1=x.s1)
     act, _ = P.gn_apply(x.b1, C, None, 0, ab, silu=True, resample=0, B=B, H=H, W=W,
-                        act_dtype=torch.bfloat16 if P.tc else torch.float32)
+                        act_dtype=P.head_act_dtype(C, conv.weight.shape[0], H, W))
     P.head_conv(act, conv.weight, conv.bias, out, B=B, H=H, W=W, Cin=C, Cout=conv.weight.shape[0])
 
 
