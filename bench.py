@@ -255,10 +255,11 @@ def main():
                      "tflops": round(v["flops"] / (v["ms"] * 1e9), 2) if v["flops"] and v["ms"] > 0 else None}
                  for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
         peak_tf, peak_bw, peak_src = peaks()
-        dom = "conv_tc" if "conv_tc" in prof else "conv2d_simt"
+        dom = max((k for k in prof if k.startswith("conv")), key=lambda k: prof[k]["ms"])
         n_l = prof[dom]["launches"]
         ach = prof[dom]["flops"] / (prof[dom]["ms"] * 1e9)
-        roof = {"bound": "tensor", "kernel": "pdae::conv_tc_kernel" if dom == "conv_tc" else "pdae::conv_simt_kernel",
+        kname = {"conv_tc2": "pdae::conv_tc2_kernel", "conv_tc": "pdae::conv_tc_kernel"}.get(dom, "pdae::conv_simt_kernel")
+        roof = {"bound": "tensor", "kernel": kname,
                 "achieved": round(ach, 2), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4), "traffic": None,
                 "peak_source": peak_src, "launches_per_decoder_step": n_l,
                 "flops_per_launch_avg": prof[dom]["flops"] / n_l, "ms_per_launch_avg": prof[dom]["ms"] / n_l,

@@ -146,7 +146,16 @@ typedef struct pdae_conv_tc2_plan pdae_conv_tc2_plan;
 int pdae_conv_tc2_create(pdae_conv_tc2_plan** plan, const void* in_bf16, const void* w_bf16, const float* bias,
                          const float* residual, void* out, int out_dtype, float* ch_stats, int B, int H, int W, int Cin,
                          int Cout, int ksize, int cout_valid, int bn_override);
+/* Batched GEMM on the same kernel (tensor-core attention, model/module.py:452-456,483-487): for each batch item
+ * out[M x N] = A[M x K] * Bm[N x K]^T, both operands bf16 K-major; *_ld = elements between rows, *_bs = between items.
+ * M % 128 == 0, N % 64 == 0, K % 64 == 0.                                                                             */
+int pdae_gemm_tc2_create(pdae_conv_tc2_plan** plan, const void* a_bf16, long long a_ld, long long a_bs, const void* b_bf16,
+                         long long b_ld, long long b_bs, void* out, int out_dtype, long long out_ld, long long out_bs,
+                         int batch, int M, int N, int K);
 int pdae_conv_tc2_run(const pdae_conv_tc2_plan* plan, pdae_stream_t stream);
+/* P = softmax(alpha * S) per row, fp32 in -> bf16 out.  vT[b*heads+h][c][t] = V part of qkv (bf16 [B][T][3C]).        */
+int pdae_softmax_bf16(const float* S, void* P_bf16, int64_t rows, int cols, float alpha, pdae_stream_t stream);
+int pdae_transpose_v(const void* qkv_bf16, void* vT_bf16, int B, int T, int C, int heads, int legacy, pdae_stream_t stream);
 void pdae_conv_tc2_destroy(pdae_conv_tc2_plan* plan);
 
 #ifdef __cplusplus

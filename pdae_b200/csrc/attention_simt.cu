@@ -104,9 +104,79 @@ __global__ void softmax_rows_kernel(float* __restrict__ S, long long rows, int c
   for (int j = lane; j < cols; j += 32) r[j] *= inv;
 }
 
+// softmax(alpha * S) over rows of fp32 scores, written as bf16 probabilities (one warp per row)
+__global__ void softmax_rows_bf16_kernel(const float* __restrict__ S, __nv_bfloat16* __restrict__ P, long long rows, int cols,
+                                         float alpha) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* r = S + row * cols;
+  __nv_bfloat16* o = P + row * cols;
+  float mx = -INFINITY;
+  for (int j = lane * 4; j < cols; j += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(r + j);
+    mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+  float sum = 0.f;
+  for (int j = lane * 4; j < cols; j += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(r + j);
+    sum += __expf(alpha * (v.x - mx)) + __expf(alpha * (v.y - mx)) + __expf(alpha * (v.z - mx)) + __expf(alpha * (v.w - mx));
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+  const float inv = 1.0f / sum;
+  for (int j = lane * 4; j < cols; j += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(r + j);
+    store4<__nv_bfloat16>(o + j, make_float4(__expf(alpha * (v.x - mx)) * inv, __expf(alpha * (v.y - mx)) * inv,
+                                             __expf(alpha * (v.z - mx)) * inv, __expf(alpha * (v.w - mx)) * inv));
+  }
+}
+
+// vT[z][c][t] = qkv[b][t][voff + h*hs + c]   (z = b*heads + h): 32x32 shared-memory tile transpose, bf16
+__global__ void transpose_v_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ vT, int T, int C3,
+                                   int ch, int heads, long long voff, long long hs) {
+  __shared__ __nv_bfloat16 tile[32][34];
+  const int z = blockIdx.z, b = z / heads, h = z % heads;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const __nv_bfloat16* src = qkv + (long long)b * T * C3 + voff + h * hs;
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + tx;
+    tile[i][tx] = (t < T && c < ch) ? src[(long long)t * C3 + c] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  __nv_bfloat16* dst = vT + (long long)z * ch * T;
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + tx;
+    if (c < ch && t < T) dst[(long long)c * T + t] = tile[tx][i];
+  }
+}
+
 }  // namespace pdae
 
 using namespace pdae;
+
+extern "C" int pdae_softmax_bf16(const float* S, void* P_bf16, int64_t rows, int cols, float alpha, pdae_stream_t stream) {
+  PDAE_REQUIRE(S && P_bf16 && cols % 4 == 0, "softmax_bf16: bad args");
+  softmax_rows_bf16_kernel<<<cdiv(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(S, (__nv_bfloat16*)P_bf16, rows, cols, alpha);
+  PDAE_LAUNCH_CHECK("softmax_rows_bf16_kernel");
+  return PDAE_OK;
+}
+
+extern "C" int pdae_transpose_v(const void* qkv_bf16, void* vT_bf16, int B, int T, int C, int heads, int legacy,
+                                pdae_stream_t stream) {
+  PDAE_REQUIRE(qkv_bf16 && vT_bf16 && heads > 0 && C % heads == 0, "transpose_v: bad args");
+  const int ch = C / heads;
+  const long long voff = legacy ? 2LL * ch : 2LL * C, hs = legacy ? 3LL * ch : ch;
+  dim3 grid(cdiv(T, 32), cdiv(ch, 32), B * heads);
+  PDAE_REQUIRE(grid.z <= 65535, "transpose_v: B*heads too large");
+  transpose_v_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)qkv_bf16, (__nv_bfloat16*)vT_bf16, T, 3 * C,
+                                                            ch, heads, voff, hs);
+  PDAE_LAUNCH_CHECK("transpose_v_kernel");
+  return PDAE_OK;
+}
 
 extern "C" int pdae_attention_simt(const float* qkv, float* out, float* scratch, int B, int T, int C, int heads,
                                    int legacy, pdae_stream_t stream) {

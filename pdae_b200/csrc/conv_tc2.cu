@@ -34,6 +34,7 @@ struct ConvTc2Args {
   int taps, ksize, kblocks;
   int stages;
   int has_res, out_bf16, cout_valid;
+  int w_batched;  // B operand is a per-image matrix (batched GEMM): 3rd TMA coordinate = image index
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -198,7 +199,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           mb_expect_tx(full, T2_A_BYTES + B_BYTES);
           const uint32_t sa = smem0 + (uint32_t)s * STAGE_BYTES;
           tma_ld4(sa, &tmA, full, kb * T2_BK, x0 + dx, y0 + dy, b0);
-          tma_ld3(sa + T2_A_BYTES, &tmB, full, kb * T2_BK, n0, tap);
+          tma_ld3(sa + T2_A_BYTES, &tmB, full, kb * T2_BK, n0, p.w_batched ? b0 : tap);
           if (++kb == p.kblocks) {
             kb = 0;
             ++tap;
@@ -490,20 +491,32 @@ struct pdae_conv_tc2_plan {
 
 static int g_num_sms = 0;
 
-extern "C" int pdae_conv_tc2_create(pdae_conv_tc2_plan** plan_out, const void* in_bf16, const void* w_bf16, const float* bias,
-                                    const float* residual, void* out, int out_dtype, float* ch_stats, int B, int H, int W,
-                                    int Cin, int Cout, int ksize, int cout_valid, int bn_override) {
-  PDAE_REQUIRE(plan_out && in_bf16 && w_bf16 && out, "conv_tc2_create: null pointer");
+struct Tc2Desc {
+  const void* in; const void* w; const float* bias; const float* residual; void* out;
+  int out_dtype; float* ch_stats;
+  int B, H, W, Cin, Cout, ksize, cout_valid, bn_override;
+  long long in_ld;            // elements between consecutive pixels of the A operand
+  long long in_bs;            // elements between consecutive images of the A operand
+  int w_batched;              // 0: weights [taps][Cout][Cin] ; 1: per-image matrix [B][Cout rows][Cin], strides below
+  long long w_ld, w_bs;
+  long long out_ld, out_bs;   // elements between consecutive pixels / images of the output
+};
+
+static int tc2_create(pdae_conv_tc2_plan** plan_out, const Tc2Desc& d) {
+  const int B = d.B, H = d.H, W = d.W, Cin = d.Cin, Cout = d.Cout, ksize = d.ksize, cout_valid = d.cout_valid;
+  PDAE_REQUIRE(plan_out && d.in && d.w && d.out, "conv_tc2_create: null pointer");
   PDAE_REQUIRE(ksize == 1 || ksize == 3, "conv_tc2_create: ksize must be 1 or 3");
   PDAE_REQUIRE(Cin % T2_BK == 0, "conv_tc2_create: Cin=%d not a multiple of 64", Cin);
   const bool head = cout_valid > 0;
-  PDAE_REQUIRE(head ? (Cout == 16 && cout_valid <= 16 && out_dtype == PDAE_F32 && !residual && !ch_stats) : (Cout % 64 == 0),
+  PDAE_REQUIRE(head ? (Cout == 16 && cout_valid <= 16 && d.out_dtype == PDAE_F32 && !d.residual && !d.ch_stats) : (Cout % 64 == 0),
                "conv_tc2_create: unsupported Cout=%d (cout_valid=%d)", Cout, cout_valid);
-  PDAE_REQUIRE(out_dtype == PDAE_F32 || out_dtype == PDAE_BF16, "conv_tc2_create: bad out dtype");
-  PDAE_REQUIRE(!(residual && out_dtype != PDAE_F32), "conv_tc2_create: a residual needs an fp32 output");
-  PDAE_REQUIRE(((uintptr_t)in_bf16 & 15) == 0 && ((uintptr_t)w_bf16 & 15) == 0 && ((uintptr_t)out & 15) == 0 &&
-                   ((uintptr_t)residual & 15) == 0 && ((uintptr_t)bias & 15) == 0,
+  PDAE_REQUIRE(d.out_dtype == PDAE_F32 || d.out_dtype == PDAE_BF16, "conv_tc2_create: bad out dtype");
+  PDAE_REQUIRE(!(d.residual && d.out_dtype != PDAE_F32), "conv_tc2_create: a residual needs an fp32 output");
+  PDAE_REQUIRE(((uintptr_t)d.in & 15) == 0 && ((uintptr_t)d.w & 15) == 0 && ((uintptr_t)d.out & 15) == 0 &&
+                   ((uintptr_t)d.residual & 15) == 0 && ((uintptr_t)d.bias & 15) == 0,
                "conv_tc2_create: pointers must be 16-byte aligned");
+  PDAE_REQUIRE(d.in_ld % 8 == 0 && d.in_bs % 8 == 0 && d.w_ld % 8 == 0 && d.w_bs % 8 == 0 && d.out_ld % 8 == 0 &&
+                   d.out_bs % 8 == 0, "conv_tc2_create: strides must be multiples of 16 bytes");
   EncodeTiledFn2 enc = encode_fn2();
   PDAE_REQUIRE(enc != nullptr, "conv_tc2_create: cuTensorMapEncodeTiled unavailable (no driver)");
   if (g_num_sms == 0) {
@@ -513,22 +526,24 @@ extern "C" int pdae_conv_tc2_create(pdae_conv_tc2_plan** plan_out, const void* i
   }
   pdae_conv_tc2_plan* pl = new pdae_conv_tc2_plan();
   ConvTc2Args& a = pl->args;
-  a.bias = bias; a.ch_stats = ch_stats; a.out_nchw = head ? (float*)out : nullptr;
+  a.bias = d.bias; a.ch_stats = d.ch_stats; a.out_nchw = head ? (float*)d.out : nullptr;
   a.B = B; a.H = H; a.W = W; a.Cout = Cout;
   a.tw = pow2_tile(W, T2_BM);
   a.th = pow2_tile(H, T2_BM / a.tw);
   a.tn = T2_BM / (a.tw * a.th);
-  if (W % a.tw != 0 || H % a.th != 0 || a.tw * a.th * a.tn != T2_BM || a.tn > 256) {
+  if (W % a.tw != 0 || H % a.th != 0 || a.tw * a.th * a.tn != T2_BM || a.tn > 256 || (d.w_batched && a.tn != 1)) {
     delete pl;
-    PDAE_REQUIRE(false, "conv_tc2_create: H=%d W=%d cannot be tiled into 128-pixel boxes", H, W);
+    PDAE_REQUIRE(false, "conv_tc2_create: H=%d W=%d cannot be tiled into 128-pixel boxes%s", H, W,
+                 d.w_batched ? " of a single image (batched GEMM)" : "");
   }
   a.tiles_x = W / a.tw; a.tiles_y = H / a.th; a.tiles_b = (B + a.tn - 1) / a.tn;
   a.tiles_m = a.tiles_x * a.tiles_y * a.tiles_b;
   a.taps = ksize * ksize; a.ksize = ksize; a.kblocks = Cin / T2_BK;
-  a.has_res = residual != nullptr; a.out_bf16 = out_dtype == PDAE_BF16; a.cout_valid = cout_valid;
+  a.has_res = d.residual != nullptr; a.out_bf16 = d.out_dtype == PDAE_BF16; a.cout_valid = cout_valid;
+  a.w_batched = d.w_batched;
   int BN;
   if (head) BN = 16;
-  else if (bn_override == 64 || bn_override == 128 || bn_override == 256) BN = bn_override;
+  else if (d.bn_override == 64 || d.bn_override == 128 || d.bn_override == 256) BN = d.bn_override;
   else if (Cout % 256 == 0 && (long long)a.tiles_m * (Cout / 256) >= g_num_sms) BN = 256;  // fewer A re-reads per FLOP
   else BN = (Cout % 128 == 0) ? 128 : 64;
   if (!head && Cout % BN != 0) {
@@ -556,19 +571,19 @@ extern "C" int pdae_conv_tc2_create(pdae_conv_tc2_plan** plan_out, const void* i
   cuuint32_t estr4[4] = {1, 1, 1, 1};
   {
     cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+    cuuint64_t strides[3] = {(cuuint64_t)d.in_ld * 2, (cuuint64_t)W * d.in_ld * 2, (cuuint64_t)d.in_bs * 2};
     cuuint32_t box[4] = {(cuuint32_t)T2_BK, (cuuint32_t)a.tw, (cuuint32_t)a.th, (cuuint32_t)a.tn};
-    CUresult r = enc(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in_bf16), dims, strides, box, estr4,
+    CUresult r = enc(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d.in), dims, strides, box, estr4,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("A", (int)r);
   }
   {
-    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)a.taps};
-    cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
+    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)(d.w_batched ? B : a.taps)};
+    cuuint64_t strides[2] = {(cuuint64_t)d.w_ld * 2, (cuuint64_t)d.w_bs * 2};
     cuuint32_t box[3] = {(cuuint32_t)T2_BK, (cuuint32_t)BN, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&pl->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_bf16), dims, strides, box, estr,
+    CUresult r = enc(&pl->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d.w), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("W", (int)r);
@@ -578,16 +593,16 @@ extern "C" int pdae_conv_tc2_create(pdae_conv_tc2_plan** plan_out, const void* i
   if (!head) {
     const int esz = a.out_bf16 ? 2 : 4;
     cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)Cout * esz, (cuuint64_t)W * Cout * esz, (cuuint64_t)H * W * Cout * esz};
+    cuuint64_t strides[3] = {(cuuint64_t)d.out_ld * esz, (cuuint64_t)W * d.out_ld * esz, (cuuint64_t)d.out_bs * esz};
     cuuint32_t box[4] = {(cuuint32_t)(a.out_bf16 ? 64 : 32), (cuuint32_t)a.tw, (cuuint32_t)a.th, (cuuint32_t)a.tn};
-    CUresult r = enc(&pl->tmO, a.out_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, dims,
+    CUresult r = enc(&pl->tmO, a.out_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.out, dims,
                      strides, box, estr4, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("O", (int)r);
     if (a.has_res) {
       cuuint64_t rstr[3] = {(cuuint64_t)Cout * 4, (cuuint64_t)W * Cout * 4, (cuuint64_t)H * W * Cout * 4};
       cuuint32_t rbox[4] = {32, (cuuint32_t)a.tw, (cuuint32_t)a.th, (cuuint32_t)a.tn};
-      r = enc(&pl->tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(residual), dims, rstr, rbox, estr4,
+      r = enc(&pl->tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(d.residual), dims, rstr, rbox, estr4,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail("R", (int)r);
@@ -595,6 +610,33 @@ extern "C" int pdae_conv_tc2_create(pdae_conv_tc2_plan** plan_out, const void* i
   }
   *plan_out = pl;
   return PDAE_OK;
+}
+
+extern "C" int pdae_conv_tc2_create(pdae_conv_tc2_plan** plan_out, const void* in_bf16, const void* w_bf16, const float* bias,
+                                    const float* residual, void* out, int out_dtype, float* ch_stats, int B, int H, int W,
+                                    int Cin, int Cout, int ksize, int cout_valid, int bn_override) {
+  Tc2Desc d;
+  d.in = in_bf16; d.w = w_bf16; d.bias = bias; d.residual = residual; d.out = out; d.out_dtype = out_dtype;
+  d.ch_stats = ch_stats; d.B = B; d.H = H; d.W = W; d.Cin = Cin; d.Cout = Cout; d.ksize = ksize; d.cout_valid = cout_valid;
+  d.bn_override = bn_override;
+  d.in_ld = Cin; d.in_bs = (long long)H * W * Cin;
+  d.w_batched = 0; d.w_ld = Cin; d.w_bs = (long long)Cout * Cin;
+  d.out_ld = Cout; d.out_bs = (long long)H * W * Cout;
+  return tc2_create(plan_out, d);
+}
+
+// Batched GEMM on the same kernel: for every batch item i,  out_i[M x N] = A_i[M x K] * Bm_i[N x K]^T  (both K-major bf16).
+// a_ld / b_ld / out_ld: elements between consecutive rows; *_bs: elements between consecutive batch items.
+extern "C" int pdae_gemm_tc2_create(pdae_conv_tc2_plan** plan_out, const void* a_bf16, long long a_ld, long long a_bs,
+                                    const void* b_bf16, long long b_ld, long long b_bs, void* out, int out_dtype,
+                                    long long out_ld, long long out_bs, int batch, int M, int N, int K) {
+  Tc2Desc d;
+  d.in = a_bf16; d.w = b_bf16; d.bias = nullptr; d.residual = nullptr; d.out = out; d.out_dtype = out_dtype;
+  d.ch_stats = nullptr; d.B = batch; d.H = 1; d.W = M; d.Cin = K; d.Cout = N; d.ksize = 1; d.cout_valid = 0; d.bn_override = 0;
+  d.in_ld = a_ld; d.in_bs = a_bs;
+  d.w_batched = 1; d.w_ld = b_ld; d.w_bs = b_bs;
+  d.out_ld = out_ld; d.out_bs = out_bs;
+  return tc2_create(plan_out, d);
 }
 
 extern "C" int pdae_conv_tc2_run(const pdae_conv_tc2_plan* pl, pdae_stream_t stream) {

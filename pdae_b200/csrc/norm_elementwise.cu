@@ -169,11 +169,71 @@ __global__ void gn_coef_kernel(const double* __restrict__ sums, const float* __r
 
 // ---------------------------------------------------------------------------------------------
 // apply: flat float4 work items over [pixels][C/4]; consecutive threads walk consecutive channel quads.
+// FAST: approximate exp / division (MUFU) -- used when the result is rounded to bf16 anyway
+template <bool FAST>
+__device__ __forceinline__ float silu_t(float x) {
+  if (FAST) return __fdividef(x, 1.0f + __expf(-x));
+  return silu_f(x);
+}
+template <bool FAST = false>
 __device__ __forceinline__ float4 affine_act(float4 v, float4 a, float4 b, int silu) {
   float4 r;
   r.x = fmaf(a.x, v.x, b.x); r.y = fmaf(a.y, v.y, b.y); r.z = fmaf(a.z, v.z, b.z); r.w = fmaf(a.w, v.w, b.w);
-  if (silu) { r.x = silu_f(r.x); r.y = silu_f(r.y); r.z = silu_f(r.z); r.w = silu_f(r.w); }
+  if (silu) { r.x = silu_t<FAST>(r.x); r.y = silu_t<FAST>(r.y); r.z = silu_t<FAST>(r.z); r.w = silu_t<FAST>(r.w); }
   return r;
+}
+
+// Non-resampling, bf16-activation fast path: 8 channels (16 B of bf16 output) per work item, fast SiLU.
+template <typename TSrc, typename TRaw>
+__global__ void __launch_bounds__(256) gn_apply8_kernel(const TSrc* __restrict__ s1, int C1, const float* __restrict__ s2,
+                                                        int C2, const float* __restrict__ ab, int silu, long long HW,
+                                                        __nv_bfloat16* __restrict__ out_act, TRaw* __restrict__ out_raw) {
+  const int C = C1 + C2, L = C >> 3;
+  const int b = blockIdx.y;
+  const long long items = HW * L;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
+       it += (long long)gridDim.x * blockDim.x) {
+    const int cq = (int)(it % L);
+    const long long pix = it / L;
+    const int c = cq * 8;
+    float4 v0, v1;
+    if (c < C1) {
+      const TSrc* p = s1 + ((long long)b * HW + pix) * C1 + c;
+      if (sizeof(TSrc) == 2) {
+        const uint4 u = *reinterpret_cast<const uint4*>(p);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+        const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]), f2 = __bfloat1622float2(h[2]),
+                     f3 = __bfloat1622float2(h[3]);
+        v0 = make_float4(f0.x, f0.y, f1.x, f1.y);
+        v1 = make_float4(f2.x, f2.y, f3.x, f3.y);
+      } else {
+        v0 = *reinterpret_cast<const float4*>(p);
+        v1 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + 4);
+      }
+    } else {
+      const float* p = s2 + ((long long)b * HW + pix) * C2 + (c - C1);
+      v0 = *reinterpret_cast<const float4*>(p);
+      v1 = *reinterpret_cast<const float4*>(p + 4);
+    }
+    float4 a0 = make_float4(1.f, 1.f, 1.f, 1.f), a1 = a0, b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+    if (ab) {
+      const float* pa = ab + ((long long)b * 2 + 0) * C + c;
+      const float* pb = ab + ((long long)b * 2 + 1) * C + c;
+      a0 = *reinterpret_cast<const float4*>(pa); a1 = *reinterpret_cast<const float4*>(pa + 4);
+      b0 = *reinterpret_cast<const float4*>(pb); b1 = *reinterpret_cast<const float4*>(pb + 4);
+    }
+    const float4 r0 = affine_act<true>(v0, a0, b0, silu), r1 = affine_act<true>(v1, a1, b1, silu);
+    const long long o = ((long long)b * HW + pix) * C + c;
+    {
+      __nv_bfloat162 h[4] = {__floats2bfloat162_rn(r0.x, r0.y), __floats2bfloat162_rn(r0.z, r0.w),
+                             __floats2bfloat162_rn(r1.x, r1.y), __floats2bfloat162_rn(r1.z, r1.w)};
+      *reinterpret_cast<uint4*>(out_act + o) = *reinterpret_cast<uint4*>(h);
+    }
+    if (out_raw) {
+      store4<TRaw>(out_raw + o, v0);
+      store4<TRaw>(out_raw + o + 4, v1);
+    }
+  }
 }
 
 template <typename TSrc, typename TAct, typename TRaw, int RS>
@@ -476,6 +536,22 @@ extern "C" int pdae_gn_apply(const void* src1, int src1_dtype, int C1, const flo
   PDAE_REQUIRE(resample != PDAE_RESAMPLE_DOWN2 || (H % 2 == 0 && W % 2 == 0), "gn_apply: odd dims for DOWN2");
   cudaStream_t s = (cudaStream_t)stream;
   typedef __nv_bfloat16 bf;
+  if (resample == PDAE_RESAMPLE_NONE && act_dtype == PDAE_BF16 && C1 % 8 == 0 && C2 % 8 == 0 &&
+      (src1_dtype == PDAE_F32 || !out_raw)) {
+    const long long HW = (long long)H * W;
+    const long long items = HW * ((C1 + C2) / 8);
+    int gx = cdiv(items, 256);
+    if (gx > 148 * 8) gx = 148 * 8;
+    dim3 grid(gx, B);
+    if (src1_dtype == PDAE_BF16)
+      gn_apply8_kernel<bf, float><<<grid, 256, 0, s>>>((const bf*)src1, C1, src2, C2, ab, silu, HW, (bf*)out_act, (float*)nullptr);
+    else if (raw_dtype == PDAE_BF16)
+      gn_apply8_kernel<float, bf><<<grid, 256, 0, s>>>((const float*)src1, C1, src2, C2, ab, silu, HW, (bf*)out_act, (bf*)out_raw);
+    else
+      gn_apply8_kernel<float, float><<<grid, 256, 0, s>>>((const float*)src1, C1, src2, C2, ab, silu, HW, (bf*)out_act, (float*)out_raw);
+    PDAE_LAUNCH_CHECK("gn_apply8_kernel");
+    return PDAE_OK;
+  }
   if (src1_dtype == PDAE_BF16) {
     PDAE_REQUIRE(act_dtype == PDAE_BF16 && !out_raw, "gn_apply: a bf16 source supports a bf16 activation output only");
     return launch_apply<bf, bf, float>(src1, C1, src2, C2, ab, silu, resample, B, H, W, out_act, nullptr, s);

@@ -207,6 +207,9 @@ class Plan:
             if fn == "conv_tc2":
                 compiled.append(self._compile_tc2(args))
                 continue
+            if fn == "gemm_tc2":
+                compiled.append(self._compile_gemm(args))
+                continue
             cargs = []
             sidx = -1
             for k, a in enumerate(args):
@@ -246,6 +249,23 @@ class Plan:
         _native.check(rc, "pdae_conv_tc2_create")
         self._tc2_handles.append(h)
         return (self.L.pdae_conv_tc2_run, [h, None], 1, "conv_tc2")
+
+    def _compile_gemm(self, args):
+        a, a_ld, a_bs, b, b_ld, b_bs, out, odt, o_ld, o_bs, batch, M, N, K = args
+        h = ctypes.c_void_p()
+        rc = self.L.pdae_gemm_tc2_create(ctypes.byref(h), self._resolve(a), a_ld, a_bs, self._resolve(b), b_ld, b_bs,
+                                         self._resolve(out), odt, o_ld, o_bs, batch, M, N, K)
+        _native.check(rc, "pdae_gemm_tc2_create")
+        self._tc2_handles.append(h)
+        return (self.L.pdae_conv_tc2_run, [h, None], 1, "gemm_tc2")
+
+    def gemm_tc(self, a, a_ld, a_bs, b, b_ld, b_bs, out, out_ld, out_bs, *, batch, M, N, K, out_dtype) -> None:
+        """Batched out_i = A_i (MxK) * B_i (NxK)^T on the persistent tcgen05 kernel; a/b/out are Buf or BufView."""
+        self.call("gemm_tc2", a, a_ld, a_bs, b, b_ld, b_bs, out, _DT[out_dtype], out_ld, out_bs, batch, M, N, K,
+                  flops=2.0 * batch * M * N * K)
+
+    def can_gemm_tc(self, M: int, N: int, K: int) -> bool:
+        return self.tc and self.v2 and M % 128 == 0 and N % 64 == 0 and K % 64 == 0
 
     def __del__(self):
         try:

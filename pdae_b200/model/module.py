@@ -11,6 +11,7 @@ against the reference keep working; activations inside a plan are NHWC.
 """
 from __future__ import annotations
 
+import ctypes
 import math
 from typing import Dict, List, Optional, Tuple
 
@@ -384,15 +385,35 @@ class AttentionBlock(PlannedModule):
         tcq = P.use_tc(C, 3 * C, 1, 1, H, W)
         xn, _ = P.gn_apply(x.b1, C, None, 0, ab, silu=False, resample=RESAMPLE_NONE, B=B, H=H, W=W,
                            act_dtype=torch.bfloat16 if tcq else torch.float32)
-        qkv = P.new((B, T, 3 * C), torch.float32, "qkv")
-        P.conv(xn, self.qkv.weight, self.qkv.bias, qkv, B=B, H=H, W=W, Cin=C, Cout=3 * C, k=1)
-        att = P.new((B, T, C), torch.float32, "att")
-        scratch = P.new((B * self.num_heads, T, T), torch.float32, "att_scores")
-        P.call("attention_simt", qkv, att, scratch, B, T, C, self.num_heads, int(legacy), _STREAM, flops=4.0 * B * T * T * C)
-        tcp = P.use_tc(C, C, 1, 1, H, W)
-        if tcp:
-            att, _ = P.gn_apply(att, C, None, 0, None, silu=False, resample=RESAMPLE_NONE, B=B, H=H, W=W,
-                                act_dtype=torch.bfloat16)
+        heads, ch = self.num_heads, C // self.num_heads
+        if tcq and P.can_gemm_tc(T, T, ch) and P.can_gemm_tc(T, ch, T):
+            # ---- tensor-core attention: bf16 qkv -> S = Q K^T (batched tcgen05 GEMM) -> softmax -> P V ----
+            qkv = P.new((B, T, 3 * C), torch.bfloat16, "qkv")
+            P.conv(xn, self.qkv.weight, self.qkv.bias, qkv, B=B, H=H, W=W, Cin=C, Cout=3 * C, k=1)
+            vT = P.new((B * heads, ch, T), torch.bfloat16, "vT")
+            P.call("transpose_v", qkv, vT, B, T, C, heads, int(legacy), _STREAM)
+            S = P.new((B * heads, T, T), torch.float32, "att_scores")
+            Pm = P.new((B * heads, T, T), torch.bfloat16, "att_probs")
+            att = P.new((B, T, C), torch.bfloat16, "att")
+            hs_ = 3 * ch if legacy else ch                  # channel stride between heads inside a qkv row
+            ko = ch if legacy else C                        # offset of K relative to Q
+            for h in range(heads):
+                P.gemm_tc(qkv.at(h * hs_), 3 * C, T * 3 * C, qkv.at(h * hs_ + ko), 3 * C, T * 3 * C,
+                          S.at(h * T * T), T, heads * T * T, batch=B, M=T, N=T, K=ch, out_dtype=torch.float32)
+            P.call("softmax_bf16", S, Pm, ctypes.c_int64(B * heads * T), T, ctypes.c_float(1.0 / math.sqrt(ch)), _STREAM)
+            for h in range(heads):
+                P.gemm_tc(Pm.at(h * T * T), T, heads * T * T, vT.at(h * ch * T), T, heads * ch * T,
+                          att.at(h * ch), C, T * C, batch=B, M=T, N=ch, K=T, out_dtype=torch.bfloat16)
+        else:
+            qkv = P.new((B, T, 3 * C), torch.float32, "qkv")
+            P.conv(xn, self.qkv.weight, self.qkv.bias, qkv, B=B, H=H, W=W, Cin=C, Cout=3 * C, k=1)
+            att = P.new((B, T, C), torch.float32, "att")
+            scratch = P.new((B * self.num_heads, T, T), torch.float32, "att_scores")
+            P.call("attention_simt", qkv, att, scratch, B, T, C, self.num_heads, int(legacy), _STREAM, flops=4.0 * B * T * T * C)
+            tcp = P.use_tc(C, C, 1, 1, H, W)
+            if tcp:
+                att, _ = P.gn_apply(att, C, None, 0, None, silu=False, resample=RESAMPLE_NONE, B=B, H=H, W=W,
+                                    act_dtype=torch.bfloat16)
         out = P.new((B, H, W, C), torch.float32, "attn_out")
         os_ = P.conv(att, self.proj_out.weight, self.proj_out.bias, out, B=B, H=H, W=W, Cin=C, Cout=C, k=1, residual=x.b1,
                      want_stats=True)

@@ -48,3 +48,18 @@ for ms, key, fl in rows:
 print("conv shapes by total time:")
 for key, (n, ms, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
     print(f"  {key:58s} n={n:3d} {ms:8.3f} ms  avg {1e3 * ms / n:8.1f} us  {fl / (ms * 1e9):7.1f} TFLOP/s")
+
+print("gn_apply by total time:")
+agg = {}
+for i, (fn, args) in enumerate(plan.ops):
+    if fn == "gn_apply":
+        src1, sdt, C1, src2, C2, ab, silu, rs, Bb, H, W, act, adt, raw, rdt = args[:15]
+        C = C1 + C2
+        Ho, Wo = (2 * H, 2 * W) if rs == 1 else ((H // 2, W // 2) if rs == 2 else (H, W))
+        rd = Bb * H * W * (C1 * (2 if sdt == 1 else 4) + C2 * 4)
+        wr = Bb * Ho * Wo * C * ((2 if adt == 1 else 4) + (0 if raw is None else (2 if rdt == 1 else 4)))
+        key = f"{H}x{W} C={C1}+{C2} src={'bf16' if sdt else 'f32'} rs={rs} raw={0 if raw is None else (2 if rdt == 1 else 4)}"
+        a = agg.setdefault(key, [0, 0.0, 0])
+        a[0] += 1; a[1] += plan.last_op_ms[i]; a[2] += rd + wr
+for key, (n, ms, by) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]:
+    print(f"  {key:48s} n={n:3d} {ms:7.3f} ms avg {1e3 * ms / n:7.1f} us  {by / ms / 1e6:7.0f} GB/s")
