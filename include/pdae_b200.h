@@ -138,6 +138,33 @@ int pdae_conv_tc_run(const pdae_conv_tc_plan* plan, pdae_stream_t stream);
 void pdae_conv_tc_destroy(pdae_conv_tc_plan* plan);
 
 
+/* ---- backward (training config: autograd through module.py:278-297,361-384,422-428 and the encoders), fp32 ---------
+ * dgrad: dx[B,H,W,Cin] (+)= conv^T(dy[B,Ho,Wo,Cout]); w_tco fp32 [k*k][Cout][Cin].
+ * wgrad: dw_tcico[k*k][Cin][Cout] += sum_pixels f(x) * dy  (caller zeroes; f = SiLU if a_silu).  colsum: out[n] += sum_m dy. */
+int pdae_conv2d_dgrad_simt(const float* dy, const float* w_tco, float* dx, int B, int H, int W, int Cin, int Cout, int ksize,
+                           int stride, int pad, int accumulate, pdae_stream_t stream);
+int pdae_conv2d_wgrad_simt(const float* x, int in_nchw, int a_silu, const float* dy, float* dw_tcico, int B, int H, int W,
+                           int Cin, int Cout, int ksize, int stride, int pad, pdae_stream_t stream);
+int pdae_colsum(const float* dy, int64_t M, int N, float* out, pdae_stream_t stream);
+/* GroupNorm(+AdaGN)+SiLU(+resample) backward in three passes (forward: y = R(f(a*x+b)), see pdae_gn_apply):
+ *  sums : S[b][c] = (sum du, sum du*x), du = f'(u) * R^T(dy)           (dy has the RESAMPLED spatial size, C channels)
+ *  coef : kk[b][3][C] with dx = k0*du + k1*x + k2; accumulates dgamma/dbeta; writes the (scale|shift) grads of emb/embz
+ *  apply: dx[B,H,W,C1] = k0*du + k1*x + k2 (+ R^T(add)), only for the first C1 channels of a concatenated input.     */
+int pdae_gn_bwd_sums(const float* src1, int C1, const float* src2, int C2, const float* ab, const float* dy, int silu,
+                     int resample, int B, int H, int W, float* S, pdae_stream_t stream);
+int pdae_gn_bwd_coef(const float* S, const double* sums, const float* gamma, const float* beta, const float* emb, int emb_ld,
+                     const float* embz, int embz_ld, int B, int C, int HW, float eps, float* kk, float* dgamma, float* dbeta,
+                     float* demb, int demb_ld, float* dembz, int dembz_ld, pdae_stream_t stream);
+int pdae_gn_bwd_apply(const float* src1, int C1, int C, const float* ab, const float* kk, const float* dy, int silu,
+                      int resample, int B, int H, int W, const float* add, int add_ld, float* dx, pdae_stream_t stream);
+int pdae_softmax_bwd(const float* P, float* dP, int64_t rows, int cols, float alpha, pdae_stream_t stream);
+int pdae_dsilu_mul(const float* g, const float* x, float* out, int64_t n, pdae_stream_t stream);
+int pdae_add_inplace(float* a, const float* b, int64_t n, pdae_stream_t stream);
+int pdae_nchw_to_nhwc(const float* src, float* dst, int B, int C, int HW, pdae_stream_t stream);
+int pdae_gemm_batched_simt(const float* A, int64_t lda, int64_t a_bs, int64_t a_hs, int transA, const float* Bm, int64_t ldb,
+                           int64_t b_bs, int64_t b_hs, int transB, float* C, int64_t ldc, int64_t c_bs, int64_t c_hs, int M,
+                           int N, int K, int batch, int heads, float alpha, pdae_stream_t stream);
+
 /* v2: persistent CTAs, double-buffered TMEM accumulators (epilogue overlaps the next tile's main loop), TMA-store
  * epilogue.  out_dtype PDAE_F32|PDAE_BF16; ch_stats (optional) fp32 [B][Cout][2] accumulates per-channel (sum, sum^2)
  * of the stored values (zero it first); residual needs an fp32 output.  cout_valid > 0 selects the image-head variant:

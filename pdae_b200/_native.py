@@ -16,7 +16,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libpdae_b200.so")
-SOURCES = ["conv_simt.cu", "norm_elementwise.cu", "attention_simt.cu", "conv_tc.cu", "conv_tc2.cu"]
+SOURCES = ["conv_simt.cu", "norm_elementwise.cu", "attention_simt.cu", "conv_tc.cu", "conv_tc2.cu", "backward_simt.cu"]
 
 PDAE_F32, PDAE_BF16 = 0, 1
 RESAMPLE_NONE, RESAMPLE_UP2, RESAMPLE_DOWN2 = 0, 1, 2
@@ -70,6 +70,19 @@ _SIGS = {
     "pdae_noise_p_sample": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int64, _P]),
     "pdae_mlp_mod_ln_act": (c_int, [_P, _P, _P, _P, c_float, c_int, _P, c_int, c_int, c_int, _P]),
     "pdae_copy_cols": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
+    "pdae_conv2d_dgrad_simt": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "pdae_conv2d_wgrad_simt": (c_int, [_P, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "pdae_colsum": (c_int, [_P, c_int64, c_int, _P, _P]),
+    "pdae_gn_bwd_sums": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "pdae_gn_bwd_coef": (c_int, [_P, _P, _P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P, c_int, _P,
+                                 c_int, _P]),
+    "pdae_gn_bwd_apply": (c_int, [_P, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P]),
+    "pdae_softmax_bwd": (c_int, [_P, _P, c_int64, c_int, c_float, _P]),
+    "pdae_dsilu_mul": (c_int, [_P, _P, _P, c_int64, _P]),
+    "pdae_add_inplace": (c_int, [_P, _P, c_int64, _P]),
+    "pdae_nchw_to_nhwc": (c_int, [_P, _P, c_int, c_int, c_int, _P]),
+    "pdae_gemm_batched_simt": (c_int, [_P, c_int64, c_int64, c_int64, c_int, _P, c_int64, c_int64, c_int64, c_int, _P, c_int64,
+                                       c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_float, _P]),
     "pdae_conv_tc_create": (c_int, [POINTER(c_void_p), _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int]),
     "pdae_conv_tc_run": (c_int, [_P, _P]),
     "pdae_conv_tc_destroy": (None, [_P]),

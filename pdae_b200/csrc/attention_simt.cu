@@ -15,6 +15,7 @@ struct GemmArgs {
   long long a_bs, a_hs, b_bs, b_hs, c_bs, c_hs;
   int heads;
   int transB;  // 1: B given as [N][K] (row n, k contiguous) ; 0: [K][N]
+  int transA;  // 1: A given as [K][M] (row k, m contiguous)
   float alpha;
 };
 
@@ -39,7 +40,7 @@ __global__ void __launch_bounds__(256) gemm_batched_kernel(GemmArgs p) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int m = m0 + r, k = k0 + kq + i;
-        As[kq + i][r] = (m < p.M && k < p.K) ? A[(long long)m * p.lda + k] : 0.f;
+        As[kq + i][r] = (m < p.M && k < p.K) ? (p.transA ? A[(long long)k * p.lda + m] : A[(long long)m * p.lda + k]) : 0.f;
       }
     }
     if (p.transB) {
@@ -178,6 +179,22 @@ extern "C" int pdae_transpose_v(const void* qkv_bf16, void* vT_bf16, int B, int 
   return PDAE_OK;
 }
 
+// C[z] = alpha * op(A[z]) * op(B[z]),  z = (b, h) with offsets b * *_bs + h * *_hs  (attention backward GEMMs)
+extern "C" int pdae_gemm_batched_simt(const float* A, int64_t lda, int64_t a_bs, int64_t a_hs, int transA, const float* Bm,
+                                      int64_t ldb, int64_t b_bs, int64_t b_hs, int transB, float* C, int64_t ldc, int64_t c_bs,
+                                      int64_t c_hs, int M, int N, int K, int batch, int heads, float alpha,
+                                      pdae_stream_t stream) {
+  PDAE_REQUIRE(A && Bm && C && heads > 0 && (long long)batch * heads <= 65535, "gemm_batched_simt: bad args");
+  GemmArgs g;
+  g.A = A; g.Bm = Bm; g.C = C; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+  g.a_bs = a_bs; g.a_hs = a_hs; g.b_bs = b_bs; g.b_hs = b_hs; g.c_bs = c_bs; g.c_hs = c_hs;
+  g.heads = heads; g.transA = transA; g.transB = transB; g.alpha = alpha;
+  dim3 grid(cdiv(M, GM), cdiv(N, GN), batch * heads);
+  gemm_batched_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g);
+  PDAE_LAUNCH_CHECK("gemm_batched_kernel");
+  return PDAE_OK;
+}
+
 extern "C" int pdae_attention_simt(const float* qkv, float* out, float* scratch, int B, int T, int C, int heads,
                                    int legacy, pdae_stream_t stream) {
   PDAE_REQUIRE(qkv && out && scratch, "attention_simt: null pointer");
@@ -197,6 +214,7 @@ extern "C" int pdae_attention_simt(const float* qkv, float* out, float* scratch,
   g.a_bs = (long long)T * row; g.a_hs = hs; g.b_bs = (long long)T * row; g.b_hs = hs;
   g.c_bs = (long long)heads * T * T; g.c_hs = (long long)T * T;
   g.transB = 1;
+  g.transA = 0;
   g.alpha = 1.0f / sqrtf((float)ch);
   dim3 grid1(cdiv(T, GM), cdiv(T, GN), B * heads);
   gemm_batched_kernel<<<grid1, 256, 0, s>>>(g);

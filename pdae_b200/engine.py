@@ -111,14 +111,31 @@ class Plan:
         self._tc_handles: List[ctypes.c_void_p] = []
         self._tc2_handles: List[ctypes.c_void_p] = []
         self.n_launch = 0
+        self.keep_all = False
+        self.last_sums = None
+        self._stats_arena = Buf((1,), torch.float32, None, "stats_arena")  # sized at finalize
+        self._stats_arena.keep = True
+        self._stats_arena.first = 0
+        self._stats_arena.last = 0
+        self.bufs.append(self._stats_arena)
+        self._stats_elems = 0
         self.graph = None
         self.flops: List[float] = []  # algorithmic FLOPs (2*MACs) per recorded op, 0 for non-contraction ops
 
     # ---- buffers ----------------------------------------------------------------------------
     def new(self, shape, dtype=torch.float32, name="") -> Buf:
         b = Buf(shape, dtype, None, name)
+        if self.keep_all:  # training plans: every intermediate may be needed by the backward plan -> no recycling
+            b.keep = True
         self.bufs.append(b)
         return b
+
+    def new_zeroed(self, nelems: int) -> "BufView":
+        """fp32 scratch of `nelems` elements inside the arena that ONE memset per replay zeroes (gradient / statistics
+        accumulators written with atomics)."""
+        off = self._stats_elems
+        self._stats_elems += int(nelems)
+        return BufView(self._stats_arena, off)
 
     def fixed(self, t: torch.Tensor) -> Buf:
         assert t.is_contiguous(), "plan tensors must be contiguous"
@@ -164,6 +181,15 @@ class Plan:
             return self._finalize()
 
     def _finalize(self) -> "Plan":
+        self._stats_arena.shape = (max(self._stats_elems, 4),)
+        if self._stats_elems:
+            self.ops.insert(0, ("zero", [self._stats_arena, ctypes.c_int64(self._stats_elems * 4), _STREAM]))
+            self.flops.insert(0, 0.0)
+            for b in self.bufs:  # op indices shift by one
+                if b is not self._stats_arena and b.first is not None:
+                    b.first += 1
+                    b.last += 1
+            self._stats_arena.last = len(self.ops) - 1
         starts: Dict[int, List[Buf]] = {}
         ends: Dict[int, List[Buf]] = {}
         for b in self.bufs:
@@ -367,10 +393,7 @@ class Plan:
                 assert out.dtype == torch.float32
                 self.call("conv_tc", x, wp, bias_b, residual, out, B, H, W, Cin, Cout, k, flops=fl)
                 return None
-            stats = None
-            if want_stats:
-                stats = self.new((B, Cout, 2), torch.float32, "chs")
-                self.call("zero", stats, ctypes.c_int64(B * Cout * 8), _STREAM)
+            stats = self.new_stats(B, Cout) if want_stats else None
             self.call("conv_tc2", x, wp, bias_b, residual, out, _DT[out.dtype], stats, B, H, W, Cin, Cout, k, 0,
                       bn_override or self.bn_override, flops=fl)
             return stats
@@ -424,6 +447,12 @@ class Plan:
             return torch.bfloat16
         return torch.float32
 
+    def new_stats(self, B: int, C: int) -> "BufView":
+        """A [B][C][2] fp32 accumulator inside the plan's statistics arena (ONE memset per replay zeroes them all)."""
+        off = self._stats_elems
+        self._stats_elems += B * C * 2
+        return BufView(self._stats_arena, off)
+
     def ch_stats(self, src: Buf, C: int, *, B, HW) -> Buf:
         """Per-channel (sum, sum^2) of an fp32 NHWC tensor that no conv epilogue produced."""
         chs = self.new((B, C, 2), torch.float32, "chs")
@@ -449,6 +478,7 @@ class Plan:
                       emb, emb_ld, embz, embz_ld, ab, _STREAM)
             return ab
         sums = self.new((B, 32, 2), torch.float64, "gn_sums")
+        self.last_sums = sums
         self.call("gn_stats", src1, C1, src2, C2, B, HW, sums, _STREAM)
         self.call("gn_coef", sums, self.param(gamma), self.param(beta), B, C, HW, ctypes.c_float(1e-5), emb, emb_ld, embz,
                   embz_ld, ab, _STREAM)

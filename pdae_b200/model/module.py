@@ -236,8 +236,10 @@ class _ResBase(PlannedModule):
             self.skip_connection = conv_nd(dims, channels, co, 3 if use_conv else 1, padding=1 if use_conv else 0)
 
     # ---- plan emission --------------------------------------------------------------------------
-    def emit(self, P: Plan, x: Src, emb: Tuple[Buf, int, int], embz: Optional[Tuple[Buf, int, int]] = None) -> Src:
-        """emb / embz = (buffer, element offset of this block's [scale|shift] row slice, leading dim)."""
+    def emit(self, P: Plan, x: Src, emb: Tuple[Buf, int, int], embz: Optional[Tuple[Buf, int, int]] = None,
+             tape: Optional[list] = None) -> Src:
+        """emb / embz = (buffer, element offset of this block's [scale|shift] row slice, leading dim).
+        tape (training plans): receives the buffers the backward pass needs."""
         if self.training and self.dropout > 0:
             raise NotImplementedError("pdae_b200: dropout>0 in train mode needs the training kernels (not built yet)")
         assert x.C == self.channels, f"expected {self.channels} channels, got {x.C}"
@@ -249,6 +251,7 @@ class _ResBase(PlannedModule):
         ident = isinstance(self.skip_connection, nn.Identity)
 
         ab1 = P.gn_coef(x.b1, x.C1, x.b2, x.C2, gn1.weight, gn1.bias, B=B, HW=H * W, stats1=x.s1, stats2=x.s2)
+        sums1 = P.last_sums
         tc1 = P.use_tc(C, Co, 3, 1, H2, W2)
         # raw (un-normalised) copy of the possibly concatenated / resampled input for the skip path
         raw_dtype = None
@@ -275,6 +278,7 @@ class _ResBase(PlannedModule):
             zb, zoff, zld = embz
         ab2 = P.gn_coef(h, Co, None, 0, gn2.weight, gn2.bias, B=B, HW=H2 * W2, emb=eb.at(eoff), emb_ld=eld,
                         embz=zb.at(zoff) if zb is not None else None, embz_ld=zld or 0, stats1=hs)
+        sums2 = P.last_sums
         tc2 = P.use_tc(Co, Co, 3, 1, H2, W2)
         act2, _ = P.gn_apply(h, Co, None, 0, ab2, silu=True, resample=RESAMPLE_NONE, B=B, H=H2, W=W2,
                              act_dtype=torch.bfloat16 if tc2 else torch.float32)
@@ -288,6 +292,9 @@ class _ResBase(PlannedModule):
         out = P.new((B, H2, W2, Co), torch.float32, "res_out")
         os_ = P.conv(act2, conv2.weight, conv2.bias, out, B=B, H=H2, W=W2, Cin=Co, Cout=Co, k=3, residual=resid,
                      want_stats=True)
+        if tape is not None:
+            tape.append(("res", self, dict(x=x, ab1=ab1, sums1=sums1, act1=act1, raw=raw, h=h, sums2=sums2, ab2=ab2, act2=act2,
+                                           emb=emb, embz=embz, rs=rs, ident=ident, H2=H2, W2=W2)))
         return Src(out, Co, B, H2, W2, s1=os_)
 
     def emit_emb(self, P: Plan, emb: Buf, B: int, which: str = "t") -> Tuple[Buf, int, int]:
@@ -376,12 +383,13 @@ class AttentionBlock(PlannedModule):
         self.attention = QKVAttention(self.num_heads) if use_new_attention_order else QKVAttentionLegacy(self.num_heads)
         self.proj_out = zero_module(conv_nd(1, channels, channels, 1))
 
-    def emit(self, P: Plan, x: Src) -> Src:
+    def emit(self, P: Plan, x: Src, tape: Optional[list] = None) -> Src:
         assert x.b2 is None and x.C == self.channels
         B, H, W, C = x.B, x.H, x.W, x.C
         T = H * W
         legacy = isinstance(self.attention, QKVAttentionLegacy)
         ab = P.gn_coef(x.b1, C, None, 0, self.norm.weight, self.norm.bias, B=B, HW=T, stats1=x.s1)
+        sums = P.last_sums
         tcq = P.use_tc(C, 3 * C, 1, 1, H, W)
         xn, _ = P.gn_apply(x.b1, C, None, 0, ab, silu=False, resample=RESAMPLE_NONE, B=B, H=H, W=W,
                            act_dtype=torch.bfloat16 if tcq else torch.float32)
@@ -410,6 +418,8 @@ class AttentionBlock(PlannedModule):
             att = P.new((B, T, C), torch.float32, "att")
             scratch = P.new((B * self.num_heads, T, T), torch.float32, "att_scores")
             P.call("attention_simt", qkv, att, scratch, B, T, C, self.num_heads, int(legacy), _STREAM, flops=4.0 * B * T * T * C)
+            if tape is not None:
+                tape.append(("attn", self, dict(x=x, ab=ab, sums=sums, xn=xn, qkv=qkv, probs=scratch, att=att, legacy=legacy)))
             tcp = P.use_tc(C, C, 1, 1, H, W)
             if tcp:
                 att, _ = P.gn_apply(att, C, None, 0, None, silu=False, resample=RESAMPLE_NONE, B=B, H=H, W=W,
@@ -445,14 +455,14 @@ class AttentionBlock(PlannedModule):
 class TimestepSequential(nn.Sequential, TimestepBlock, TimestepContextBlock):
     """model/module.py:131-140 (dispatch by block type), in plan-emission form."""
 
-    def emit(self, P: Plan, x, emb_of, embz_of=None) -> Src:
+    def emit(self, P: Plan, x, emb_of, embz_of=None, tape: Optional[list] = None) -> Src:
         for layer in self:
             if isinstance(layer, ResBlockShift):
-                x = layer.emit(P, x, emb_of(layer), embz_of(layer))
+                x = layer.emit(P, x, emb_of(layer), embz_of(layer), tape=tape)
             elif isinstance(layer, ResBlock):
-                x = layer.emit(P, x, emb_of(layer))
+                x = layer.emit(P, x, emb_of(layer), tape=tape)
             elif isinstance(layer, AttentionBlock):
-                x = layer.emit(P, x)
+                x = layer.emit(P, x, tape=tape)
             else:
                 raise TypeError(f"unexpected layer {type(layer).__name__} in TimestepSequential")
         return x

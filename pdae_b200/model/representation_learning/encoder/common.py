@@ -83,12 +83,14 @@ class ConvStackEncoder(PlannedModule):
 
     def forward(self, x):
         """x [N,3,S,S] fp32 -> z [N, latent_dim]."""
-        self._check_no_grad(x)
         B, C, H, W = x.shape
         assert C == 3
         if (H, W) != (self.image_size, self.image_size):
             raise ValueError(f"{type(self).__name__} is hard-wired to {self.image_size}x{self.image_size} inputs "
                              f"(View(-1, C*4*4) in the reference), got {H}x{W}")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from ....train import encoder_train_forward
+            return encoder_train_forward(self, x.contiguous())
         plan, (x_in, z) = self._get_plan(("enc", B, H, W), lambda P: self._build(P, B, H, W))
         x_in.tensor.copy_(x)
         plan.run()

@@ -105,9 +105,13 @@ class ShiftUNet(PlannedModule):
 
     def forward(self, x, time, condition):
         """x [N,3,H,W], time int64 [N], condition = z [N, latent_dim] -> (epsilon, shift), both NCHW fp32."""
-        self._check_no_grad(x, condition)
-        if torch.is_grad_enabled() and any(p.requires_grad for m in self._shift_parts() for p in m.parameters()):
-            raise NotImplementedError("pdae_b200: ShiftUNet backward kernels are not built yet; call under torch.no_grad()")
+        if torch.is_grad_enabled() and (condition.requires_grad or
+                                        any(p.requires_grad for m in self._shift_parts() for p in m.parameters())):
+            # training step (gaussian_diffusion.py:234-255): hand-written backward behind a torch.autograd.Function
+            if x.requires_grad:
+                raise NotImplementedError("pdae_b200: gradients w.r.t. x_t are not provided (the reference never needs them)")
+            from ..train import shiftunet_train_forward
+            return shiftunet_train_forward(self, x.contiguous(), time, condition)
         B, C, H, W = x.shape
         assert C == self.input_channel
         plan, (x_in, t_in, z_in, eps, grad) = self.plan_for(B, H, W)

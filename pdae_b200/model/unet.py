@@ -110,13 +110,16 @@ def emit_time_embed(P: Plan, time_embed: Slots, t: Buf, B: int, base: int, E: in
     return emb
 
 
-def emit_head(P: Plan, head: Slots, x: Src, out: Buf) -> None:
+def emit_head(P: Plan, head: Slots, x: Src, out: Buf, tape=None) -> None:
     gn, conv = head[0], head[2]
     B, H, W, C = x.B, x.H, x.W, x.C
     ab = P.gn_coef(x.b1, C, None, 0, gn.weight, gn.bias, B=B, HW=H * W, stats1=x.s1)
+    sums = P.last_sums
     act, _ = P.gn_apply(x.b1, C, None, 0, ab, silu=True, resample=0, B=B, H=H, W=W,
                         act_dtype=P.head_act_dtype(C, conv.weight.shape[0], H, W))
     P.head_conv(act, conv.weight, conv.bias, out, B=B, H=H, W=W, Cin=C, Cout=conv.weight.shape[0])
+    if tape is not None:
+        tape.append(("head", head, dict(x=x, ab=ab, sums=sums, act=act)))
 
 
 def res_blocks_of(*containers) -> List[nn.Module]:

@@ -1,0 +1,446 @@
+"""Training path: forward plans that keep their intermediates + hand-written backward plans, exposed through
+``torch.autograd.Function`` so the reference trainers' ``loss.backward()`` / DDP hooks / Adam / EMA code keeps working
+(trainer/train_representation_learning.py:86-112).
+
+Scope (the PDAE training step, diffusion/gaussian_diffusion.py:234-255): the semantic encoder (all parameters) and the
+trainable half of the ShiftUNet (``label_emb``, ``shift_middle_block``, ``shift_output_blocks``, ``shift_out``); the frozen
+half builds no graph in the reference either (its parameters and x_t do not require grad).  Arithmetic is fp32 on CUDA
+cores (``pdae_conv2d_dgrad_simt`` / ``_wgrad_simt``, ``pdae_gn_bwd_*``, ``pdae_gemm_batched_simt``, ``pdae_softmax_bwd``);
+the tensor-core backward is future work.  Dropout must be 0 (the mask is not implemented).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _native
+from .engine import Buf, BufView, Plan, RESAMPLE_NONE, _STREAM
+from .model.module import AttentionBlock, ResBlock, ResBlockShift, Src
+
+F32 = ctypes.c_float
+
+
+class GradSink:
+    """parameter -> (zero-initialised accumulation view in the backward plan, un-packing function)."""
+
+    def __init__(self):
+        self.items: List[Tuple[torch.Tensor, BufView, Callable[[torch.Tensor], torch.Tensor], int]] = []
+
+    def add(self, param: torch.Tensor, view: BufView, nelems: int, unpack: Callable[[torch.Tensor], torch.Tensor]) -> None:
+        self.items.append((param, view, unpack, nelems))
+
+    def collect(self) -> Dict[int, torch.Tensor]:
+        out: Dict[int, torch.Tensor] = {}
+        for param, view, unpack, n in self.items:
+            flat = view.buf.tensor[view.off: view.off + n]
+            g = unpack(flat).reshape(param.shape).contiguous()
+            out[id(param)] = out[id(param)] + g if id(param) in out else g.clone()
+        return out
+
+
+class Backward:
+    """Emission helpers for the backward plan (fp32)."""
+
+    def __init__(self, BP: Plan, sink: GradSink):
+        self.P = BP
+        self.sink = sink
+        self._fixed: Dict[int, Buf] = {}
+
+    def fx(self, b):
+        if b is None:
+            return None
+        if isinstance(b, BufView):
+            return BufView(self.fx(b.buf), b.off)
+        if b.fixed:
+            return b
+        k = id(b)
+        if k not in self._fixed:
+            self._fixed[k] = self.P.fixed(b.tensor)
+        return self._fixed[k]
+
+    # ---- conv / linear ------------------------------------------------------------------------------------------
+    def conv(self, x, dy: Buf, weight: torch.Tensor, bias: Optional[torch.Tensor], *, B, H, W, Cin, Cout, k, stride=1, pad=None,
+             need_dx=True, in_nchw=False, a_silu=False, trainable=True, w_unpack=None) -> Optional[Buf]:
+        """x: forward input of the conv (NHWC fp32, or NCHW if in_nchw); dy: grad of its output [B,Ho,Wo,Cout]."""
+        P = self.P
+        pad = k // 2 if pad is None else pad
+        Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        kk = k * k
+        if trainable:
+            dw = P.new_zeroed(kk * Cin * Cout)
+            P.call("conv2d_wgrad_simt", self.fx(x), int(in_nchw), int(a_silu), dy, dw, B, H, W, Cin, Cout, k, stride, pad, _STREAM)
+            unpack = w_unpack or (lambda t, kk=kk, Cin=Cin, Cout=Cout: t.view(kk, Cin, Cout).permute(2, 1, 0))
+            self.sink.add(weight, dw, kk * Cin * Cout, unpack)
+            if bias is not None:
+                db = P.new_zeroed(Cout)
+                P.call("colsum", dy, ctypes.c_int64(B * Ho * Wo), Cout, db, _STREAM)
+                self.sink.add(bias, db, Cout, lambda t: t)
+        if not need_dx:
+            return None
+        wt = P.pack((id(weight), "tco"), [weight], lambda: weight.detach().reshape(Cout, Cin, kk).permute(2, 0, 1).float())
+        dx = P.new((B, H, W, Cin), torch.float32, "dx")
+        P.call("conv2d_dgrad_simt", dy, wt, dx, B, H, W, Cin, Cout, k, stride, pad, 0, _STREAM)
+        return dx
+
+    # ---- GroupNorm (+AdaGN) + SiLU (+resample) --------------------------------------------------------------------
+    def gn(self, src: Src, ab: Buf, sums: Buf, gn_mod: nn.GroupNorm, dy: Buf, *, silu: bool, resample: int, emb=None, embz=None,
+           demb=None, dembz=None, add: Optional[Buf] = None, add_ld: int = 0, trainable=True) -> Buf:
+        """dy: grad of the (resampled) normalised activation, all C channels.  Returns dx for the first C1 channels."""
+        P = self.P
+        B, H, W, C1, C2 = src.B, src.H, src.W, src.C1, src.C2
+        C = C1 + C2
+        S = P.new((B, C, 2), torch.float32, "gn_bwd_S")
+        P.call("gn_bwd_sums", self.fx(src.b1), C1, self.fx(src.b2), C2, self.fx(ab), dy, int(silu), resample, B, H, W, S, _STREAM)
+        kk = P.new((B, 3, C), torch.float32, "gn_bwd_k")
+        dg = db = None
+        if trainable:
+            dg, db = P.new_zeroed(C), P.new_zeroed(C)
+            self.sink.add(gn_mod.weight, dg, C, lambda t: t)
+            self.sink.add(gn_mod.bias, db, C, lambda t: t)
+        e, eld = (self.fx(emb[0]).at(emb[1]), emb[2]) if emb is not None else (None, 0)
+        z, zld = (self.fx(embz[0]).at(embz[1]), embz[2]) if embz is not None else (None, 0)
+        de, deld = (demb[0].at(demb[1]), demb[2]) if demb is not None else (None, 0)
+        dz, dzld = (dembz[0].at(dembz[1]), dembz[2]) if dembz is not None else (None, 0)
+        P.call("gn_bwd_coef", S, self.fx(sums), P.param(gn_mod.weight), P.param(gn_mod.bias), e, eld, z, zld, B, C, H * W, F32(1e-5),
+               kk, dg, db, de, deld, dz, dzld, _STREAM)
+        dx = P.new((B, H, W, C1), torch.float32, "gn_dx")
+        P.call("gn_bwd_apply", self.fx(src.b1), C1, C, self.fx(ab), kk, dy, int(silu), resample, B, H, W, add, add_ld, dx, _STREAM)
+        return dx
+
+    # ---- blocks ----------------------------------------------------------------------------------------------------
+    def resblock(self, blk, sv: dict, d_out: Buf, demb, dembz) -> Buf:
+        P = self.P
+        x: Src = sv["x"]
+        B, H, W, C = x.B, x.H, x.W, x.C
+        Co, H2, W2, rs = blk.out_channels, sv["H2"], sv["W2"], sv["rs"]
+        conv1, conv2, gn1, gn2 = blk.in_layers[2], blk.out_layers[3], blk.in_layers[0], blk.out_layers[0]
+        d_act2 = self.conv(sv["act2"], d_out, conv2.weight, conv2.bias, B=B, H=H2, W=W2, Cin=Co, Cout=Co, k=3)
+        hsrc = Src(sv["h"], Co, B, H2, W2)
+        d_h = self.gn(hsrc, sv["ab2"], sv["sums2"], gn2, d_act2, silu=True, resample=RESAMPLE_NONE, emb=sv["emb"], embz=sv["embz"],
+                      demb=demb, dembz=dembz)
+        d_act1 = self.conv(sv["act1"], d_h, conv1.weight, conv1.bias, B=B, H=H2, W=W2, Cin=C, Cout=Co, k=3)
+        if sv["ident"]:
+            add, add_ld = d_out, Co          # skip = x_upd(x): gathered through the same resample^T inside gn_bwd_apply
+        else:
+            sk = blk.skip_connection
+            sk_in = sv["raw"] if sv["raw"] is not None else x.b1
+            add = self.conv(sk_in, d_out, sk.weight, sk.bias, B=B, H=H2, W=W2, Cin=C, Cout=Co, k=sk.kernel_size[0])
+            add_ld = C
+        return self.gn(x, sv["ab1"], sv["sums1"], gn1, d_act1, silu=True, resample=rs, add=add, add_ld=add_ld)
+
+    def attention(self, blk: AttentionBlock, sv: dict, d_out: Buf) -> Buf:
+        P = self.P
+        x: Src = sv["x"]
+        B, H, W, C = x.B, x.H, x.W, x.C
+        T, heads = H * W, blk.num_heads
+        ch = C // heads
+        legacy = sv["legacy"]
+        d_att = self.conv(sv["att"], d_out, blk.proj_out.weight, blk.proj_out.bias, B=B, H=H, W=W, Cin=C, Cout=C, k=1)
+        qkv, probs = self.fx(sv["qkv"]), self.fx(sv["probs"])
+        row = 3 * C
+        hs = 3 * ch if legacy else ch
+        ko, vo = (ch, 2 * ch) if legacy else (C, 2 * C)
+        d_qkv = P.new((B, T, 3 * C), torch.float32, "d_qkv")
+        dP = P.new((B * heads, T, T), torch.float32, "dP")
+        i64 = ctypes.c_int64
+        alpha = 1.0 / math.sqrt(ch)
+
+        def gemm(A, lda, abs_, ahs, tA, Bm, ldb, bbs, bhs, tB, Cc, ldc, cbs, chs, M, N, K, al=1.0):
+            P.call("gemm_batched_simt", A, i64(lda), i64(abs_), i64(ahs), int(tA), Bm, i64(ldb), i64(bbs), i64(bhs), int(tB), Cc,
+                   i64(ldc), i64(cbs), i64(chs), M, N, K, B, heads, F32(al), _STREAM)
+        TT = T * T
+        # dV = P^T dO
+        gemm(probs, T, heads * TT, TT, 1, d_att, C, T * C, ch, 0, d_qkv.at(vo), row, T * row, hs, T, ch, T)
+        # dP = dO V^T
+        gemm(d_att, C, T * C, ch, 0, qkv.at(vo), row, T * row, hs, 1, dP, T, heads * TT, TT, T, T, ch)
+        P.call("softmax_bwd", probs, dP, i64(B * heads * T), T, F32(alpha), _STREAM)   # dS (scale folded in), in place
+        # dQ = dS K ; dK = dS^T Q
+        gemm(dP, T, heads * TT, TT, 0, qkv.at(ko), row, T * row, hs, 0, d_qkv.at(0), row, T * row, hs, T, ch, T)
+        gemm(dP, T, heads * TT, TT, 1, qkv.at(0), row, T * row, hs, 0, d_qkv.at(ko), row, T * row, hs, T, ch, T)
+        d_xn = self.conv(sv["xn"], d_qkv, blk.qkv.weight, blk.qkv.bias, B=B, H=H, W=W, Cin=C, Cout=3 * C, k=1)
+        return self.gn(x, sv["ab"], sv["sums"], blk.norm, d_xn, silu=False, resample=RESAMPLE_NONE, add=d_out, add_ld=C)
+
+    def head(self, head, sv: dict, d_nchw: Buf) -> Buf:
+        P = self.P
+        x: Src = sv["x"]
+        B, H, W, C = x.B, x.H, x.W, x.C
+        conv = head[2]
+        Co = conv.weight.shape[0]
+        dy = P.new((B, H, W, Co), torch.float32, "d_head")
+        P.call("nchw_to_nhwc", d_nchw, dy, B, Co, H * W, _STREAM)
+        d_act = self.conv(sv["act"], dy, conv.weight, conv.bias, B=B, H=H, W=W, Cin=C, Cout=Co, k=3)
+        return self.gn(x, sv["ab"], sv["sums"], head[0], d_act, silu=True, resample=RESAMPLE_NONE)
+
+    def linear_bank(self, emb_in: Buf, d_bank: Buf, lins: List[nn.Linear], offsets: List[int], total: int, *, B, E,
+                    need_dx: bool) -> Optional[Buf]:
+        """Backward of  bank = Linear_cat(SiLU(emb_in)) : per-block weight/bias grads, and (optionally) d emb_in."""
+        P = self.P
+        dw = P.new_zeroed(E * total)
+        P.call("conv2d_wgrad_simt", self.fx(emb_in), 0, 1, d_bank, dw, B, 1, 1, E, total, 1, 1, 0, _STREAM)
+        db = P.new_zeroed(total)
+        P.call("colsum", d_bank, ctypes.c_int64(B), total, db, _STREAM)
+        for lin, off in zip(lins, offsets):
+            n = lin.weight.shape[0]
+            self.sink.add(lin.weight, dw, E * total, lambda t, off=off, n=n: t.view(E, total)[:, off:off + n].t())
+            self.sink.add(lin.bias, db, total, lambda t, off=off, n=n: t[off:off + n])
+        if not need_dx:
+            return None
+        ws = [l.weight for l in lins]
+        wt = P.pack(("bank_tco", id(ws[0])), ws, lambda: torch.cat([w.detach() for w in ws], dim=0).float())  # [total][E]
+        g = P.new((B, E), torch.float32, "d_silu_emb")
+        P.call("conv2d_dgrad_simt", d_bank, wt, g, B, 1, 1, E, total, 1, 1, 0, 0, _STREAM)
+        dx = P.new((B, E), torch.float32, "d_emb")
+        P.call("dsilu_mul", g, self.fx(emb_in), dx, ctypes.c_int64(B * E), _STREAM)
+        return dx
+
+
+# ======================================================================================================================
+# ShiftUNet
+# ======================================================================================================================
+class ShiftUNetTrainer:
+    """Forward (fp32, all intermediates kept) + backward plans of a ShiftUNet for one input shape."""
+
+    def __init__(self, net, B: int, H: int, W: int):
+        from .model.unet import EmbBank, emit_head, emit_time_embed, res_blocks_of
+        self.net = net
+        dev = net._device()
+        for m in net._shift_parts():
+            for mod in m.modules():
+                if isinstance(mod, (ResBlock, ResBlockShift)) and mod.training and mod.dropout > 0:
+                    raise NotImplementedError("pdae_b200 training path: dropout > 0 is not implemented (use dropout=0)")
+        P = Plan(dev, "fp32")
+        P.keep_all = True
+        E, base = net.time_embed_dim, net.base_channel
+        self.x_in = P.new((B, net.input_channel, H, W), torch.float32, "x_nchw")
+        self.t_in = P.new((B,), torch.int64, "t")
+        self.z_in = P.new((B, net.latent_dim), torch.float32, "z")
+        emb = emit_time_embed(P, net.time_embed, self.t_in, B, base, E, dev)
+        shift_emb = P.new((B, E), torch.float32, "shift_emb")
+        P.linear(self.z_in, net.label_emb.weight, net.label_emb.bias, shift_emb, B=B, Cin=net.latent_dim, Cout=E)
+        shift_blocks = res_blocks_of(net.shift_middle_block, net.shift_output_blocks)
+        frozen_blocks = res_blocks_of(net.input_blocks, net.middle_block, net.output_blocks)
+        bank_f = EmbBank(P, frozen_blocks, "t", emb, B, E, "train_t_frozen")
+        bank_t = EmbBank(P, shift_blocks, "t", emb, B, E, "train_t_shift")
+        bank_z = EmbBank(P, shift_blocks, "z", shift_emb, B, E, "train_z_shift")
+        emb_of = lambda blk: (bank_t if id(blk) in bank_t.offsets else bank_f)(blk)
+
+        stem = net.input_blocks[0][0]
+        c0 = stem.weight.shape[0]
+        h0 = P.new((B, H, W, c0), torch.float32, "stem")
+        P.conv(self.x_in, stem.weight, stem.bias, h0, B=B, H=H, W=W, Cin=net.input_channel, Cout=c0, k=3, in_nchw=True)
+        h = Src(h0, c0, B, H, W)
+        hs = [h]
+        for stage in list(net.input_blocks)[1:]:
+            h = stage.emit(P, h, emb_of)
+            hs.append(h)
+        eps_h = net.middle_block.emit(P, h, emb_of)
+        tape: list = []
+        shift_h = net.shift_middle_block.emit(P, h, emb_of, bank_z, tape=tape)
+        for stage, shift_stage in zip(net.output_blocks, net.shift_output_blocks):
+            skip = hs.pop()
+            eps_h = stage.emit(P, eps_h.cat(skip), emb_of)
+            shift_h = shift_stage.emit(P, shift_h.cat(skip), emb_of, bank_z, tape=tape)
+        self.eps = P.new((B, net.output_channel, H, W), torch.float32, "eps_nchw")
+        self.grad = P.new((B, net.input_channel, H, W), torch.float32, "shift_nchw")
+        emit_head(P, net.out, eps_h, self.eps)
+        emit_head(P, net.shift_out, shift_h, self.grad, tape=tape)
+        P.finalize()
+        self.fwd = P
+
+        # ---------------- backward plan ----------------
+        BP = Plan(dev, "fp32")
+        self.sink = GradSink()
+        bw = Backward(BP, self.sink)
+        self.d_grad = BP.new((B, net.input_channel, H, W), torch.float32, "d_shift_nchw")
+        self.d_grad.keep = True
+        d_bank_t = BP.new((B, bank_t.total), torch.float32, "d_bank_t")
+        d_bank_z = BP.new((B, bank_z.total), torch.float32, "d_bank_z")
+        d = None
+        for kind, mod, sv in reversed(tape):
+            if kind == "head":
+                d = bw.head(mod, sv, self.d_grad)
+            elif kind == "res":
+                d = bw.resblock(mod, sv, d, (d_bank_t, bank_t.offsets[id(mod)], bank_t.total),
+                                (d_bank_z, bank_z.offsets[id(mod)], bank_z.total))
+            else:
+                d = bw.attention(mod, sv, d)
+        # d now = grad wrt the (frozen) middle input: not needed.  Embedding paths:
+        lt = [b.emb_layers[1] for b in shift_blocks]
+        lz = [b.emb_z_layers[1] for b in shift_blocks]
+        bw.linear_bank(emb, d_bank_t, lt, [bank_t.offsets[id(b)] for b in shift_blocks], bank_t.total, B=B, E=E, need_dx=False)
+        d_shift_emb = bw.linear_bank(shift_emb, d_bank_z, lz, [bank_z.offsets[id(b)] for b in shift_blocks], bank_z.total, B=B,
+                                     E=E, need_dx=True)
+        self.dz = bw.conv(self.z_in, d_shift_emb, net.label_emb.weight, net.label_emb.bias, B=B, H=1, W=1, Cin=net.latent_dim,
+                          Cout=E, k=1, w_unpack=lambda t, L=net.latent_dim: t.view(L, E).t())
+        self.dz.keep = True
+        BP.finalize()
+        self.bwd = BP
+        self.params = [p for m in net._shift_parts() for p in m.parameters()]
+
+    def forward(self, x, t, z):
+        self.x_in.tensor.copy_(x)
+        self.t_in.tensor.copy_(t)
+        self.z_in.tensor.copy_(z)
+        self.fwd.run()
+        return self.eps.tensor.clone(), self.grad.tensor.clone()
+
+    def backward(self, d_grad):
+        self.d_grad.tensor.copy_(d_grad)
+        self.bwd.run()
+        grads = self.sink.collect()
+        return self.dz.tensor.reshape(self.z_in.shape).clone(), [grads.get(id(p)) for p in self.params]
+
+
+class _ShiftUNetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, trainer: ShiftUNetTrainer, x, t, z, *params):
+        ctx.trainer = trainer
+        ctx.z_needs = z.requires_grad
+        with torch.no_grad():
+            eps, grad = trainer.forward(x, t, z)
+        ctx.mark_non_differentiable(eps)
+        return eps, grad
+
+    @staticmethod
+    def backward(ctx, d_eps, d_grad):
+        tr = ctx.trainer
+        with torch.no_grad():
+            dz, pgrads = tr.backward(d_grad.contiguous())
+        return (None, None, None, dz if ctx.z_needs else None, *pgrads)
+
+
+def shiftunet_train_forward(net, x, t, z):
+    B, C, H, W = x.shape
+    key = ("train", B, H, W)
+    cache = net.__dict__.setdefault("_train_cache", {})
+    tr = cache.get(key)
+    if tr is None or tr.fwd.stale() or tr.bwd.stale():
+        tr = ShiftUNetTrainer(net, B, H, W)
+        cache[key] = tr
+    return _ShiftUNetFn.apply(tr, x, t, z, *tr.params)
+
+
+# ======================================================================================================================
+# Semantic encoder
+# ======================================================================================================================
+class EncoderTrainer:
+    def __init__(self, enc, B: int, H: int, W: int):
+        self.enc = enc
+        dev = enc._device()
+        P = Plan(dev, "fp32")
+        P.keep_all = True
+        self.x_in = P.new((B, 3, H, W), torch.float32, "x_nchw")
+        tape = []          # ("conv", mod, dict) / ("attn", ...) / ("fc", ...)
+        h: Optional[Src] = None
+        C = 3
+        pend = None        # (ab, sums, gn module) of the GN whose SiLU output feeds the next conv / fc
+        self.z = None
+        for kind, idx in enc._order:
+            m = enc.encoder[idx]
+            if kind == "conv":
+                Co = m.weight.shape[0]
+                Ho, Wo = H // 2, W // 2
+                out = P.new((B, Ho, Wo, Co), torch.float32, "enc_h")
+                if h is None:
+                    P.conv(self.x_in, m.weight, m.bias, out, B=B, H=H, W=W, Cin=3, Cout=Co, k=3, stride=2, pad=1, in_nchw=True)
+                    tape.append(("conv", m, dict(x=None, act=self.x_in, nchw=True, B=B, H=H, W=W, Cin=3, Cout=Co, gn=None)))
+                else:
+                    act, _ = P.gn_apply(h.b1, C, None, 0, pend[0], silu=True, resample=RESAMPLE_NONE, B=B, H=H, W=W,
+                                        act_dtype=torch.float32)
+                    P.conv(act, m.weight, m.bias, out, B=B, H=H, W=W, Cin=C, Cout=Co, k=3, stride=2, pad=1)
+                    tape.append(("conv", m, dict(x=h, act=act, nchw=False, B=B, H=H, W=W, Cin=C, Cout=Co, gn=pend)))
+                h, C, H, W = Src(out, Co, B, Ho, Wo), Co, Ho, Wo
+            elif kind == "gn":
+                ab = P.gn_coef(h.b1, C, None, 0, m.weight, m.bias, B=B, HW=H * W)
+                pend = (ab, P.last_sums, m)
+            elif kind == "attn":
+                h = m.emit(P, h, tape=tape)
+            else:
+                act, _ = P.gn_apply(h.b1, C, None, 0, pend[0], silu=True, resample=RESAMPLE_NONE, B=B, H=H, W=W,
+                                    act_dtype=torch.float32)
+                wt, HW = m.weight, H * W
+                wp = P.pack((id(wt), "enc_fc"), [wt],
+                            lambda: wt.detach().reshape(-1, C, HW).permute(2, 1, 0).reshape(HW * C, -1).float())
+                self.z = P.new((B, enc.latent_dim), torch.float32, "z")
+                P.linear_packed(act, wp, P.param(m.bias), self.z, B=B, Cin=HW * C, Cout=enc.latent_dim)
+                tape.append(("fc", m, dict(x=h, act=act, gn=pend, B=B, H=H, W=W, C=C)))
+        P.finalize()
+        self.fwd = P
+
+        BP = Plan(dev, "fp32")
+        self.sink = GradSink()
+        bw = Backward(BP, self.sink)
+        L = enc.latent_dim
+        self.dz = BP.new((B, L), torch.float32, "dz")
+        self.dz.keep = True
+        d = self.dz
+        for kind, m, sv in reversed(tape):
+            if kind == "fc":
+                Bc, Hh, Ww, Cc = sv["B"], sv["H"], sv["W"], sv["C"]
+                HW = Hh * Ww
+                K = HW * Cc
+                dw = BP.new_zeroed(K * L)
+                BP.call("conv2d_wgrad_simt", bw.fx(sv["act"]), 0, 0, d, dw, Bc, 1, 1, K, L, 1, 1, 0, _STREAM)
+                # packed [HW*C][L] (NHWC flatten) -> reference layout [L][C*HW] (NCHW flatten)
+                self.sink.add(m.weight, dw, K * L, lambda t, HW=HW, Cc=Cc: t.view(HW, Cc, L).permute(2, 1, 0).reshape(L, Cc * HW))
+                db = BP.new_zeroed(L)
+                BP.call("colsum", d, ctypes.c_int64(Bc), L, db, _STREAM)
+                self.sink.add(m.bias, db, L, lambda t: t)
+                wt = m.weight
+                wtco = BP.pack((id(wt), "enc_fc_tco"), [wt],
+                               lambda: wt.detach().reshape(L, Cc, HW).permute(0, 2, 1).reshape(L, HW * Cc).float())
+                d_act = BP.new((Bc, Hh, Ww, Cc), torch.float32, "d_fc_in")
+                BP.call("conv2d_dgrad_simt", d, wtco, d_act, Bc, 1, 1, K, L, 1, 1, 0, 0, _STREAM)
+                ab, sums, gnm = sv["gn"]
+                d = bw.gn(sv["x"], ab, sums, gnm, d_act, silu=True, resample=RESAMPLE_NONE)
+            elif kind == "attn":
+                d = bw.attention(m, sv, d)
+            else:
+                first = sv["x"] is None
+                d_act = bw.conv(sv["act"], d, m.weight, m.bias, B=sv["B"], H=sv["H"], W=sv["W"], Cin=sv["Cin"], Cout=sv["Cout"],
+                                k=3, stride=2, pad=1, need_dx=not first, in_nchw=sv["nchw"])
+                if not first:
+                    ab, sums, gnm = sv["gn"]
+                    d = bw.gn(sv["x"], ab, sums, gnm, d_act, silu=True, resample=RESAMPLE_NONE)
+        BP.finalize()
+        self.bwd = BP
+        self.params = list(enc.parameters())
+
+    def forward(self, x):
+        self.x_in.tensor.copy_(x)
+        self.fwd.run()
+        return self.z.tensor.clone()
+
+    def backward(self, dz):
+        self.dz.tensor.copy_(dz)
+        self.bwd.run()
+        grads = self.sink.collect()
+        return [grads.get(id(p)) for p in self.params]
+
+
+class _EncoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, trainer: EncoderTrainer, x, *params):
+        ctx.trainer = trainer
+        with torch.no_grad():
+            return trainer.forward(x)
+
+    @staticmethod
+    def backward(ctx, dz):
+        with torch.no_grad():
+            pg = ctx.trainer.backward(dz.contiguous())
+        return (None, None, *pg)
+
+
+def encoder_train_forward(enc, x):
+    B, C, H, W = x.shape
+    cache = enc.__dict__.setdefault("_train_cache", {})
+    tr = cache.get((B, H, W))
+    if tr is None or tr.fwd.stale() or tr.bwd.stale():
+        tr = EncoderTrainer(enc, B, H, W)
+        cache[(B, H, W)] = tr
+    return _EncoderFn.apply(tr, x, *tr.params)

@@ -1,0 +1,102 @@
+"""Training step (diffusion/gaussian_diffusion.py:234-255): loss and EVERY trainable gradient of the hand-written
+backward vs (a) the fixture recorded from the real reference and (b) torch.autograd through the CPU oracle."""
+import pytest
+import torch
+
+from oracle import pdae_oracle as O
+from tests import cases
+from tests.util import assert_close, load_golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _loss(gd, enc, dec, x0, t, noise):
+    z = enc(x0)
+    x_t = gd.q_sample(x0, t, noise)
+    eps, grad = dec(x_t, t, z)
+    s = x0.shape
+    target = eps + gd.extract_coef_at_t(gd.shift_coef, t, s) * grad
+    return gd.p_loss(noise, target, weight=gd.extract_coef_at_t(gd.weight, t, s))
+
+
+def test_representation_learning_step_matches_reference_and_oracle():
+    from pdae_b200.diffusion.gaussian_diffusion import GaussianDiffusion
+    from pdae_b200.utils.synth import synth_images
+    cfg, g = load_golden("train_representation_learning")
+    dec, _ = cases.model_case({"kind": "shiftunet", "cfg": cfg["cfg"], "size": 64})
+    enc, _ = cases.model_case({"kind": "encoder", "size": 64})
+    x0 = synth_images(2, 3, 64, 31)
+    # ---- oracle autograd on the CPU (same weights, same t / noise as the reference run) ----
+    dsd = {k: v.requires_grad_(k.startswith(("label_emb", "shift_"))) for k, v in cases.sd_of(dec).items()}
+    esd = {k: v.requires_grad_(True) for k, v in cases.sd_of(enc).items()}
+    D = O.DiffusionOracle(cases.DIFF)
+    ref_loss = D.representation_learning_loss(lambda x: O.encoder_forward(esd, "celeba64", x),
+                                              lambda x, t, z: O.shiftunet_forward(dsd, cfg["cfg"], x, t, z), x0, g["t"], g["noise"])
+    ref_loss.backward()
+    # ---- native path ----
+    dev = torch.device("cuda")
+    dec, enc = dec.cuda().train(), enc.cuda().train()
+    dec.freeze()
+    dec.set_train_mode()
+    dec.precision = enc.precision = "fp32"
+    gd = GaussianDiffusion(cases.DIFF, dev)
+    loss = _loss(gd, enc, dec, x0.cuda(), g["t"].cuda(), g["noise"].cuda())
+    assert_close(loss, g["loss"], rtol=1e-4, atol=1e-7, what="loss vs reference fixture")
+    assert_close(loss, ref_loss, rtol=1e-4, atol=1e-7, what="loss vs oracle")
+    loss.backward()
+    named = dict(dec.named_parameters())
+    n_grad = sum(1 for p in list(dec.parameters()) + list(enc.parameters()) if p.grad is not None)
+    assert n_grad == cfg["n_params_with_grad"], (n_grad, cfg["n_params_with_grad"])
+    assert all(p.grad is None for k, p in named.items() if not k.startswith(("label_emb", "shift_")))
+    worst = (0.0, "")
+    bad = []
+    gmax = max(float(v.grad.abs().max()) for v in list(dsd.values()) + list(esd.values()) if v.grad is not None)
+    floor = 2e-4 * gmax   # absolute floor relative to the largest gradient entry of the step
+    print(f"largest |grad| entry {gmax:.3e}, absolute floor {floor:.3e}")
+    for prefix, mod, sd in (("dec.", dec, dsd), ("enc.", enc, esd)):
+        for k, p in mod.named_parameters():
+            if sd[k].grad is None:
+                continue
+            r = rel_l2(p.grad, sd[k].grad)
+            err = float((p.grad.cpu() - sd[k].grad).abs().max())
+            ref_max = float(sd[k].grad.abs().max())
+            # biases feeding a GroupNorm have analytically ~zero gradient (large sums that cancel): absolute floor
+            if r >= 2e-3 and err > 2e-3 * ref_max + floor:
+                bad.append((prefix + k, tuple(p.shape), round(r, 4), f"err={err:.2e} ref_max={ref_max:.2e}"))
+            elif ref_max > 50 * floor:
+                worst = max(worst, (r, prefix + k))
+    print("worst grad rel-L2:", worst)
+    assert not bad, "gradients off: " + "; ".join(map(str, bad[:40]))
+    # spot-check against the fixture from the real reference
+    for key, ref in (("label_emb.weight", "g_label_emb_weight"), ("shift_out.2.weight", "g_shift_out_2_weight"),
+                     ("shift_middle_block.0.in_layers.2.weight", "g_shift_middle_block_0_in_layers_2_weight"),
+                     ("shift_output_blocks.0.0.emb_z_layers.1.weight", "g_shift_output_blocks_0_0_emb_z_layers_1_weight")):
+        got = named[key].grad.flatten()[:512].cpu()
+        assert rel_l2(got, g[ref]) < 2e-3, key
+        assert_close(named[key].grad.double().norm().float(), g["n" + ref], rtol=2e-3, atol=0, what=key + " norm")
+    assert rel_l2(dict(enc.named_parameters())["encoder.0.weight"].grad.flatten()[:512].cpu(), g["g_enc_encoder_0_weight"]) < 2e-3
+
+
+def test_second_step_after_optimizer_update_uses_new_weights():
+    """Plans cache packed weights: an Adam step must be seen by the next forward/backward."""
+    from pdae_b200.diffusion.gaussian_diffusion import GaussianDiffusion
+    from pdae_b200.utils.synth import synth_images
+    cfg, g = load_golden("train_representation_learning")
+    dec, _ = cases.model_case({"kind": "shiftunet", "cfg": cfg["cfg"], "size": 64})
+    enc, _ = cases.model_case({"kind": "encoder", "size": 64})
+    dec, enc = dec.cuda().train(), enc.cuda().train()
+    dec.freeze()
+    dec.set_train_mode()
+    dec.precision = enc.precision = "fp32"
+    gd = GaussianDiffusion(cases.DIFF, torch.device("cuda"))
+    params = [p for p in list(dec.parameters()) + list(enc.parameters()) if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-3)
+    x0, t, noise = synth_images(2, 3, 64, 31).cuda(), g["t"].cuda(), g["noise"].cuda()
+    losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        loss = _loss(gd, enc, dec, x0, t, noise)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert losses[2] < losses[0], losses   # same batch, three Adam steps: the loss must go down
