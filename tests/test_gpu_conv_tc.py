@@ -20,15 +20,15 @@ def _run_conv(x, w, bias, resid, precision, k, out_dtype=torch.float32, want_sta
     out.keep = True
     st = P.conv(P.fixed(x), w, bias, out, B=B, H=H, W=W, Cin=Cin, Cout=Cout, k=k,
                 residual=P.fixed(resid) if resid is not None else None, want_stats=want_stats, bn_override=bn)
-    if st is not None:
-        st.keep = True
     P.finalize()
     P.run()
     P.run()   # a second replay must give the same answer (persistent-kernel barriers / stats zeroing re-arm correctly)
     torch.cuda.synchronize()
     kinds = [op[0] for op in P.ops if op[0] != "zero"]
-    if want_stats:
-        return out.tensor.clone(), kinds, (st.tensor.clone() if st is not None else None)
+    if want_stats:  # `st` is a view into the plan's (zeroed-once-per-replay) statistics arena
+        n = x.shape[0] * w.shape[0] * 2
+        return out.tensor.clone(), kinds, (st.buf.tensor[st.off: st.off + n].reshape(x.shape[0], w.shape[0], 2).clone()
+                                           if st is not None else None)
     return out.tensor.clone(), kinds
 
 

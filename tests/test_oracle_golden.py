@@ -157,8 +157,8 @@ def test_loop_sensitivity():
     sd = cases.sd_of(m)
     dec = lambda x, t, z: O.shiftunet_forward(sd, cfg["cfg"], x, t, z)
     z, xT = synth_normal((2, 64), 27), synth_normal((2, 3, 16, 16), 25)
+    a = g["sample"]   # unperturbed result (== test_loops)
     with torch.no_grad():
-        a = D.representation_learning_ddim_sample("ddim10", dec, xT, z)
         b = D.representation_learning_ddim_sample("ddim10", dec, xT + 1e-5 * synth_normal((2, 3, 16, 16), 99), z)
     amp = float((a - b).abs().max()) / 1e-5
     assert 1.0 < amp < 1e3, amp
