@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(256) gn_apply8_kernel(const TSrc* __restrict__
   const int C = C1 + C2, L = C >> 3;
   const int b = blockIdx.y;
   const long long items = HW * L;
+#pragma unroll 2
   for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
        it += (long long)gridDim.x * blockDim.x) {
     const int cq = (int)(it % L);
@@ -540,8 +541,9 @@ extern "C" int pdae_gn_apply(const void* src1, int src1_dtype, int C1, const flo
       (src1_dtype == PDAE_F32 || !out_raw)) {
     const long long HW = (long long)H * W;
     const long long items = HW * ((C1 + C2) / 8);
-    int gx = cdiv(items, 256);
-    if (gx > 148 * 8) gx = 148 * 8;
+    int gx = cdiv(items, 512);          // two items per thread (unrolled) keeps more loads in flight
+    if (gx > 148 * 16) gx = 148 * 16;
+    if (gx < 1) gx = 1;
     dim3 grid(gx, B);
     if (src1_dtype == PDAE_BF16)
       gn_apply8_kernel<bf, float><<<grid, 256, 0, s>>>((const bf*)src1, C1, src2, C2, ab, silu, HW, (bf*)out_act, (float*)nullptr);
