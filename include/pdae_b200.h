@@ -76,8 +76,8 @@ int pdae_gn_coef(const double* sums, const float* gamma, const float* beta, int 
 /* out_act = resample( f(a*x+b) ) over the virtual concat; f = SiLU if silu.  ab == NULL -> a=1,b=0.
  * out_raw (optional) = resample(x) (the un-normalised input, for the skip path).  H, W are the SOURCE
  * dims; outputs are [B][H'][W'][C1+C2] with H' = 2H (UP2), H/2 (DOWN2) or H.                          */
-int pdae_gn_apply(const void* src1, int src1_dtype, int C1, const float* src2, int C2, const float* ab, int silu,
-                  int resample, int B, int H, int W, void* out_act, int act_dtype, void* out_raw, int raw_dtype,
+int pdae_gn_apply(const void* src1, int src1_dtype, int C1, const void* src2, int src2_dtype, int C2, const float* ab,
+                  int silu, int resample, int B, int H, int W, void* out_act, int act_dtype, void* out_raw, int raw_dtype,
                   pdae_stream_t stream);
 
 /* Per-channel variant of the statistics (what the tensor-core conv epilogue accumulates): chs[b][c] = (sum, sum^2)
@@ -167,11 +167,11 @@ int pdae_gemm_batched_simt(const float* A, int64_t lda, int64_t a_bs, int64_t a_
 
 /* v2: persistent CTAs, double-buffered TMEM accumulators (epilogue overlaps the next tile's main loop), TMA-store
  * epilogue.  out_dtype PDAE_F32|PDAE_BF16; ch_stats (optional) fp32 [B][Cout][2] accumulates per-channel (sum, sum^2)
- * of the stored values (zero it first); residual needs an fp32 output.  cout_valid > 0 selects the image-head variant:
+ * of the stored values (zero it first); a residual is read in the OUTPUT's dtype.  cout_valid > 0 selects the image-head variant:
  * Cout must be 16 (weights zero-padded), `out` is NCHW fp32 [B][cout_valid][H][W].  bn_override: 0 = auto.              */
 typedef struct pdae_conv_tc2_plan pdae_conv_tc2_plan;
 int pdae_conv_tc2_create(pdae_conv_tc2_plan** plan, const void* in_bf16, const void* w_bf16, const float* bias,
-                         const float* residual, void* out, int out_dtype, float* ch_stats, int B, int H, int W, int Cin,
+                         const void* residual, void* out, int out_dtype, float* ch_stats, int B, int H, int W, int Cin,
                          int Cout, int ksize, int cout_valid, int bn_override);
 /* Batched GEMM on the same kernel (tensor-core attention, model/module.py:452-456,483-487): for each batch item
  * out[M x N] = A[M x K] * Bm[N x K]^T, both operands bf16 K-major; *_ld = elements between rows, *_bs = between items.

@@ -58,7 +58,8 @@ _SIGS = {
     "pdae_conv3x3_smalln": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "pdae_gn_stats": (c_int, [_P, c_int, _P, c_int, c_int, c_int, _P, _P]),
     "pdae_gn_coef": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_float, _P, c_int, _P, c_int, _P, _P]),
-    "pdae_gn_apply": (c_int, [_P, c_int, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, _P]),
+    "pdae_gn_apply": (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int,
+                              _P]),
     "pdae_zero": (c_int, [_P, c_int64, _P]),
     "pdae_ch_stats": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     "pdae_gn_coef_ch": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_float, _P, c_int, _P, c_int, _P, _P]),

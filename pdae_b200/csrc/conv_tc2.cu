@@ -274,7 +274,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       } else {
         const int CW = p.out_bf16 ? 64 : 32;  // accumulator columns per staging tile (128-byte rows)
         const int nch = BN / CW;
-        if (p.has_res && elected) {            // residual chunk 0 of this tile
+        if (p.has_res && elected) {            // residual chunk 0 of this tile (issued before the accumulator is needed)
           const uint32_t rb = s_u32(&bar_res[rc & 1]);
           mb_expect_tx(rb, T2_STG_BYTES);
           tma_ld4(stg_res + (uint32_t)(rc & 1) * T2_STG_BYTES, &tmR, rb, n0, x0, y0, b0);
@@ -304,20 +304,34 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               }
             }
           }
-          if (p.has_res) {                      // fp32 output only (CW == 32)
+          if (p.has_res) {                      // the residual has the output's dtype: CW columns = one 128-byte row
             if (elected && c + 1 < nch) {
               const uint32_t rb = s_u32(&bar_res[(rc + 1) & 1]);
               mb_expect_tx(rb, T2_STG_BYTES);
-              tma_ld4(stg_res + (uint32_t)((rc + 1) & 1) * T2_STG_BYTES, &tmR, rb, n0 + (c + 1) * 32, x0, y0, b0);
+              tma_ld4(stg_res + (uint32_t)((rc + 1) & 1) * T2_STG_BYTES, &tmR, rb, n0 + (c + 1) * CW, x0, y0, b0);
             }
             mb_wait(s_u32(&bar_res[rc & 1]), (uint32_t)((rc >> 1) & 1));
             const uint32_t rbuf = stg_res + (uint32_t)(rc & 1) * T2_STG_BYTES;
+            if (p.out_bf16) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 rv;
-              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(rv.x), "=f"(rv.y), "=f"(rv.z), "=f"(rv.w)
-                           : "r"(rbuf + swz(r, j)));
-              val[4 * j + 0] += rv.x; val[4 * j + 1] += rv.y; val[4 * j + 2] += rv.z; val[4 * j + 3] += rv.w;
+              for (int j = 0; j < 8; ++j) {
+                uint32_t w[4];
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
+                             : "r"(rbuf + swz(r, j)));
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                  val[8 * j + 2 * h] += __uint_as_float(w[h] << 16);
+                  val[8 * j + 2 * h + 1] += __uint_as_float(w[h] & 0xffff0000u);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 rv;
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(rv.x), "=f"(rv.y), "=f"(rv.z), "=f"(rv.w)
+                             : "r"(rbuf + swz(r, j)));
+                val[4 * j + 0] += rv.x; val[4 * j + 1] += rv.y; val[4 * j + 2] += rv.z; val[4 * j + 3] += rv.w;
+              }
             }
             ++rc;
           }
@@ -492,7 +506,7 @@ struct pdae_conv_tc2_plan {
 static int g_num_sms = 0;
 
 struct Tc2Desc {
-  const void* in; const void* w; const float* bias; const float* residual; void* out;
+  const void* in; const void* w; const float* bias; const void* residual; void* out;
   int out_dtype; float* ch_stats;
   int B, H, W, Cin, Cout, ksize, cout_valid, bn_override;
   long long in_ld;            // elements between consecutive pixels of the A operand
@@ -511,7 +525,7 @@ static int tc2_create(pdae_conv_tc2_plan** plan_out, const Tc2Desc& d) {
   PDAE_REQUIRE(head ? (Cout == 16 && cout_valid <= 16 && d.out_dtype == PDAE_F32 && !d.residual && !d.ch_stats) : (Cout % 64 == 0),
                "conv_tc2_create: unsupported Cout=%d (cout_valid=%d)", Cout, cout_valid);
   PDAE_REQUIRE(d.out_dtype == PDAE_F32 || d.out_dtype == PDAE_BF16, "conv_tc2_create: bad out dtype");
-  PDAE_REQUIRE(!(d.residual && d.out_dtype != PDAE_F32), "conv_tc2_create: a residual needs an fp32 output");
+  // (a residual is read in the output's dtype: fp32 with an fp32 output, bf16 with a bf16 output)
   PDAE_REQUIRE(((uintptr_t)d.in & 15) == 0 && ((uintptr_t)d.w & 15) == 0 && ((uintptr_t)d.out & 15) == 0 &&
                    ((uintptr_t)d.residual & 15) == 0 && ((uintptr_t)d.bias & 15) == 0,
                "conv_tc2_create: pointers must be 16-byte aligned");
@@ -600,9 +614,10 @@ static int tc2_create(pdae_conv_tc2_plan** plan_out, const Tc2Desc& d) {
                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("O", (int)r);
     if (a.has_res) {
-      cuuint64_t rstr[3] = {(cuuint64_t)Cout * 4, (cuuint64_t)W * Cout * 4, (cuuint64_t)H * W * Cout * 4};
-      cuuint32_t rbox[4] = {32, (cuuint32_t)a.tw, (cuuint32_t)a.th, (cuuint32_t)a.tn};
-      r = enc(&pl->tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(d.residual), dims, rstr, rbox, estr4,
+      cuuint64_t rstr[3] = {(cuuint64_t)Cout * esz, (cuuint64_t)W * Cout * esz, (cuuint64_t)H * W * Cout * esz};
+      cuuint32_t rbox[4] = {(cuuint32_t)(a.out_bf16 ? 64 : 32), (cuuint32_t)a.tw, (cuuint32_t)a.th, (cuuint32_t)a.tn};
+      r = enc(&pl->tmR, a.out_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+              const_cast<void*>((const void*)d.residual), dims, rstr, rbox, estr4,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail("R", (int)r);
@@ -613,7 +628,7 @@ static int tc2_create(pdae_conv_tc2_plan** plan_out, const Tc2Desc& d) {
 }
 
 extern "C" int pdae_conv_tc2_create(pdae_conv_tc2_plan** plan_out, const void* in_bf16, const void* w_bf16, const float* bias,
-                                    const float* residual, void* out, int out_dtype, float* ch_stats, int B, int H, int W,
+                                    const void* residual, void* out, int out_dtype, float* ch_stats, int B, int H, int W,
                                     int Cin, int Cout, int ksize, int cout_valid, int bn_override) {
   Tc2Desc d;
   d.in = in_bf16; d.w = w_bf16; d.bias = bias; d.residual = residual; d.out = out; d.out_dtype = out_dtype;

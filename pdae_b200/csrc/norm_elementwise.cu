@@ -184,62 +184,63 @@ __device__ __forceinline__ float4 affine_act(float4 v, float4 a, float4 b, int s
 }
 
 // Non-resampling, bf16-activation fast path: 8 channels (16 B of bf16 output) per work item, fast SiLU.
-template <typename TSrc, typename TRaw>
-__global__ void __launch_bounds__(256) gn_apply8_kernel(const TSrc* __restrict__ s1, int C1, const float* __restrict__ s2,
-                                                        int C2, const float* __restrict__ ab, int silu, long long HW,
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float4& v0, float4& v1) {
+  if (sizeof(T) == 2) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+    const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]), f2 = __bfloat1622float2(h[2]),
+                 f3 = __bfloat1622float2(h[3]);
+    v0 = make_float4(f0.x, f0.y, f1.x, f1.y);
+    v1 = make_float4(f2.x, f2.y, f3.x, f3.y);
+  } else {
+    v0 = *reinterpret_cast<const float4*>(p);
+    v1 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + 4);
+  }
+}
+
+template <typename TSrc, typename TSrc2, typename TRaw>
+__global__ void __launch_bounds__(256) gn_apply8_kernel(const TSrc* __restrict__ s1, int C1, const TSrc2* __restrict__ s2,
+                                                        int C2, const float* __restrict__ ab, int silu, int HW,
                                                         __nv_bfloat16* __restrict__ out_act, TRaw* __restrict__ out_raw) {
+  // thread -> fixed channel octet (tid % L), pixels strided: no division and no coefficient reload inside the loop.
+  // blockDim.x = L * floor(256 / L) with L = C/8 <= 256; the host falls back to the generic kernel otherwise.
   const int C = C1 + C2, L = C >> 3;
   const int b = blockIdx.y;
-  const long long items = HW * L;
-#pragma unroll 2
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items;
-       it += (long long)gridDim.x * blockDim.x) {
-    const int cq = (int)(it % L);
-    const long long pix = it / L;
-    const int c = cq * 8;
+  const int cq = threadIdx.x % L, prow = threadIdx.x / L, ppc = blockDim.x / L;   // pixels per CTA pass (blockDim = L * ppc)
+  const int c = cq * 8;
+  float4 a0 = make_float4(1.f, 1.f, 1.f, 1.f), a1 = a0, b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+  if (ab) {
+    const float* pa = ab + ((long long)b * 2 + 0) * C + c;
+    const float* pb = ab + ((long long)b * 2 + 1) * C + c;
+    a0 = *reinterpret_cast<const float4*>(pa); a1 = *reinterpret_cast<const float4*>(pa + 4);
+    b0 = *reinterpret_cast<const float4*>(pb); b1 = *reinterpret_cast<const float4*>(pb + 4);
+  }
+  const bool first = c < C1;
+  const TSrc* p1 = s1 + (long long)b * HW * C1 + c;
+  const TSrc2* p2 = s2 + (long long)b * HW * C2 + (c - C1);
+  __nv_bfloat16* po = out_act + (long long)b * HW * C + c;
+  TRaw* pr = out_raw ? out_raw + (long long)b * HW * C + c : nullptr;
+  const int stride = gridDim.x * ppc;
+#pragma unroll 4
+  for (int pix = blockIdx.x * ppc + prow; pix < HW; pix += stride) {
     float4 v0, v1;
-    if (c < C1) {
-      const TSrc* p = s1 + ((long long)b * HW + pix) * C1 + c;
-      if (sizeof(TSrc) == 2) {
-        const uint4 u = *reinterpret_cast<const uint4*>(p);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-        const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]), f2 = __bfloat1622float2(h[2]),
-                     f3 = __bfloat1622float2(h[3]);
-        v0 = make_float4(f0.x, f0.y, f1.x, f1.y);
-        v1 = make_float4(f2.x, f2.y, f3.x, f3.y);
-      } else {
-        v0 = *reinterpret_cast<const float4*>(p);
-        v1 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + 4);
-      }
-    } else {
-      const float* p = s2 + ((long long)b * HW + pix) * C2 + (c - C1);
-      v0 = *reinterpret_cast<const float4*>(p);
-      v1 = *reinterpret_cast<const float4*>(p + 4);
-    }
-    float4 a0 = make_float4(1.f, 1.f, 1.f, 1.f), a1 = a0, b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-    if (ab) {
-      const float* pa = ab + ((long long)b * 2 + 0) * C + c;
-      const float* pb = ab + ((long long)b * 2 + 1) * C + c;
-      a0 = *reinterpret_cast<const float4*>(pa); a1 = *reinterpret_cast<const float4*>(pa + 4);
-      b0 = *reinterpret_cast<const float4*>(pb); b1 = *reinterpret_cast<const float4*>(pb + 4);
-    }
+    if (first) load8<TSrc>(p1 + (long long)pix * C1, v0, v1);
+    else load8<TSrc2>(p2 + (long long)pix * C2, v0, v1);
     const float4 r0 = affine_act<true>(v0, a0, b0, silu), r1 = affine_act<true>(v1, a1, b1, silu);
-    const long long o = ((long long)b * HW + pix) * C + c;
-    {
-      __nv_bfloat162 h[4] = {__floats2bfloat162_rn(r0.x, r0.y), __floats2bfloat162_rn(r0.z, r0.w),
-                             __floats2bfloat162_rn(r1.x, r1.y), __floats2bfloat162_rn(r1.z, r1.w)};
-      *reinterpret_cast<uint4*>(out_act + o) = *reinterpret_cast<uint4*>(h);
-    }
-    if (out_raw) {
-      store4<TRaw>(out_raw + o, v0);
-      store4<TRaw>(out_raw + o + 4, v1);
+    __nv_bfloat162 h[4] = {__floats2bfloat162_rn(r0.x, r0.y), __floats2bfloat162_rn(r0.z, r0.w),
+                           __floats2bfloat162_rn(r1.x, r1.y), __floats2bfloat162_rn(r1.z, r1.w)};
+    *reinterpret_cast<uint4*>(po + (long long)pix * C) = *reinterpret_cast<uint4*>(h);
+    if (pr) {
+      store4<TRaw>(pr + (long long)pix * C, v0);
+      store4<TRaw>(pr + (long long)pix * C + 4, v1);
     }
   }
 }
 
-template <typename TSrc, typename TAct, typename TRaw, int RS>
+template <typename TSrc, typename TSrc2, typename TAct, typename TRaw, int RS>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const TSrc* __restrict__ s1, int C1,
-                                                       const float* __restrict__ s2, int C2,
+                                                       const TSrc2* __restrict__ s2, int C2,
                                                        const float* __restrict__ ab, int silu, int H, int W,
                                                        TAct* __restrict__ out_act, TRaw* __restrict__ out_raw) {
   const int C = C1 + C2, L = C >> 2;
@@ -259,7 +260,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const TSrc* __restrict__ 
     const int cs = first ? C1 : C2, cc = first ? c : c - C1;
     const long long boff = (long long)b * H * W * cs + cc;
     auto ld = [&](long long pixoff) -> float4 {
-      return first ? load4<TSrc>(s1 + boff + pixoff * cs) : load4<float>(s2 + boff + pixoff * cs);
+      return first ? load4<TSrc>(s1 + boff + pixoff * cs) : load4<TSrc2>(s2 + boff + pixoff * cs);
     };
     float4 a = make_float4(1.f, 1.f, 1.f, 1.f), bb = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ab) {
@@ -505,10 +506,11 @@ extern "C" int pdae_gn_coef_ch(const float* chs1, int C1, const float* chs2, int
   return PDAE_OK;
 }
 
-template <typename TSrc, typename TAct, typename TRaw>
-static int launch_apply(const void* s1v, int C1, const float* s2, int C2, const float* ab, int silu, int resample, int B,
+template <typename TSrc, typename TSrc2, typename TAct, typename TRaw>
+static int launch_apply(const void* s1v, int C1, const void* s2v, int C2, const float* ab, int silu, int resample, int B,
                         int H, int W, void* out_act, void* out_raw, cudaStream_t s) {
   const TSrc* s1 = (const TSrc*)s1v;
+  const TSrc2* s2 = (const TSrc2*)s2v;
   const int L = (C1 + C2) / 4;
   const int Hi = resample == PDAE_RESAMPLE_DOWN2 ? H / 2 : H, Wi = resample == PDAE_RESAMPLE_DOWN2 ? W / 2 : W;
   const long long items = (long long)Hi * Wi * L;
@@ -518,54 +520,71 @@ static int launch_apply(const void* s1v, int C1, const float* s2, int C2, const 
   TAct* oa = (TAct*)out_act;
   TRaw* orw = (TRaw*)out_raw;
   if (resample == PDAE_RESAMPLE_NONE)
-    gn_apply_kernel<TSrc, TAct, TRaw, PDAE_RESAMPLE_NONE><<<grid, 256, 0, s>>>(s1, C1, s2, C2, ab, silu, H, W, oa, orw);
+    gn_apply_kernel<TSrc, TSrc2, TAct, TRaw, PDAE_RESAMPLE_NONE><<<grid, 256, 0, s>>>(s1, C1, s2, C2, ab, silu, H, W, oa, orw);
   else if (resample == PDAE_RESAMPLE_UP2)
-    gn_apply_kernel<TSrc, TAct, TRaw, PDAE_RESAMPLE_UP2><<<grid, 256, 0, s>>>(s1, C1, s2, C2, ab, silu, H, W, oa, orw);
+    gn_apply_kernel<TSrc, TSrc2, TAct, TRaw, PDAE_RESAMPLE_UP2><<<grid, 256, 0, s>>>(s1, C1, s2, C2, ab, silu, H, W, oa, orw);
   else
-    gn_apply_kernel<TSrc, TAct, TRaw, PDAE_RESAMPLE_DOWN2><<<grid, 256, 0, s>>>(s1, C1, s2, C2, ab, silu, H, W, oa, orw);
+    gn_apply_kernel<TSrc, TSrc2, TAct, TRaw, PDAE_RESAMPLE_DOWN2><<<grid, 256, 0, s>>>(s1, C1, s2, C2, ab, silu, H, W, oa, orw);
   PDAE_LAUNCH_CHECK("gn_apply_kernel");
   return PDAE_OK;
 }
 
-extern "C" int pdae_gn_apply(const void* src1, int src1_dtype, int C1, const float* src2, int C2, const float* ab, int silu,
-                             int resample, int B, int H, int W, void* out_act, int act_dtype, void* out_raw,
-                             int raw_dtype, pdae_stream_t stream) {
+extern "C" int pdae_gn_apply(const void* src1, int src1_dtype, int C1, const void* src2, int src2_dtype, int C2,
+                             const float* ab, int silu, int resample, int B, int H, int W, void* out_act, int act_dtype,
+                             void* out_raw, int raw_dtype, pdae_stream_t stream) {
   PDAE_REQUIRE(src1 && out_act, "gn_apply: null pointer");
-  if (!src2) C2 = 0;
+  if (!src2) { C2 = 0; src2_dtype = PDAE_F32; }
   PDAE_REQUIRE(C1 % 4 == 0 && C2 % 4 == 0 && C1 + C2 > 0, "gn_apply: C1=%d C2=%d unsupported", C1, C2);
   PDAE_REQUIRE(resample >= 0 && resample <= 2, "gn_apply: bad resample mode");
   PDAE_REQUIRE(resample != PDAE_RESAMPLE_DOWN2 || (H % 2 == 0 && W % 2 == 0), "gn_apply: odd dims for DOWN2");
+  if (!out_raw) raw_dtype = (act_dtype == PDAE_BF16 && src1_dtype == PDAE_BF16 && src2_dtype == PDAE_BF16) ? PDAE_BF16 : PDAE_F32;
   cudaStream_t s = (cudaStream_t)stream;
   typedef __nv_bfloat16 bf;
-  if (resample == PDAE_RESAMPLE_NONE && act_dtype == PDAE_BF16 && C1 % 8 == 0 && C2 % 8 == 0 &&
-      (src1_dtype == PDAE_F32 || !out_raw)) {
-    const long long HW = (long long)H * W;
-    const long long items = HW * ((C1 + C2) / 8);
-    int gx = cdiv(items, 512);          // two items per thread (unrolled) keeps more loads in flight
+  const int key = src1_dtype | (src2_dtype << 1) | (act_dtype << 2) | (raw_dtype << 3);
+  if (resample == PDAE_RESAMPLE_NONE && act_dtype == PDAE_BF16 && C1 % 8 == 0 && C2 % 8 == 0 && (C1 + C2) / 8 <= 256) {
+    const int HW = H * W;
+    const int L8 = (C1 + C2) / 8;
+    const int ppc = 256 / L8;
+    const int nthr = L8 * ppc;
+    int gx = cdiv(HW, ppc * 4);          // ~4 pixels per thread (unrolled) keep several loads in flight
     if (gx > 148 * 16) gx = 148 * 16;
     if (gx < 1) gx = 1;
     dim3 grid(gx, B);
-    if (src1_dtype == PDAE_BF16)
-      gn_apply8_kernel<bf, float><<<grid, 256, 0, s>>>((const bf*)src1, C1, src2, C2, ab, silu, HW, (bf*)out_act, (float*)nullptr);
-    else if (raw_dtype == PDAE_BF16)
-      gn_apply8_kernel<float, bf><<<grid, 256, 0, s>>>((const float*)src1, C1, src2, C2, ab, silu, HW, (bf*)out_act, (bf*)out_raw);
-    else
-      gn_apply8_kernel<float, float><<<grid, 256, 0, s>>>((const float*)src1, C1, src2, C2, ab, silu, HW, (bf*)out_act, (float*)out_raw);
-    PDAE_LAUNCH_CHECK("gn_apply8_kernel");
-    return PDAE_OK;
+    bool ok = true;
+    switch (key) {
+      case 0 | 0 | 4 | 8: gn_apply8_kernel<float, float, bf><<<grid, nthr, 0, s>>>((const float*)src1, C1, (const float*)src2, C2, ab, silu, HW, (bf*)out_act, (bf*)out_raw); break;
+      case 0 | 0 | 4 | 0: gn_apply8_kernel<float, float, float><<<grid, nthr, 0, s>>>((const float*)src1, C1, (const float*)src2, C2, ab, silu, HW, (bf*)out_act, (float*)out_raw); break;
+      case 1 | 0 | 4 | 0: gn_apply8_kernel<bf, float, float><<<grid, nthr, 0, s>>>((const bf*)src1, C1, (const float*)src2, C2, ab, silu, HW, (bf*)out_act, (float*)out_raw); break;
+      case 1 | 2 | 4 | 8: gn_apply8_kernel<bf, bf, bf><<<grid, nthr, 0, s>>>((const bf*)src1, C1, (const bf*)src2, C2, ab, silu, HW, (bf*)out_act, (bf*)out_raw); break;
+      case 1 | 0 | 4 | 8: gn_apply8_kernel<bf, float, bf><<<grid, nthr, 0, s>>>((const bf*)src1, C1, (const float*)src2, C2, ab, silu, HW, (bf*)out_act, (bf*)out_raw); break;
+      case 0 | 2 | 4 | 0: gn_apply8_kernel<float, bf, float><<<grid, nthr, 0, s>>>((const float*)src1, C1, (const bf*)src2, C2, ab, silu, HW, (bf*)out_act, (float*)out_raw); break;
+      case 0 | 2 | 4 | 8: gn_apply8_kernel<float, bf, bf><<<grid, nthr, 0, s>>>((const float*)src1, C1, (const bf*)src2, C2, ab, silu, HW, (bf*)out_act, (bf*)out_raw); break;
+      case 1 | 2 | 4 | 0: gn_apply8_kernel<bf, bf, float><<<grid, nthr, 0, s>>>((const bf*)src1, C1, (const bf*)src2, C2, ab, silu, HW, (bf*)out_act, (float*)out_raw); break;
+      default: ok = false;
+    }
+    if (ok) {
+      PDAE_LAUNCH_CHECK("gn_apply8_kernel");
+      return PDAE_OK;
+    }
   }
-  if (src1_dtype == PDAE_BF16) {
-    PDAE_REQUIRE(act_dtype == PDAE_BF16 && !out_raw, "gn_apply: a bf16 source supports a bf16 activation output only");
-    return launch_apply<bf, bf, float>(src1, C1, src2, C2, ab, silu, resample, B, H, W, out_act, nullptr, s);
+  switch (key) {
+    case 0 | 0 | 0 | 0: return launch_apply<float, float, float, float>(src1, C1, src2, C2, ab, silu, resample, B, H, W, out_act, out_raw, s);
+    case 0 | 0 | 4 | 0: return launch_apply<float, float, bf, float>(src1, C1, src2, C2, ab, silu, resample, B, H, W, out_act, out_raw, s);
+    case 0 | 0 | 4 | 8: return launch_apply<float, float, bf, bf>(src1, C1, src2, C2, ab, silu, resample, B, H, W, out_act, out_raw, s);
+    case 1 | 0 | 4 | 0: return launch_apply<bf, float, bf, float>(src1, C1, src2, C2, ab, silu, resample, B, H, W, out_act, out_raw, s);
+    case 1 | 2 | 4 | 8: return launch_apply<bf, bf, bf, bf>(src1, C1, src2, C2, ab, silu, resample, B, H, W, out_act, out_raw, s);
+    case 1 | 0 | 4 | 8: return launch_apply<bf, float, bf, bf>(src1, C1, src2, C2, ab, silu, resample, B, H, W, out_act, out_raw, s);
+    case 0 | 2 | 4 | 0: return launch_apply<float, bf, bf, float>(src1, C1, src2, C2, ab, silu, resample, B, H, W, out_act, out_raw, s);
+    case 0 | 2 | 4 | 8: return launch_apply<float, bf, bf, bf>(src1, C1, src2, C2, ab, silu, resample, B, H, W, out_act, out_raw, s);
+    case 1 | 2 | 4 | 0: return launch_apply<bf, bf, bf, float>(src1, C1, src2, C2, ab, silu, resample, B, H, W, out_act, out_raw, s);
+    // a bf16-stream tensor feeding a CUDA-core (fp32) conv
+    case 1 | 0 | 0 | 0: return launch_apply<bf, float, float, float>(src1, C1, src2, C2, ab, silu, resample, B, H, W, out_act, out_raw, s);
+    case 1 | 2 | 0 | 0: return launch_apply<bf, bf, float, float>(src1, C1, src2, C2, ab, silu, resample, B, H, W, out_act, out_raw, s);
+    case 0 | 2 | 0 | 0: return launch_apply<float, bf, float, float>(src1, C1, src2, C2, ab, silu, resample, B, H, W, out_act, out_raw, s);
+    default: break;
   }
-  PDAE_REQUIRE(src1_dtype == PDAE_F32, "gn_apply: bad source dtype");
-  if (act_dtype == PDAE_F32 && raw_dtype == PDAE_F32)
-    return launch_apply<float, float, float>(src1, C1, src2, C2, ab, silu, resample, B, H, W, out_act, out_raw, s);
-  if (act_dtype == PDAE_BF16 && raw_dtype == PDAE_F32)
-    return launch_apply<float, bf, float>(src1, C1, src2, C2, ab, silu, resample, B, H, W, out_act, out_raw, s);
-  if (act_dtype == PDAE_BF16 && raw_dtype == PDAE_BF16)
-    return launch_apply<float, bf, bf>(src1, C1, src2, C2, ab, silu, resample, B, H, W, out_act, out_raw, s);
-  PDAE_REQUIRE(false, "gn_apply: unsupported dtype combination act=%d raw=%d", act_dtype, raw_dtype);
+  PDAE_REQUIRE(false, "gn_apply: unsupported dtype combination src1=%d src2=%d act=%d raw=%d", src1_dtype, src2_dtype, act_dtype,
+               raw_dtype);
 }
 
 extern "C" int pdae_timestep_embedding(const int64_t* t, int B, int dim, const float* freqs, float* out,

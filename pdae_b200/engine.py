@@ -101,6 +101,9 @@ class Plan:
         self.tc = self.precision == "bf16"
         self.v2 = os.environ.get("PDAE_TC_V1", "0") != "1"       # persistent v2 conv kernel (default) vs the simple v1
         self.bn_override = int(os.environ.get("PDAE_TC_BN", "0"))  # tuning aid: force the N tile of the v2 kernel
+        # residual stream (block outputs / skip tensors) kept in bf16 instead of fp32: halves the HBM bytes of the
+        # bandwidth-bound top-level layers.  "bf16" precision + v2 kernel only.
+        self.stream_bf16 = self.tc and self.v2 and os.environ.get("PDAE_STREAM_BF16", "1") == "1"
         self.L = _native.lib()
         self.ops: List[Tuple[str, list]] = []
         self.bufs: List[Buf] = []
@@ -463,6 +466,17 @@ class Plan:
     def fused_stats(self) -> bool:
         return self.tc and self.v2
 
+    @property
+    def stream_dtype(self):
+        return torch.bfloat16 if self.stream_bf16 else torch.float32
+
+    def to_stream(self, src: Buf, C: int, *, B, H, W) -> Buf:
+        """Cast an fp32 NHWC tensor into the residual-stream dtype (no-op for an fp32 stream)."""
+        if not self.stream_bf16 or src.dtype == torch.bfloat16 or C % 8:
+            return src
+        out, _ = self.gn_apply(src, C, None, 0, None, silu=False, resample=RESAMPLE_NONE, B=B, H=H, W=W, act_dtype=torch.bfloat16)
+        return out
+
     def gn_coef(self, src1: Buf, C1: int, src2: Optional[Buf], C2: int, gamma, beta, *, B, HW, emb=None, emb_ld=0,
                 embz=None, embz_ld=0, stats1: Optional[Buf] = None, stats2: Optional[Buf] = None) -> Buf:
         """GroupNorm(32) statistics -> per-(b,c) affine coefficients.  bf16/v2 mode consumes the per-channel sums the
@@ -490,8 +504,8 @@ class Plan:
         Ho, Wo = (2 * H, 2 * W) if resample == RESAMPLE_UP2 else ((H // 2, W // 2) if resample == RESAMPLE_DOWN2 else (H, W))
         act = self.new((B, Ho, Wo, C), act_dtype, "act")
         raw = self.new((B, Ho, Wo, C), raw_dtype, "raw") if raw_dtype is not None else None
-        self.call("gn_apply", src1, _DT[src1.dtype], C1, src2, C2, ab, int(silu), resample, B, H, W, act, _DT[act_dtype], raw,
-                  _DT[raw_dtype] if raw_dtype is not None else PDAE_F32, _STREAM)
+        self.call("gn_apply", src1, _DT[src1.dtype], C1, src2, _DT[src2.dtype] if src2 is not None else PDAE_F32, C2, ab, int(silu),
+                  resample, B, H, W, act, _DT[act_dtype], raw, _DT[raw_dtype] if raw_dtype is not None else PDAE_F32, _STREAM)
         return act, raw
 
 

@@ -253,18 +253,20 @@ class _ResBase(PlannedModule):
         ab1 = P.gn_coef(x.b1, x.C1, x.b2, x.C2, gn1.weight, gn1.bias, B=B, HW=H * W, stats1=x.s1, stats2=x.s2)
         sums1 = P.last_sums
         tc1 = P.use_tc(C, Co, 3, 1, H2, W2)
+        tc2 = P.use_tc(Co, Co, 3, 1, H2, W2)
+        tcs = (not ident) and P.use_tc(C, Co, self.skip_connection.kernel_size[0], 1, H2, W2)
+        # dtype of this block's output (the residual stream): bf16 only when every conv of the block is a tensor-core one
+        out_dt = P.stream_dtype if (tc1 and tc2 and (ident or tcs)) else torch.float32
         # raw (un-normalised) copy of the possibly concatenated / resampled input for the skip path
+        plain = not self.updown and x.b2 is None        # x.b1 itself is the skip-path input
         raw_dtype = None
         if ident:
-            if self.updown or x.b2 is not None:
-                raw_dtype = torch.float32
+            if not (plain and x.b1.dtype == out_dt):
+                raw_dtype = out_dt                       # identity residual must have the output's dtype
         else:
-            ks = self.skip_connection.kernel_size[0]
-            tcs = P.use_tc(C, Co, ks, 1, H2, W2)
-            if tcs:
-                raw_dtype = torch.bfloat16
-            elif self.updown or x.b2 is not None:
-                raw_dtype = torch.float32
+            want = torch.bfloat16 if tcs else torch.float32
+            if not (plain and x.b1.dtype == want):
+                raw_dtype = want
         act1, raw = P.gn_apply(x.b1, x.C1, x.b2, x.C2, ab1, silu=True, resample=rs, B=B, H=H, W=W,
                                act_dtype=torch.bfloat16 if tc1 else torch.float32, raw_dtype=raw_dtype)
         # h only feeds GroupNorm-2: with the v2 kernel it is stored in bf16 and its statistics come from the epilogue
@@ -279,17 +281,16 @@ class _ResBase(PlannedModule):
         ab2 = P.gn_coef(h, Co, None, 0, gn2.weight, gn2.bias, B=B, HW=H2 * W2, emb=eb.at(eoff), emb_ld=eld,
                         embz=zb.at(zoff) if zb is not None else None, embz_ld=zld or 0, stats1=hs)
         sums2 = P.last_sums
-        tc2 = P.use_tc(Co, Co, 3, 1, H2, W2)
         act2, _ = P.gn_apply(h, Co, None, 0, ab2, silu=True, resample=RESAMPLE_NONE, B=B, H=H2, W=W2,
                              act_dtype=torch.bfloat16 if tc2 else torch.float32)
         if ident:
             resid = raw if raw is not None else x.b1
         else:
             sk_in = raw if raw is not None else x.b1
-            resid = P.new((B, H2, W2, Co), torch.float32, "res_skip")
+            resid = P.new((B, H2, W2, Co), out_dt, "res_skip")
             P.conv(sk_in, self.skip_connection.weight, self.skip_connection.bias, resid, B=B, H=H2, W=W2, Cin=C, Cout=Co,
                    k=self.skip_connection.kernel_size[0])
-        out = P.new((B, H2, W2, Co), torch.float32, "res_out")
+        out = P.new((B, H2, W2, Co), out_dt, "res_out")
         os_ = P.conv(act2, conv2.weight, conv2.bias, out, B=B, H=H2, W=W2, Cin=Co, Cout=Co, k=3, residual=resid,
                      want_stats=True)
         if tape is not None:
@@ -331,7 +332,7 @@ class _ResBase(PlannedModule):
         if self.has_z:
             ez.tensor.copy_(emb_z)
         plan.run()
-        return y.b1.tensor.permute(0, 3, 1, 2).contiguous()
+        return y.b1.tensor.float().permute(0, 3, 1, 2).contiguous()
 
 
 class ResBlock(_ResBase, TimestepBlock):
@@ -424,7 +425,7 @@ class AttentionBlock(PlannedModule):
             if tcp:
                 att, _ = P.gn_apply(att, C, None, 0, None, silu=False, resample=RESAMPLE_NONE, B=B, H=H, W=W,
                                     act_dtype=torch.bfloat16)
-        out = P.new((B, H, W, C), torch.float32, "attn_out")
+        out = P.new((B, H, W, C), x.b1.dtype if att.dtype == torch.bfloat16 else torch.float32, "attn_out")
         os_ = P.conv(att, self.proj_out.weight, self.proj_out.bias, out, B=B, H=H, W=W, Cin=C, Cout=C, k=1, residual=x.b1,
                      want_stats=True)
         return Src(out, C, B, H, W, s1=os_)
@@ -449,7 +450,7 @@ class AttentionBlock(PlannedModule):
         plan, (xin, y) = self._get_plan(key, build)
         xin.tensor.copy_(x.reshape(B, C, H, W).permute(0, 2, 3, 1))
         plan.run()
-        return y.b1.tensor.permute(0, 3, 1, 2).reshape(shape).contiguous()
+        return y.b1.tensor.float().permute(0, 3, 1, 2).reshape(shape).contiguous()
 
 
 class TimestepSequential(nn.Sequential, TimestepBlock, TimestepContextBlock):

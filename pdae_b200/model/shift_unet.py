@@ -81,7 +81,8 @@ class ShiftUNet(PlannedModule):
         c0 = stem.weight.shape[0]
         h0 = P.new((B, H, W, c0), torch.float32, "stem")
         P.conv(x_in, stem.weight, stem.bias, h0, B=B, H=H, W=W, Cin=self.input_channel, Cout=c0, k=3, in_nchw=True)
-        h = Src(h0, c0, B, H, W, s1=P.ch_stats(h0, c0, B=B, HW=H * W) if P.fused_stats else None)
+        st0 = P.ch_stats(h0, c0, B=B, HW=H * W) if P.fused_stats else None
+        h = Src(P.to_stream(h0, c0, B=B, H=H, W=W), c0, B, H, W, s1=st0)
         hs = [h]
         for stage in list(self.input_blocks)[1:]:
             h = stage.emit(P, h, bank_t)

@@ -173,7 +173,9 @@ class UNet(PlannedModule):
         P.conv(x_in, stem.weight, stem.bias, h0, B=B, H=H, W=W, Cin=self.input_channel, Cout=stem.weight.shape[0], k=3,
                in_nchw=True)
         # the stem output is a skip tensor read by three GroupNorms: compute its per-channel sums once
-        h = Src(h0, stem.weight.shape[0], B, H, W, s1=P.ch_stats(h0, stem.weight.shape[0], B=B, HW=H * W) if P.fused_stats else None)
+        c0_ = stem.weight.shape[0]
+        st0 = P.ch_stats(h0, c0_, B=B, HW=H * W) if P.fused_stats else None
+        h = Src(P.to_stream(h0, c0_, B=B, H=H, W=W), c0_, B, H, W, s1=st0)
         hs = [h]
         for stage in list(self.input_blocks)[1:]:
             h = stage.emit(P, h, bank)

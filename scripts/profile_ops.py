@@ -53,12 +53,12 @@ print("gn_apply by total time:")
 agg = {}
 for i, (fn, args) in enumerate(plan.ops):
     if fn == "gn_apply":
-        src1, sdt, C1, src2, C2, ab, silu, rs, Bb, H, W, act, adt, raw, rdt = args[:15]
+        src1, sdt, C1, src2, sdt2, C2, ab, silu, rs, Bb, H, W, act, adt, raw, rdt = args[:16]
         C = C1 + C2
         Ho, Wo = (2 * H, 2 * W) if rs == 1 else ((H // 2, W // 2) if rs == 2 else (H, W))
-        rd = Bb * H * W * (C1 * (2 if sdt == 1 else 4) + C2 * 4)
+        rd = Bb * H * W * (C1 * (2 if sdt == 1 else 4) + C2 * (2 if sdt2 == 1 else 4))
         wr = Bb * Ho * Wo * C * ((2 if adt == 1 else 4) + (0 if raw is None else (2 if rdt == 1 else 4)))
-        key = f"{H}x{W} C={C1}+{C2} src={'bf16' if sdt else 'f32'} rs={rs} raw={0 if raw is None else (2 if rdt == 1 else 4)}"
+        key = f"{H}x{W} C={C1}+{C2} src={'bf16' if sdt else 'f32'}/{'bf16' if sdt2 else 'f32'} rs={rs} raw={0 if raw is None else (2 if rdt == 1 else 4)}"
         a = agg.setdefault(key, [0, 0.0, 0])
         a[0] += 1; a[1] += plan.last_op_ms[i]; a[2] += rd + wr
 for key, (n, ms, by) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]:

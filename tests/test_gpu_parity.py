@@ -20,6 +20,7 @@ def check(got, want, precision, what):
         assert_close(got, want, what=what, **FP32)
     else:
         r = rel_l2(got, want)
+        print(f"[bf16] {what}: rel-L2 {r:.3e}")
         assert r <= 2e-2, f"{what}: bf16 rel-L2 {r:.3e} > 2e-2"
         assert_close(got, want, rtol=0.0, atol=5e-2 * float(want.abs().max()), what=what + " (bf16)")
 
