@@ -259,8 +259,14 @@ def main():
         n_l = prof[dom]["launches"]
         ach = prof[dom]["flops"] / (prof[dom]["ms"] * 1e9)
         kname = {"conv_tc2": "pdae::conv_tc2_kernel", "conv_tc": "pdae::conv_tc_kernel"}.get(dom, "pdae::conv_simt_kernel")
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "conv_tc2_traffic.json")
+        if dom == "conv_tc2" and os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("workload") == args.workload and tj.get("batch") == B:   # ncu dram bytes, per launch like `achieved`
+                traffic = tj["traffic_bytes_per_launch"]
         roof = {"bound": "tensor", "kernel": kname,
-                "achieved": round(ach, 2), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4), "traffic": None,
+                "achieved": round(ach, 2), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4), "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write, profiles/conv_tc2_traffic.json)",
                 "peak_source": peak_src, "launches_per_decoder_step": n_l,
                 "flops_per_launch_avg": prof[dom]["flops"] / n_l, "ms_per_launch_avg": prof[dom]["ms"] / n_l,
                 "step_ms_sum_of_kernels": round(tot, 3)}

@@ -172,7 +172,12 @@ __global__ void gn_coef_kernel(const double* __restrict__ sums, const float* __r
 // FAST: approximate exp / division (MUFU) -- used when the result is rounded to bf16 anyway
 template <bool FAST>
 __device__ __forceinline__ float silu_t(float x) {
-  if (FAST) return __fdividef(x, 1.0f + __expf(-x));
+  if (FAST) {  // x*sigmoid(x) = h + h*tanh(h), h = x/2 : ONE MUFU op (tanh.approx) instead of ex2 + rcp
+    const float h = 0.5f * x;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+  }
   return silu_f(x);
 }
 template <bool FAST = false>
