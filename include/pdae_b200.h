@@ -173,6 +173,11 @@ typedef struct pdae_conv_tc2_plan pdae_conv_tc2_plan;
 int pdae_conv_tc2_create(pdae_conv_tc2_plan** plan, const void* in_bf16, const void* w_bf16, const float* bias,
                          const void* residual, void* out, int out_dtype, float* ch_stats, int B, int H, int W, int Cin,
                          int Cout, int ksize, int cout_valid, int bn_override);
+/* Same, with the ResBlock's 1x1 skip conv (model/module.py:268-276,297) folded in as extra K blocks:
+ * out = conv(in, w) + in2[B,H,W,Cin2] * w2[Cout][Cin2]^T + bias   (bias = conv bias + skip bias, combined by the caller). */
+int pdae_conv_tc2_create_skip(pdae_conv_tc2_plan** plan, const void* in_bf16, const void* w_bf16, const float* bias,
+                              const void* in2_bf16, const void* w2_bf16, int Cin2, void* out, int out_dtype, float* ch_stats,
+                              int B, int H, int W, int Cin, int Cout, int ksize, int bn_override);
 /* Batched GEMM on the same kernel (tensor-core attention, model/module.py:452-456,483-487): for each batch item
  * out[M x N] = A[M x K] * Bm[N x K]^T, both operands bf16 K-major; *_ld = elements between rows, *_bs = between items.
  * M % 128 == 0, N % 64 == 0, K % 64 == 0.                                                                             */

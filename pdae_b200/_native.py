@@ -89,6 +89,8 @@ _SIGS = {
     "pdae_conv_tc_destroy": (None, [_P]),
     "pdae_conv_tc2_create": (c_int, [POINTER(c_void_p), _P, _P, _P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_int, c_int]),
+    "pdae_conv_tc2_create_skip": (c_int, [POINTER(c_void_p), _P, _P, _P, _P, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int,
+                                          c_int, c_int, c_int]),
     "pdae_gemm_tc2_create": (c_int, [POINTER(c_void_p), _P, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int, c_int64, c_int64,
                                      c_int, c_int, c_int, c_int]),
     "pdae_conv_tc2_run": (c_int, [_P, _P]),

@@ -35,6 +35,7 @@ struct ConvTc2Args {
   int stages;
   int has_res, out_bf16, cout_valid;
   int w_batched;  // B operand is a per-image matrix (batched GEMM): 3rd TMA coordinate = image index
+  int kblocks2;   // fused 1x1 skip conv: extra K blocks from a second (activation, weight) pair, accumulated into the same tile
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -127,7 +128,8 @@ __device__ __forceinline__ uint32_t swz(int row, int chunk16) { return (uint32_t
 template <int BN>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, ConvTc2Args p) {
+                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
+                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, ConvTc2Args p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[T2_MAX_STAGES], bar_empty[T2_MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2], bar_res[2];
@@ -142,7 +144,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t stg_out = smem0 + (uint32_t)S * STAGE_BYTES;   // 2 x 16 KB output staging
   const uint32_t stg_res = stg_out + 2u * T2_STG_BYTES;         // 2 x 16 KB residual staging (only if has_res)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_k = p.taps * p.kblocks;
+  const int total_k = p.taps * p.kblocks;          // main conv
+  const int total_all = total_k + p.kblocks2;      // + fused 1x1 skip conv
   // contiguous tile range per CTA: consecutive tiles of a CTA mostly belong to the same image, so the per-channel
   // GroupNorm partial sums can be accumulated in shared memory across tiles and flushed once per image
   const int per_cta = (p.tiles_total + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -207,6 +210,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           if (++s == S) { s = 0; ph ^= 1u; }
         }
+        for (int kb2 = 0; kb2 < p.kblocks2; ++kb2) {   // fused 1x1 skip conv: un-normalised input, centre tap
+          mb_wait(s_u32(&bar_empty[s]), ph ^ 1u);
+          const uint32_t full = s_u32(&bar_full[s]);
+          mb_expect_tx(full, T2_A_BYTES + B_BYTES);
+          const uint32_t sa = smem0 + (uint32_t)s * STAGE_BYTES;
+          tma_ld4(sa, &tmA2, full, kb2 * T2_BK, x0, y0, b0);
+          tma_ld3(sa + T2_A_BYTES, &tmB2, full, kb2 * T2_BK, n0, 0);
+          if (++s == S) { s = 0; ph ^= 1u; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -221,7 +233,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mb_wait(s_u32(&bar_acc_empty[ab]), (uint32_t)(((tl >> 1) & 1) ^ 1));  // epilogue drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_d = tmem_base + (uint32_t)(ab * BN);
-        for (int it = 0; it < total_k; ++it) {
+        for (int it = 0; it < total_all; ++it) {
           mb_wait(s_u32(&bar_full[s]), ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem0 + (uint32_t)s * STAGE_BYTES;
@@ -481,14 +493,15 @@ static int pow2_tile(int W, int cap) {
 
 template <int BN>
 static cudaError_t launch_tc2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& r,
-                              const ConvTc2Args& args, int grid, size_t smem, cudaStream_t s) {
+                              const CUtensorMap& a2, const CUtensorMap& b2, const ConvTc2Args& args, int grid, size_t smem,
+                              cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);  // + static (barriers, stats) <= 227 KB
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  conv_tc2_kernel<BN><<<grid, T2_THREADS, smem, s>>>(a, b, o, r, args);
+  conv_tc2_kernel<BN><<<grid, T2_THREADS, smem, s>>>(a, b, o, r, a2, b2, args);
   return cudaPeekAtLastError();
 }
 
@@ -497,7 +510,7 @@ static cudaError_t launch_tc2(const CUtensorMap& a, const CUtensorMap& b, const 
 using namespace pdae;
 
 struct pdae_conv_tc2_plan {
-  CUtensorMap tmA, tmB, tmO, tmR;
+  CUtensorMap tmA, tmB, tmO, tmR, tmA2, tmB2;
   ConvTc2Args args;
   int BN, grid;
   size_t smem;
@@ -514,6 +527,7 @@ struct Tc2Desc {
   int w_batched;              // 0: weights [taps][Cout][Cin] ; 1: per-image matrix [B][Cout rows][Cin], strides below
   long long w_ld, w_bs;
   long long out_ld, out_bs;   // elements between consecutive pixels / images of the output
+  const void* in2 = nullptr; const void* w2 = nullptr; int Cin2 = 0;   // fused 1x1 skip conv (bf16 NHWC input, [Cout][Cin2] weights)
 };
 
 static int tc2_create(pdae_conv_tc2_plan** plan_out, const Tc2Desc& d) {
@@ -555,6 +569,7 @@ static int tc2_create(pdae_conv_tc2_plan** plan_out, const Tc2Desc& d) {
   a.taps = ksize * ksize; a.ksize = ksize; a.kblocks = Cin / T2_BK;
   a.has_res = d.residual != nullptr; a.out_bf16 = d.out_dtype == PDAE_BF16; a.cout_valid = cout_valid;
   a.w_batched = d.w_batched;
+  a.kblocks2 = d.Cin2 / T2_BK;
   int BN;
   if (head) BN = 16;
   else if (d.bn_override == 64 || d.bn_override == 128 || d.bn_override == 256) BN = d.bn_override;
@@ -571,7 +586,7 @@ static int tc2_create(pdae_conv_tc2_plan** plan_out, const Tc2Desc& d) {
   const int staging = head ? 0 : (a.has_res ? 4 : 2) * T2_STG_BYTES;
   int stages = (220 * 1024 - 1024 - staging) / stage_bytes;
   if (stages > T2_MAX_STAGES) stages = T2_MAX_STAGES;
-  if (stages > a.taps * a.kblocks) stages = a.taps * a.kblocks;
+  if (stages > a.taps * a.kblocks + a.kblocks2) stages = a.taps * a.kblocks + a.kblocks2;
   if (stages < 2) stages = 2;
   a.stages = stages;
   pl->smem = (size_t)stages * stage_bytes + staging + 1024;
@@ -604,6 +619,28 @@ static int tc2_create(pdae_conv_tc2_plan** plan_out, const Tc2Desc& d) {
   }
   pl->tmO = pl->tmA;
   pl->tmR = pl->tmA;
+  pl->tmA2 = pl->tmA;
+  pl->tmB2 = pl->tmB;
+  if (d.Cin2 > 0) {
+    if (!d.in2 || !d.w2 || d.Cin2 % T2_BK != 0 || head || d.w_batched || ((uintptr_t)d.in2 & 15) || ((uintptr_t)d.w2 & 15)) {
+      delete pl;
+      PDAE_REQUIRE(false, "conv_tc2_create: bad fused-skip operands (Cin2=%d)", d.Cin2);
+    }
+    cuuint64_t dims[4] = {(cuuint64_t)d.Cin2, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)d.Cin2 * 2, (cuuint64_t)W * d.Cin2 * 2, (cuuint64_t)H * W * d.Cin2 * 2};
+    cuuint32_t box[4] = {(cuuint32_t)T2_BK, (cuuint32_t)a.tw, (cuuint32_t)a.th, (cuuint32_t)a.tn};
+    CUresult r = enc(&pl->tmA2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d.in2), dims, strides, box, estr4,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("A2", (int)r);
+    cuuint64_t wd[3] = {(cuuint64_t)d.Cin2, (cuuint64_t)Cout, 1};
+    cuuint64_t ws[2] = {(cuuint64_t)d.Cin2 * 2, (cuuint64_t)Cout * d.Cin2 * 2};
+    cuuint32_t wb[3] = {(cuuint32_t)T2_BK, (cuuint32_t)BN, 1};
+    cuuint32_t we[3] = {1, 1, 1};
+    r = enc(&pl->tmB2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d.w2), wd, ws, wb, we, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("W2", (int)r);
+  }
   if (!head) {
     const int esz = a.out_bf16 ? 2 : 4;
     cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -640,6 +677,21 @@ extern "C" int pdae_conv_tc2_create(pdae_conv_tc2_plan** plan_out, const void* i
   return tc2_create(plan_out, d);
 }
 
+// conv (ksize 1|3) + fused 1x1 skip conv:  out = conv(in, w) + in2 * w2^T + bias (+ residual); bias must already hold b + b_skip
+extern "C" int pdae_conv_tc2_create_skip(pdae_conv_tc2_plan** plan_out, const void* in_bf16, const void* w_bf16, const float* bias,
+                                         const void* in2_bf16, const void* w2_bf16, int Cin2, void* out, int out_dtype,
+                                         float* ch_stats, int B, int H, int W, int Cin, int Cout, int ksize, int bn_override) {
+  Tc2Desc d;
+  d.in = in_bf16; d.w = w_bf16; d.bias = bias; d.residual = nullptr; d.out = out; d.out_dtype = out_dtype;
+  d.ch_stats = ch_stats; d.B = B; d.H = H; d.W = W; d.Cin = Cin; d.Cout = Cout; d.ksize = ksize; d.cout_valid = 0;
+  d.bn_override = bn_override;
+  d.in_ld = Cin; d.in_bs = (long long)H * W * Cin;
+  d.w_batched = 0; d.w_ld = Cin; d.w_bs = (long long)Cout * Cin;
+  d.out_ld = Cout; d.out_bs = (long long)H * W * Cout;
+  d.in2 = in2_bf16; d.w2 = w2_bf16; d.Cin2 = Cin2;
+  return tc2_create(plan_out, d);
+}
+
 // Batched GEMM on the same kernel: for every batch item i,  out_i[M x N] = A_i[M x K] * Bm_i[N x K]^T  (both K-major bf16).
 // a_ld / b_ld / out_ld: elements between consecutive rows; *_bs: elements between consecutive batch items.
 extern "C" int pdae_gemm_tc2_create(pdae_conv_tc2_plan** plan_out, const void* a_bf16, long long a_ld, long long a_bs,
@@ -659,10 +711,10 @@ extern "C" int pdae_conv_tc2_run(const pdae_conv_tc2_plan* pl, pdae_stream_t str
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e;
   switch (pl->BN) {
-    case 16: e = launch_tc2<16>(pl->tmA, pl->tmB, pl->tmO, pl->tmR, pl->args, pl->grid, pl->smem, s); break;
-    case 64: e = launch_tc2<64>(pl->tmA, pl->tmB, pl->tmO, pl->tmR, pl->args, pl->grid, pl->smem, s); break;
-    case 128: e = launch_tc2<128>(pl->tmA, pl->tmB, pl->tmO, pl->tmR, pl->args, pl->grid, pl->smem, s); break;
-    default: e = launch_tc2<256>(pl->tmA, pl->tmB, pl->tmO, pl->tmR, pl->args, pl->grid, pl->smem, s); break;
+    case 16: e = launch_tc2<16>(pl->tmA, pl->tmB, pl->tmO, pl->tmR, pl->tmA2, pl->tmB2, pl->args, pl->grid, pl->smem, s); break;
+    case 64: e = launch_tc2<64>(pl->tmA, pl->tmB, pl->tmO, pl->tmR, pl->tmA2, pl->tmB2, pl->args, pl->grid, pl->smem, s); break;
+    case 128: e = launch_tc2<128>(pl->tmA, pl->tmB, pl->tmO, pl->tmR, pl->tmA2, pl->tmB2, pl->args, pl->grid, pl->smem, s); break;
+    default: e = launch_tc2<256>(pl->tmA, pl->tmB, pl->tmO, pl->tmR, pl->tmA2, pl->tmB2, pl->args, pl->grid, pl->smem, s); break;
   }
   if (e != cudaSuccess) {
     (void)cudaGetLastError();

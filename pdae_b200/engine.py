@@ -239,6 +239,9 @@ class Plan:
             if fn == "gemm_tc2":
                 compiled.append(self._compile_gemm(args))
                 continue
+            if fn == "conv_tc2_skip":
+                compiled.append(self._compile_tc2_skip(args))
+                continue
             cargs = []
             sidx = -1
             for k, a in enumerate(args):
@@ -276,6 +279,16 @@ class Plan:
                                          self._resolve(resid), self._resolve(out), odt, self._resolve(stats), B, H, W, Cin,
                                          Cout, k, cout_valid, bn)
         _native.check(rc, "pdae_conv_tc2_create")
+        self._tc2_handles.append(h)
+        return (self.L.pdae_conv_tc2_run, [h, None], 1, "conv_tc2")
+
+    def _compile_tc2_skip(self, args):
+        x, w, bias, x2, w2, Cin2, out, odt, stats, B, H, W, Cin, Cout, k, bn = args
+        h = ctypes.c_void_p()
+        rc = self.L.pdae_conv_tc2_create_skip(ctypes.byref(h), self._resolve(x), self._resolve(w), self._resolve(bias),
+                                              self._resolve(x2), self._resolve(w2), Cin2, self._resolve(out), odt,
+                                              self._resolve(stats), B, H, W, Cin, Cout, k, bn)
+        _native.check(rc, "pdae_conv_tc2_create_skip")
         self._tc2_handles.append(h)
         return (self.L.pdae_conv_tc2_run, [h, None], 1, "conv_tc2")
 
@@ -382,7 +395,7 @@ class Plan:
 
     def conv(self, x: Buf, weight: torch.Tensor, bias: Optional[torch.Tensor], out: Buf, *, B, H, W, Cin, Cout, k=3,
              stride=1, pad=None, residual: Optional[Buf] = None, in_nchw=False, out_nchw=False, a_silu=False,
-             wkey=None, want_stats=False, bn_override=0) -> Optional[Buf]:
+             wkey=None, want_stats=False, bn_override=0, skip=None) -> Optional[Buf]:
         """weight: nn-style [Cout, Cin, k, k] / [Cout, Cin, 1] / [Cout, Cin] parameter.
         Returns the per-channel (sum, sum^2) buffer [B][Cout][2] if the tensor-core epilogue produced one."""
         pad = k // 2 if pad is None else pad
@@ -397,6 +410,16 @@ class Plan:
                 self.call("conv_tc", x, wp, bias_b, residual, out, B, H, W, Cin, Cout, k, flops=fl)
                 return None
             stats = self.new_stats(B, Cout) if want_stats else None
+            if skip is not None:
+                # fused 1x1 skip conv (model/module.py:268-276): extra K blocks accumulated into the same TMEM tile
+                sk_in, sw, sb, Cin2 = skip
+                assert residual is None and sk_in.dtype == torch.bfloat16
+                w2 = self.pack((id(sw), "tc_skip"), [sw], lambda: sw.detach().reshape(Cout, Cin2).to(torch.bfloat16))
+                bsum = self.pack((id(bias), id(sb), "bias_sum"), [bias, sb], lambda: (bias.detach() + sb.detach()).float())
+                self.params.append((sb, sb.data_ptr()))
+                self.call("conv_tc2_skip", x, wp, bsum, sk_in, w2, Cin2, out, _DT[out.dtype], stats, B, H, W, Cin, Cout, k,
+                          bn_override or self.bn_override, flops=fl + 2.0 * B * H * W * Cout * Cin2)
+                return stats
             self.call("conv_tc2", x, wp, bias_b, residual, out, _DT[out.dtype], stats, B, H, W, Cin, Cout, k, 0,
                       bn_override or self.bn_override, flops=fl)
             return stats

@@ -283,16 +283,20 @@ class _ResBase(PlannedModule):
         sums2 = P.last_sums
         act2, _ = P.gn_apply(h, Co, None, 0, ab2, silu=True, resample=RESAMPLE_NONE, B=B, H=H2, W=W2,
                              act_dtype=torch.bfloat16 if tc2 else torch.float32)
+        out = P.new((B, H2, W2, Co), out_dt, "res_out")
+        fused_skip = None
         if ident:
             resid = raw if raw is not None else x.b1
         else:
+            sk = self.skip_connection
             sk_in = raw if raw is not None else x.b1
-            resid = P.new((B, H2, W2, Co), out_dt, "res_skip")
-            P.conv(sk_in, self.skip_connection.weight, self.skip_connection.bias, resid, B=B, H=H2, W=W2, Cin=C, Cout=Co,
-                   k=self.skip_connection.kernel_size[0])
-        out = P.new((B, H2, W2, Co), out_dt, "res_out")
+            if P.v2 and tcs and tc2 and sk.kernel_size[0] == 1 and sk_in.dtype == torch.bfloat16:
+                resid, fused_skip = None, (sk_in, sk.weight, sk.bias, C)   # folded into conv2 as extra K blocks
+            else:
+                resid = P.new((B, H2, W2, Co), out_dt, "res_skip")
+                P.conv(sk_in, sk.weight, sk.bias, resid, B=B, H=H2, W=W2, Cin=C, Cout=Co, k=sk.kernel_size[0])
         os_ = P.conv(act2, conv2.weight, conv2.bias, out, B=B, H=H2, W=W2, Cin=Co, Cout=Co, k=3, residual=resid,
-                     want_stats=True)
+                     want_stats=True, skip=fused_skip)
         if tape is not None:
             tape.append(("res", self, dict(x=x, ab1=ab1, sums1=sums1, act1=act1, raw=raw, h=h, sums2=sums2, ab2=ab2, act2=act2,
                                            emb=emb, embz=embz, rs=rs, ident=ident, H2=H2, W2=W2)))

@@ -34,7 +34,11 @@ rows = []
 for i, (fn, args) in enumerate(plan.ops):
     if fn.startswith("conv_tc"):
         ints = [a for a in args if isinstance(a, int)]
-        if fn == "conv_tc2":
+        if fn == "conv_tc2_skip":
+            odt, Bb, H, W, Cin, Cout, k, bn = ints[-8:]
+            cv = 0
+            fn = f"conv_tc2+skip{ints[0]}"
+        elif fn == "conv_tc2":
             odt, Bb, H, W, Cin, Cout, k, cv, bn = ints[-9:]
         else:
             Bb, H, W, Cin, Cout, k = ints[-6:]

@@ -133,6 +133,36 @@ def test_head_conv_tensor_core(shape):
     assert_close(out.tensor, ref, rtol=2e-3, atol=2e-3, what=f"tc head {shape}")
 
 
+@pytest.mark.parametrize("shape", [(2, 16, 16, 128, 64, 192), (3, 8, 8, 256, 256, 512), (1, 64, 64, 64, 64, 128)])
+def test_fused_skip_conv(shape):
+    """conv3x3(act) + conv1x1(x) + biases in ONE tensor-core launch (skip conv folded in as extra K blocks) vs torch."""
+    from pdae_b200.engine import Plan
+    B, H, W, Cin, Cout, Cin2 = shape
+    g = torch.Generator(device="cpu").manual_seed(13)
+    x = torch.randn(B, H, W, Cin, generator=g).to(torch.bfloat16)
+    x2 = torch.randn(B, H, W, Cin2, generator=g).to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).to(torch.bfloat16).float()
+    w2 = (torch.randn(Cout, Cin2, 1, 1, generator=g) / Cin2 ** 0.5).to(torch.bfloat16).float()
+    b, b2 = torch.randn(Cout, generator=g), torch.randn(Cout, generator=g)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w, b, padding=1) + F.conv2d(x2.float().permute(0, 3, 1, 2), w2, b2)
+    ref = ref.permute(0, 2, 3, 1)
+    for odt in (torch.float32, torch.bfloat16):
+        P = Plan(torch.device("cuda"), "bf16")
+        out = P.new((B, H, W, Cout), odt)
+        out.keep = True
+        st = P.conv(P.fixed(x.cuda()), w.cuda(), b.cuda(), out, B=B, H=H, W=W, Cin=Cin, Cout=Cout, k=3, want_stats=True,
+                    skip=(P.fixed(x2.cuda()), w2.cuda(), b2.cuda(), Cin2))
+        P.finalize()
+        P.run()
+        P.run()
+        assert [o[0] for o in P.ops if o[0] != "zero"] == ["conv_tc2_skip"]
+        tol = 2e-3 if odt == torch.float32 else 2e-2
+        assert_close(out.tensor.float(), ref, rtol=tol, atol=tol, what=f"fused skip {shape} {odt}")
+        y = out.tensor.float().reshape(B, H * W, Cout)
+        got = st.buf.tensor[st.off: st.off + B * Cout * 2].reshape(B, Cout, 2)
+        assert_close(got, torch.stack([y.sum(1), (y * y).sum(1)], dim=-1), rtol=2e-3, atol=5e-2, what="fused skip stats")
+
+
 def test_head_conv_smalln():
     from pdae_b200.engine import Plan
     g = torch.Generator(device="cpu").manual_seed(9)
