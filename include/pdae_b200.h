@@ -149,14 +149,16 @@ int pdae_colsum(const float* dy, int64_t M, int N, float* out, pdae_stream_t str
 /* GroupNorm(+AdaGN)+SiLU(+resample) backward in three passes (forward: y = R(f(a*x+b)), see pdae_gn_apply):
  *  sums : S[b][c] = (sum du, sum du*x), du = f'(u) * R^T(dy)           (dy has the RESAMPLED spatial size, C channels)
  *  coef : kk[b][3][C] with dx = k0*du + k1*x + k2; accumulates dgamma/dbeta; writes the (scale|shift) grads of emb/embz
- *  apply: dx[B,H,W,C1] = k0*du + k1*x + k2 (+ R^T(add)), only for the first C1 channels of a concatenated input.     */
+ *  apply: dx1[B,H,W,C1] (and, if dx2 != NULL, dx2[B,H,W,C2] for the skip source) = k0*du + k1*x + k2 (+ R^T(add)).         */
 int pdae_gn_bwd_sums(const float* src1, int C1, const float* src2, int C2, const float* ab, const float* dy, int silu,
                      int resample, int B, int H, int W, float* S, pdae_stream_t stream);
 int pdae_gn_bwd_coef(const float* S, const double* sums, const float* gamma, const float* beta, const float* emb, int emb_ld,
                      const float* embz, int embz_ld, int B, int C, int HW, float eps, float* kk, float* dgamma, float* dbeta,
                      float* demb, int demb_ld, float* dembz, int dembz_ld, pdae_stream_t stream);
-int pdae_gn_bwd_apply(const float* src1, int C1, int C, const float* ab, const float* kk, const float* dy, int silu,
-                      int resample, int B, int H, int W, const float* add, int add_ld, float* dx, pdae_stream_t stream);
+int pdae_gn_bwd_apply(const float* src1, int C1, const float* src2, int C2, const float* ab, const float* kk, const float* dy,
+                      int silu, int resample, int B, int H, int W, const float* add, int add_ld, float* dx1, float* dx2,
+                      pdae_stream_t stream);
+int pdae_embedding_bwd(const float* d_emb, const int64_t* idx, float* dw, int B, int E, pdae_stream_t stream);
 int pdae_softmax_bwd(const float* P, float* dP, int64_t rows, int cols, float alpha, pdae_stream_t stream);
 int pdae_dsilu_mul(const float* g, const float* x, float* out, int64_t n, pdae_stream_t stream);
 int pdae_add_inplace(float* a, const float* b, int64_t n, pdae_stream_t stream);

@@ -77,7 +77,8 @@ _SIGS = {
     "pdae_gn_bwd_sums": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "pdae_gn_bwd_coef": (c_int, [_P, _P, _P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P, c_int, _P,
                                  c_int, _P]),
-    "pdae_gn_bwd_apply": (c_int, [_P, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P]),
+    "pdae_gn_bwd_apply": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, _P]),
+    "pdae_embedding_bwd": (c_int, [_P, _P, _P, c_int, c_int, _P]),
     "pdae_softmax_bwd": (c_int, [_P, _P, c_int64, c_int, c_float, _P]),
     "pdae_dsilu_mul": (c_int, [_P, _P, _P, c_int64, _P]),
     "pdae_add_inplace": (c_int, [_P, _P, c_int64, _P]),

@@ -316,13 +316,17 @@ __global__ void gn_bwd_coef_kernel(const float* __restrict__ S, const double* __
   }
 }
 
-// pass 3: dx[b,pix,c] (c < C1 only) = k0*du + k1*x + k2  (+ add[b,pix,c] if given), du recomputed
+// pass 3: dx = k0*du + k1*x + k2 (+ R^T(add)), du recomputed.  Channels c < C1 go to dx1 [B,H,W,C1]; channels of the second
+// (skip) source go to dx2 [B,H,W,C2] when requested (full-UNet training needs the gradient of the skip tensors too).
 template <int RS>
-__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const float* __restrict__ s1, int C1, int C, const float* __restrict__ ab,
-                                                           const float* __restrict__ kk, const float* __restrict__ dy, int silu,
-                                                           int H, int W, const float* __restrict__ add, int add_ld,
-                                                           float* __restrict__ dx) {
-  const int L = C1 >> 2;
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const float* __restrict__ s1, int C1, const float* __restrict__ s2,
+                                                           int C2, const float* __restrict__ ab, const float* __restrict__ kk,
+                                                           const float* __restrict__ dy, int silu, int H, int W,
+                                                           const float* __restrict__ add, int add_ld, float* __restrict__ dx1,
+                                                           float* __restrict__ dx2) {
+  const int C = C1 + C2;
+  const int Cw = dx2 ? C : C1;     // channels to produce
+  const int L = Cw >> 2;
   const int b = blockIdx.y;
   const long long items = (long long)H * W * L;
   for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.x * blockDim.x) {
@@ -330,7 +334,9 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const float* __restri
     const long long pix = it / L;
     const int y = (int)(pix / W), x = (int)(pix - (long long)y * W);
     const int c = cq * 4;
-    const float4 xv = *reinterpret_cast<const float4*>(s1 + ((long long)b * H * W + pix) * C1 + c);
+    const bool first = c < C1;
+    const float4 xv = first ? *reinterpret_cast<const float4*>(s1 + ((long long)b * H * W + pix) * C1 + c)
+                            : *reinterpret_cast<const float4*>(s2 + ((long long)b * H * W + pix) * C2 + (c - C1));
     float4 g = gather_dy<RS>(dy, b, y, x, H, W, C, c);
     if (silu) {
       const float4 a = *reinterpret_cast<const float4*>(ab + ((long long)b * 2 + 0) * C + c);
@@ -348,8 +354,18 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const float* __restri
       const float4 av = gather_dy<RS>(add, b, y, x, H, W, add_ld, c);
       o.x += av.x; o.y += av.y; o.z += av.z; o.w += av.w;
     }
-    *reinterpret_cast<float4*>(dx + ((long long)b * H * W + pix) * C1 + c) = o;
+    if (first) *reinterpret_cast<float4*>(dx1 + ((long long)b * H * W + pix) * C1 + c) = o;
+    else *reinterpret_cast<float4*>(dx2 + ((long long)b * H * W + pix) * C2 + (c - C1)) = o;
   }
+}
+
+// dW[idx[b]][:] += d_emb[b][:]   (nn.Embedding backward, unet.py:190-192)
+__global__ void embedding_bwd_kernel(const float* __restrict__ d_emb, const int64_t* __restrict__ idx, float* __restrict__ dw,
+                                     int B, int E) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * E) return;
+  const int b = i / E, j = i % E;
+  atomicAdd(dw + idx[b] * E + j, d_emb[i]);
 }
 
 // dS = alpha * P * (dP - rowsum(dP * P)), in place on dP  (softmax backward with the ch^-1/2 scale folded in)
@@ -461,20 +477,28 @@ extern "C" int pdae_gn_bwd_coef(const float* S, const double* sums, const float*
   return PDAE_OK;
 }
 
-extern "C" int pdae_gn_bwd_apply(const float* src1, int C1, int C, const float* ab, const float* kk, const float* dy, int silu,
-                                 int resample, int B, int H, int W, const float* add, int add_ld, float* dx,
-                                 pdae_stream_t stream) {
-  PDAE_REQUIRE(src1 && ab && kk && dy && dx, "gn_bwd_apply: null pointer");
-  PDAE_REQUIRE(C1 % 4 == 0 && C1 <= C, "gn_bwd_apply: bad channels");
-  const long long items = (long long)H * W * (C1 / 4);
+extern "C" int pdae_gn_bwd_apply(const float* src1, int C1, const float* src2, int C2, const float* ab, const float* kk,
+                                 const float* dy, int silu, int resample, int B, int H, int W, const float* add, int add_ld,
+                                 float* dx1, float* dx2, pdae_stream_t stream) {
+  PDAE_REQUIRE(src1 && ab && kk && dy && dx1, "gn_bwd_apply: null pointer");
+  if (!src2) C2 = 0;
+  PDAE_REQUIRE(C1 % 4 == 0 && C2 % 4 == 0 && !(dx2 && !src2), "gn_bwd_apply: bad channels");
+  const long long items = (long long)H * W * ((dx2 ? C1 + C2 : C1) / 4);
   int gx = cdiv(items, 256);
   if (gx > 148 * 16) gx = 148 * 16;
   dim3 grid(gx, B);
   cudaStream_t s = (cudaStream_t)stream;
-  if (resample == PDAE_RESAMPLE_NONE) gn_bwd_apply_kernel<PDAE_RESAMPLE_NONE><<<grid, 256, 0, s>>>(src1, C1, C, ab, kk, dy, silu, H, W, add, add_ld, dx);
-  else if (resample == PDAE_RESAMPLE_UP2) gn_bwd_apply_kernel<PDAE_RESAMPLE_UP2><<<grid, 256, 0, s>>>(src1, C1, C, ab, kk, dy, silu, H, W, add, add_ld, dx);
-  else gn_bwd_apply_kernel<PDAE_RESAMPLE_DOWN2><<<grid, 256, 0, s>>>(src1, C1, C, ab, kk, dy, silu, H, W, add, add_ld, dx);
+  if (resample == PDAE_RESAMPLE_NONE) gn_bwd_apply_kernel<PDAE_RESAMPLE_NONE><<<grid, 256, 0, s>>>(src1, C1, src2, C2, ab, kk, dy, silu, H, W, add, add_ld, dx1, dx2);
+  else if (resample == PDAE_RESAMPLE_UP2) gn_bwd_apply_kernel<PDAE_RESAMPLE_UP2><<<grid, 256, 0, s>>>(src1, C1, src2, C2, ab, kk, dy, silu, H, W, add, add_ld, dx1, dx2);
+  else gn_bwd_apply_kernel<PDAE_RESAMPLE_DOWN2><<<grid, 256, 0, s>>>(src1, C1, src2, C2, ab, kk, dy, silu, H, W, add, add_ld, dx1, dx2);
   PDAE_LAUNCH_CHECK("gn_bwd_apply_kernel");
+  return PDAE_OK;
+}
+
+extern "C" int pdae_embedding_bwd(const float* d_emb, const int64_t* idx, float* dw, int B, int E, pdae_stream_t stream) {
+  PDAE_REQUIRE(d_emb && idx && dw, "embedding_bwd: null pointer");
+  embedding_bwd_kernel<<<cdiv((long long)B * E, 256), 256, 0, (cudaStream_t)stream>>>(d_emb, idx, dw, B, E);
+  PDAE_LAUNCH_CHECK("embedding_bwd_kernel");
   return PDAE_OK;
 }
 

@@ -190,9 +190,13 @@ class UNet(PlannedModule):
 
     def forward(self, x, time, condition=None):
         """x [N,C,H,W] fp32, time int64 [N], condition int64 [N] if class-conditional -> [N,C(|2C),H,W]."""
-        self._check_no_grad(x)
         if self.num_class is not None:
             assert condition is not None
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if x.requires_grad:
+                raise NotImplementedError("pdae_b200: gradients w.r.t. x_t are not provided (the reference never needs them)")
+            from ..train import unet_train_forward   # regular DPM training step (gaussian_diffusion.py:199-211)
+            return unet_train_forward(self, x.contiguous(), time, condition)
         B, C, H, W = x.shape
         assert C == self.input_channel
         plan, (x_in, t_in, c_in, out) = self._get_plan(("unet", B, H, W), lambda P: self._build(P, B, H, W))

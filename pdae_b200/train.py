@@ -88,8 +88,9 @@ class Backward:
 
     # ---- GroupNorm (+AdaGN) + SiLU (+resample) --------------------------------------------------------------------
     def gn(self, src: Src, ab: Buf, sums: Buf, gn_mod: nn.GroupNorm, dy: Buf, *, silu: bool, resample: int, emb=None, embz=None,
-           demb=None, dembz=None, add: Optional[Buf] = None, add_ld: int = 0, trainable=True) -> Buf:
-        """dy: grad of the (resampled) normalised activation, all C channels.  Returns dx for the first C1 channels."""
+           demb=None, dembz=None, add: Optional[Buf] = None, add_ld: int = 0, trainable=True, want_dx2=False):
+        """dy: grad of the (resampled) normalised activation, all C channels.  Returns dx for the first C1 channels
+        (and, with want_dx2, also the gradient of the second / skip source)."""
         P = self.P
         B, H, W, C1, C2 = src.B, src.H, src.W, src.C1, src.C2
         C = C1 + C2
@@ -108,11 +109,13 @@ class Backward:
         P.call("gn_bwd_coef", S, self.fx(sums), P.param(gn_mod.weight), P.param(gn_mod.bias), e, eld, z, zld, B, C, H * W, F32(1e-5),
                kk, dg, db, de, deld, dz, dzld, _STREAM)
         dx = P.new((B, H, W, C1), torch.float32, "gn_dx")
-        P.call("gn_bwd_apply", self.fx(src.b1), C1, C, self.fx(ab), kk, dy, int(silu), resample, B, H, W, add, add_ld, dx, _STREAM)
-        return dx
+        dx2 = P.new((B, H, W, C2), torch.float32, "gn_dx_skip") if (want_dx2 and C2) else None
+        P.call("gn_bwd_apply", self.fx(src.b1), C1, self.fx(src.b2), C2, self.fx(ab), kk, dy, int(silu), resample, B, H, W, add,
+               add_ld, dx, dx2, _STREAM)
+        return (dx, dx2) if want_dx2 else dx
 
     # ---- blocks ----------------------------------------------------------------------------------------------------
-    def resblock(self, blk, sv: dict, d_out: Buf, demb, dembz) -> Buf:
+    def resblock(self, blk, sv: dict, d_out: Buf, demb, dembz, want_dx2=False):
         P = self.P
         x: Src = sv["x"]
         B, H, W, C = x.B, x.H, x.W, x.C
@@ -130,7 +133,8 @@ class Backward:
             sk_in = sv["raw"] if sv["raw"] is not None else x.b1
             add = self.conv(sk_in, d_out, sk.weight, sk.bias, B=B, H=H2, W=W2, Cin=C, Cout=Co, k=sk.kernel_size[0])
             add_ld = C
-        return self.gn(x, sv["ab1"], sv["sums1"], gn1, d_act1, silu=True, resample=rs, add=add, add_ld=add_ld)
+        return self.gn(x, sv["ab1"], sv["sums1"], gn1, d_act1, silu=True, resample=rs, add=add, add_ld=add_ld,
+                       want_dx2=want_dx2)
 
     def attention(self, blk: AttentionBlock, sv: dict, d_out: Buf) -> Buf:
         P = self.P
@@ -322,6 +326,150 @@ def shiftunet_train_forward(net, x, t, z):
         tr = ShiftUNetTrainer(net, B, H, W)
         cache[key] = tr
     return _ShiftUNetFn.apply(tr, x, t, z, *tr.params)
+
+
+# ======================================================================================================================
+# Plain UNet (regular DPM training, gaussian_diffusion.py:199-211) -- every parameter trainable, skip gradients routed
+# ======================================================================================================================
+class UNetTrainer:
+    def __init__(self, net, B: int, H: int, W: int):
+        from .model.unet import EmbBank, emit_head, res_blocks_of
+        from .model.module import timestep_freqs
+        self.net = net
+        dev = net._device()
+        for mod in net.modules():
+            if isinstance(mod, (ResBlock, ResBlockShift)) and mod.training and mod.dropout > 0:
+                raise NotImplementedError("pdae_b200 training path: dropout > 0 is not implemented (use dropout=0)")
+        P = Plan(dev, "fp32")
+        P.keep_all = True
+        E, base, Cimg = net.time_embed_dim, net.base_channel, net.input_channel
+        self.x_in = P.new((B, Cimg, H, W), torch.float32, "x_nchw")
+        self.t_in = P.new((B,), torch.int64, "t")
+        self.c_in = P.new((B,), torch.int64, "cond") if net.num_class is not None else None
+        te = net.time_embed
+        temb = P.new((B, base), torch.float32, "temb")
+        P.call("timestep_embedding", self.t_in, B, base, P.fixed(timestep_freqs(base, dev)), temb, _STREAM)
+        th = P.new((B, E), torch.float32, "temb_h")
+        P.linear(temb, te[0].weight, te[0].bias, th, B=B, Cin=base, Cout=E)
+        emb = P.new((B, E), torch.float32, "emb")
+        P.linear(th, te[2].weight, te[2].bias, emb, B=B, Cin=E, Cout=E, a_silu=True)
+        if self.c_in is not None:
+            P.call("embedding_add", emb, P.param(net.label_emb.weight), self.c_in, B, E, _STREAM)
+        blocks = res_blocks_of(net.input_blocks, net.middle_block, net.output_blocks)
+        bank = EmbBank(P, blocks, "t", emb, B, E, "train_unet_t")
+        stem = net.input_blocks[0][0]
+        c0 = stem.weight.shape[0]
+        h0 = P.new((B, H, W, c0), torch.float32, "stem")
+        P.conv(self.x_in, stem.weight, stem.bias, h0, B=B, H=H, W=W, Cin=Cimg, Cout=c0, k=3, in_nchw=True)
+        h = Src(h0, c0, B, H, W)
+        hs = [h]
+        enc_tapes = []
+        for stage in list(net.input_blocks)[1:]:
+            tp: list = []
+            h = stage.emit(P, h, bank, tape=tp)
+            enc_tapes.append(tp)
+            hs.append(h)
+        mid_tape: list = []
+        h = net.middle_block.emit(P, h, bank, tape=mid_tape)
+        dec_tapes = []
+        n_skip = len(hs)
+        for stage in net.output_blocks:
+            tp = []
+            h = stage.emit(P, h.cat(hs.pop()), bank, tape=tp)
+            dec_tapes.append(tp)
+        self.out = P.new((B, net.output_channel, H, W), torch.float32, "eps_nchw")
+        head_tape: list = []
+        emit_head(P, net.out, h, self.out, tape=head_tape)
+        P.finalize()
+        self.fwd = P
+
+        BP = Plan(dev, "fp32")
+        self.sink = GradSink()
+        bw = Backward(BP, self.sink)
+        self.d_out = BP.new((B, net.output_channel, H, W), torch.float32, "d_eps_nchw")
+        self.d_out.keep = True
+        d_bank = BP.new((B, bank.total), torch.float32, "d_bank_t")
+        slot = lambda mod: (d_bank, bank.offsets[id(mod)], bank.total)
+
+        def run_tape(tp, d, first_has_skip):
+            dskip = None
+            for li, (kind, mod, sv) in reversed(list(enumerate(tp))):
+                if kind == "res":
+                    if li == 0 and first_has_skip:
+                        d, dskip = bw.resblock(mod, sv, d, slot(mod), None, want_dx2=True)
+                    else:
+                        d = bw.resblock(mod, sv, d, slot(mod), None)
+                else:
+                    d = bw.attention(mod, sv, d)
+            return d, dskip
+
+        d = bw.head(net.out, head_tape[0][2], self.d_out)
+        dskips = [None] * n_skip
+        for j in reversed(range(len(dec_tapes))):
+            d, dsk = run_tape(dec_tapes[j], d, True)
+            dskips[n_skip - 1 - j] = dsk       # decoder stage j consumed hs[n_skip-1-j]
+        d, _ = run_tape(mid_tape, d, False)
+        for i in reversed(range(len(enc_tapes))):          # encoder stage i produced hs[i+1]
+            sk = dskips[i + 1]
+            BP.call("add_inplace", d, sk, ctypes.c_int64(sk.nbytes // 4), _STREAM)
+            d, _ = run_tape(enc_tapes[i], d, False)
+        BP.call("add_inplace", d, dskips[0], ctypes.c_int64(dskips[0].nbytes // 4), _STREAM)
+        bw.conv(self.x_in, d, stem.weight, stem.bias, B=B, H=H, W=W, Cin=Cimg, Cout=c0, k=3, need_dx=False, in_nchw=True)
+        # embedding path: d emb -> (label_emb) -> time_embed MLP
+        lins = [b.emb_layers[1] for b in blocks]
+        d_emb = bw.linear_bank(emb, d_bank, lins, [bank.offsets[id(b)] for b in blocks], bank.total, B=B, E=E, need_dx=True)
+        if self.c_in is not None:
+            dwl = BP.new_zeroed(net.label_emb.weight.numel())
+            BP.call("embedding_bwd", d_emb, bw.fx(self.c_in), dwl, B, E, _STREAM)
+            self.sink.add(net.label_emb.weight, dwl, net.label_emb.weight.numel(), lambda t: t)
+        # emb = Linear2(SiLU(th)) ; th = Linear0(temb)
+        d_sth = bw.conv(th, d_emb, te[2].weight, te[2].bias, B=B, H=1, W=1, Cin=E, Cout=E, k=1, a_silu=True,
+                        w_unpack=lambda t: t.view(E, E).t())
+        d_th = BP.new((B, E), torch.float32, "d_th")
+        BP.call("dsilu_mul", d_sth, bw.fx(th), d_th, ctypes.c_int64(B * E), _STREAM)
+        bw.conv(temb, d_th, te[0].weight, te[0].bias, B=B, H=1, W=1, Cin=base, Cout=E, k=1, need_dx=False,
+                w_unpack=lambda t: t.view(base, E).t())
+        BP.finalize()
+        self.bwd = BP
+        self.params = [p for p in net.parameters()]
+
+    def forward(self, x, t, cond):
+        self.x_in.tensor.copy_(x)
+        self.t_in.tensor.copy_(t)
+        if self.c_in is not None:
+            self.c_in.tensor.copy_(cond)
+        self.fwd.run()
+        return self.out.tensor.clone()
+
+    def backward(self, d_out):
+        self.d_out.tensor.copy_(d_out)
+        self.bwd.run()
+        grads = self.sink.collect()
+        return [grads.get(id(p)) for p in self.params]
+
+
+class _UNetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, trainer: UNetTrainer, x, t, cond, *params):
+        ctx.trainer = trainer
+        with torch.no_grad():
+            return trainer.forward(x, t, cond)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        with torch.no_grad():
+            pg = ctx.trainer.backward(d_out.contiguous())
+        return (None, None, None, None, *pg)
+
+
+def unet_train_forward(net, x, t, cond):
+    B, C, H, W = x.shape
+    cache = net.__dict__.setdefault("_train_cache", {})
+    tr = cache.get((B, H, W))
+    if tr is None or tr.fwd.stale() or tr.bwd.stale():
+        tr = UNetTrainer(net, B, H, W)
+        cache[(B, H, W)] = tr
+    return _UNetFn.apply(tr, x, t, cond, *tr.params)
 
 
 # ======================================================================================================================

@@ -100,3 +100,49 @@ def test_second_step_after_optimizer_update_uses_new_weights():
         opt.step()
         losses.append(float(loss))
     assert losses[2] < losses[0], losses   # same batch, three Adam steps: the loss must go down
+
+
+@pytest.mark.parametrize("name", ["unet_tiny", "unet_class"])
+def test_regular_dpm_training_step(name):
+    """regular_train_one_batch (gaussian_diffusion.py:199-211): full-UNet backward incl. skip-connection gradients,
+    down/up-sampling blocks, attention, the time-embedding MLP and the class embedding -- vs oracle autograd."""
+    from pdae_b200.diffusion.gaussian_diffusion import GaussianDiffusion
+    from pdae_b200.utils.synth import synth_images
+    cfg, g = load_golden("model_" + name)
+    net, _ = cases.model_case(cfg)
+    c = cfg["cfg"]
+    size = cfg["size"]
+    x0 = synth_images(2, c["input_channel"], size, 32)
+    t = torch.tensor([7, 805])
+    noise = torch.randn(x0.shape, generator=torch.Generator().manual_seed(3))
+    cond = g["cond"] if "cond" in g else None
+    sd = {k: v.requires_grad_(True) for k, v in cases.sd_of(net).items()}
+    D = O.DiffusionOracle(cases.DIFF)
+    ref_loss = D.regular_loss(lambda x, tt, cc: O.unet_forward(sd, c, x, tt, cc), x0, t, noise, cond)
+    ref_loss.backward()
+    net = net.cuda().train()
+    net.precision = "fp32"
+    gd = GaussianDiffusion(cases.DIFF, torch.device("cuda"))
+    x_t = gd.q_sample(x0.cuda(), t.cuda(), noise.cuda())
+    loss = gd.p_loss(noise.cuda(), net(x_t, t.cuda(), cond.cuda() if cond is not None else None))
+    assert_close(loss, ref_loss, rtol=1e-4, atol=1e-7, what="regular loss")
+    if name == "unet_tiny":
+        _, gt = load_golden("train_regular")   # the reference's own loss for this net uses other (t, noise): just a sanity range
+        assert float(gt["loss"]) > 0
+    loss.backward()
+    gmax = max(float(v.grad.abs().max()) for v in sd.values() if v.grad is not None)
+    floor = 2e-4 * gmax
+    bad, worst = [], (0.0, "")
+    for k, p in net.named_parameters():
+        assert (p.grad is None) == (sd[k].grad is None), k
+        if p.grad is None:
+            continue
+        r = rel_l2(p.grad, sd[k].grad)
+        err = float((p.grad.cpu() - sd[k].grad).abs().max())
+        ref_max = float(sd[k].grad.abs().max())
+        if r >= 2e-3 and err > 2e-3 * ref_max + floor:
+            bad.append((k, tuple(p.shape), round(r, 4), f"err={err:.2e} ref_max={ref_max:.2e}"))
+        elif ref_max > 50 * floor:
+            worst = max(worst, (r, k))
+    print(name, "worst grad rel-L2:", worst)
+    assert not bad, "gradients off: " + "; ".join(map(str, bad[:30]))
