@@ -162,6 +162,8 @@ int pdae_embedding_bwd(const float* d_emb, const int64_t* idx, float* dw, int B,
 int pdae_softmax_bwd(const float* P, float* dP, int64_t rows, int cols, float alpha, pdae_stream_t stream);
 int pdae_dsilu_mul(const float* g, const float* x, float* out, int64_t n, pdae_stream_t stream);
 int pdae_add_inplace(float* a, const float* b, int64_t n, pdae_stream_t stream);
+/* inverted dropout (nn.Dropout in out_layers, module.py:259): a *= mask * scale with a caller-drawn 0/1 mask.            */
+int pdae_mul_mask(float* a, const float* mask, float scale, int64_t n, pdae_stream_t stream);
 int pdae_nchw_to_nhwc(const float* src, float* dst, int B, int C, int HW, pdae_stream_t stream);
 int pdae_gemm_batched_simt(const float* A, int64_t lda, int64_t a_bs, int64_t a_hs, int transA, const float* Bm, int64_t ldb,
                            int64_t b_bs, int64_t b_hs, int transB, float* C, int64_t ldc, int64_t c_bs, int64_t c_hs, int M,

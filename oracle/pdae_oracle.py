@@ -59,6 +59,9 @@ def _lin(sd: SD, p: str, x: torch.Tensor) -> torch.Tensor:
     return F.linear(x, sd[p + ".weight"], sd.get(p + ".bias"))
 
 
+DROPOUT_MASKS: Optional[Dict[str, torch.Tensor]] = None   # test hook: {block prefix: 0/1 mask, NCHW} + "p"
+
+
 def resblock(sd: SD, p: str, x: torch.Tensor, emb: torch.Tensor, emb_z: Optional[torch.Tensor] = None,
              up: bool = False, down: bool = False) -> torch.Tensor:
     """ResBlock.forward (model/module.py:278-297) / ResBlockShift.forward (:361-384).
@@ -82,7 +85,10 @@ def resblock(sd: SD, p: str, x: torch.Tensor, emb: torch.Tensor, emb_z: Optional
         ez = _lin(sd, p + ".emb_z_layers.1", F.silu(emb_z))[..., None, None]
         z_scale, z_shift = torch.chunk(ez, 2, dim=1)
         h = (1.0 + z_scale) * h + z_shift
-    h = _conv(sd, p + ".out_layers.3", F.silu(h))
+    h = F.silu(h)
+    if DROPOUT_MASKS is not None and p in DROPOUT_MASKS:   # nn.Dropout(p) in train mode with a given mask (module.py:259)
+        h = h * DROPOUT_MASKS[p] / (1.0 - DROPOUT_MASKS["p"])
+    h = _conv(sd, p + ".out_layers.3", h)
     if (p + ".skip_connection.weight") in sd:
         w = sd[p + ".skip_connection.weight"]
         x = F.conv2d(x, w, sd[p + ".skip_connection.bias"], padding=w.shape[-1] // 2)

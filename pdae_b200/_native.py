@@ -82,6 +82,7 @@ _SIGS = {
     "pdae_softmax_bwd": (c_int, [_P, _P, c_int64, c_int, c_float, _P]),
     "pdae_dsilu_mul": (c_int, [_P, _P, _P, c_int64, _P]),
     "pdae_add_inplace": (c_int, [_P, _P, c_int64, _P]),
+    "pdae_mul_mask": (c_int, [_P, _P, c_float, c_int64, _P]),
     "pdae_nchw_to_nhwc": (c_int, [_P, _P, c_int, c_int, c_int, _P]),
     "pdae_gemm_batched_simt": (c_int, [_P, c_int64, c_int64, c_int64, c_int, _P, c_int64, c_int64, c_int64, c_int, _P, c_int64,
                                        c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_float, _P]),

@@ -387,6 +387,11 @@ __global__ void dsilu_mul_kernel(const float* __restrict__ g, const float* __res
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = g[i] * dsilu(x[i]);
 }
+// a[i] *= mask[i] * scale   (inverted dropout with a caller-drawn 0/1 mask; used in both directions)
+__global__ void mul_mask_kernel(float* __restrict__ a, const float* __restrict__ mask, float scale, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] *= mask[i] * scale;
+}
 __global__ void add_inplace_kernel(float* __restrict__ a, const float* __restrict__ b, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[i] += b[i];
@@ -513,6 +518,13 @@ extern "C" int pdae_dsilu_mul(const float* g, const float* x, float* out, int64_
   PDAE_REQUIRE(g && x && out, "dsilu_mul: null pointer");
   dsilu_mul_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(g, x, out, n);
   PDAE_LAUNCH_CHECK("dsilu_mul_kernel");
+  return PDAE_OK;
+}
+
+extern "C" int pdae_mul_mask(float* a, const float* mask, float scale, int64_t n, pdae_stream_t stream) {
+  PDAE_REQUIRE(a && mask, "mul_mask: null pointer");
+  mul_mask_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(a, mask, scale, n);
+  PDAE_LAUNCH_CHECK("mul_mask_kernel");
   return PDAE_OK;
 }
 

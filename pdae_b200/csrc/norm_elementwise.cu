@@ -2,6 +2,7 @@
 // per-step diffusion arithmetic and the latent-MLP row op.  All HBM-bound: vectorised, coalesced along
 // the NHWC channel axis, one pass over the data each.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -551,7 +552,13 @@ extern "C" int pdae_gn_apply(const void* src1, int src1_dtype, int C1, const voi
     const int L8 = (C1 + C2) / 8;
     const int ppc = 256 / L8;
     const int nthr = L8 * ppc;
-    int gx = cdiv(HW, ppc * 4);          // ~4 pixels per thread (unrolled) keep several loads in flight
+    static int ppt = 0;                   // pixels per thread (tuning aid: PDAE_APPLY_PPT)
+    if (ppt == 0) {
+      const char* e = getenv("PDAE_APPLY_PPT");
+      ppt = e ? atoi(e) : 8;
+      if (ppt < 1) ppt = 4;
+    }
+    int gx = cdiv(HW, ppc * ppt);        // several pixels per thread (unrolled x4) keep loads in flight
     if (gx > 148 * 16) gx = 148 * 16;
     if (gx < 1) gx = 1;
     dim3 grid(gx, B);

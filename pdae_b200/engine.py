@@ -115,6 +115,7 @@ class Plan:
         self._tc2_handles: List[ctypes.c_void_p] = []
         self.n_launch = 0
         self.keep_all = False
+        self.dropout_masks: list = []   # (block, mask buffer, p): filled by the trainer before every training forward
         self.last_sums = None
         self._stats_arena = Buf((1,), torch.float32, None, "stats_arena")  # sized at finalize
         self._stats_arena.keep = True

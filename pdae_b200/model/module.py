@@ -240,8 +240,10 @@ class _ResBase(PlannedModule):
              tape: Optional[list] = None) -> Src:
         """emb / embz = (buffer, element offset of this block's [scale|shift] row slice, leading dim).
         tape (training plans): receives the buffers the backward pass needs."""
-        if self.training and self.dropout > 0:
-            raise NotImplementedError("pdae_b200: dropout>0 in train mode needs the training kernels (not built yet)")
+        drop = self.training and self.dropout > 0
+        if drop and tape is None:
+            raise NotImplementedError("pdae_b200: dropout is only active on the training path (grad enabled); "
+                                      "call .eval() / set_eval_mode() for sampling")
         assert x.C == self.channels, f"expected {self.channels} channels, got {x.C}"
         B, H, W, C, Co = x.B, x.H, x.W, x.C, self.out_channels
         rs = RESAMPLE_UP2 if self.up else (RESAMPLE_DOWN2 if self.down else RESAMPLE_NONE)
@@ -283,6 +285,12 @@ class _ResBase(PlannedModule):
         sums2 = P.last_sums
         act2, _ = P.gn_apply(h, Co, None, 0, ab2, silu=True, resample=RESAMPLE_NONE, B=B, H=H2, W=W2,
                              act_dtype=torch.bfloat16 if tc2 else torch.float32)
+        mask = None
+        if drop:   # nn.Dropout(p) between SiLU and conv2 (module.py:259): 0/1 mask drawn by the trainer every step
+            mask = P.new((B, H2, W2, Co), torch.float32, "drop_mask")
+            mask.keep = True
+            P.dropout_masks.append((self, mask, float(self.dropout)))
+            P.call("mul_mask", act2, mask, ctypes.c_float(1.0 / (1.0 - self.dropout)), ctypes.c_int64(B * H2 * W2 * Co), _STREAM)
         out = P.new((B, H2, W2, Co), out_dt, "res_out")
         fused_skip = None
         if ident:
@@ -299,7 +307,7 @@ class _ResBase(PlannedModule):
                      want_stats=True, skip=fused_skip)
         if tape is not None:
             tape.append(("res", self, dict(x=x, ab1=ab1, sums1=sums1, act1=act1, raw=raw, h=h, sums2=sums2, ab2=ab2, act2=act2,
-                                           emb=emb, embz=embz, rs=rs, ident=ident, H2=H2, W2=W2)))
+                                           emb=emb, embz=embz, rs=rs, ident=ident, H2=H2, W2=W2, mask=mask)))
         return Src(out, Co, B, H2, W2, s1=os_)
 
     def emit_emb(self, P: Plan, emb: Buf, B: int, which: str = "t") -> Tuple[Buf, int, int]:

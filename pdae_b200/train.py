@@ -6,7 +6,7 @@ Scope (the PDAE training step, diffusion/gaussian_diffusion.py:234-255): the sem
 trainable half of the ShiftUNet (``label_emb``, ``shift_middle_block``, ``shift_output_blocks``, ``shift_out``); the frozen
 half builds no graph in the reference either (its parameters and x_t do not require grad).  Arithmetic is fp32 on CUDA
 cores (``pdae_conv2d_dgrad_simt`` / ``_wgrad_simt``, ``pdae_gn_bwd_*``, ``pdae_gemm_batched_simt``, ``pdae_softmax_bwd``);
-the tensor-core backward is future work.  Dropout must be 0 (the mask is not implemented).
+the tensor-core backward is future work.  Dropout is inverted dropout with masks drawn by torch's CUDA generator.
 """
 from __future__ import annotations
 
@@ -40,6 +40,13 @@ class GradSink:
             g = unpack(flat).reshape(param.shape).contiguous()
             out[id(param)] = out[id(param)] + g if id(param) in out else g.clone()
         return out
+
+
+def draw_dropout_masks(plan: Plan) -> None:
+    """One Bernoulli(1-p) mask per active Dropout, drawn with torch's CUDA generator (the reference's Philox stream is not
+    reproduced; parity tests feed the same masks to the oracle)."""
+    for _, mask, p in plan.dropout_masks:
+        mask.tensor.bernoulli_(1.0 - p)
 
 
 class Backward:
@@ -122,6 +129,8 @@ class Backward:
         Co, H2, W2, rs = blk.out_channels, sv["H2"], sv["W2"], sv["rs"]
         conv1, conv2, gn1, gn2 = blk.in_layers[2], blk.out_layers[3], blk.in_layers[0], blk.out_layers[0]
         d_act2 = self.conv(sv["act2"], d_out, conv2.weight, conv2.bias, B=B, H=H2, W=W2, Cin=Co, Cout=Co, k=3)
+        if sv.get("mask") is not None:   # dropout backward: the same mask and 1/(1-p) scale
+            P.call("mul_mask", d_act2, self.fx(sv["mask"]), F32(1.0 / (1.0 - blk.dropout)), ctypes.c_int64(B * H2 * W2 * Co), _STREAM)
         hsrc = Src(sv["h"], Co, B, H2, W2)
         d_h = self.gn(hsrc, sv["ab2"], sv["sums2"], gn2, d_act2, silu=True, resample=RESAMPLE_NONE, emb=sv["emb"], embz=sv["embz"],
                       demb=demb, dembz=dembz)
@@ -212,10 +221,6 @@ class ShiftUNetTrainer:
         from .model.unet import EmbBank, emit_head, emit_time_embed, res_blocks_of
         self.net = net
         dev = net._device()
-        for m in net._shift_parts():
-            for mod in m.modules():
-                if isinstance(mod, (ResBlock, ResBlockShift)) and mod.training and mod.dropout > 0:
-                    raise NotImplementedError("pdae_b200 training path: dropout > 0 is not implemented (use dropout=0)")
         P = Plan(dev, "fp32")
         P.keep_all = True
         E, base = net.time_embed_dim, net.base_channel
@@ -286,6 +291,7 @@ class ShiftUNetTrainer:
         self.params = [p for m in net._shift_parts() for p in m.parameters()]
 
     def forward(self, x, t, z):
+        draw_dropout_masks(self.fwd)
         self.x_in.tensor.copy_(x)
         self.t_in.tensor.copy_(t)
         self.z_in.tensor.copy_(z)
@@ -319,7 +325,7 @@ class _ShiftUNetFn(torch.autograd.Function):
 
 def shiftunet_train_forward(net, x, t, z):
     B, C, H, W = x.shape
-    key = ("train", B, H, W)
+    key = ("train", B, H, W, tuple(m.training for m in net._shift_parts()))
     cache = net.__dict__.setdefault("_train_cache", {})
     tr = cache.get(key)
     if tr is None or tr.fwd.stale() or tr.bwd.stale():
@@ -337,9 +343,6 @@ class UNetTrainer:
         from .model.module import timestep_freqs
         self.net = net
         dev = net._device()
-        for mod in net.modules():
-            if isinstance(mod, (ResBlock, ResBlockShift)) and mod.training and mod.dropout > 0:
-                raise NotImplementedError("pdae_b200 training path: dropout > 0 is not implemented (use dropout=0)")
         P = Plan(dev, "fp32")
         P.keep_all = True
         E, base, Cimg = net.time_embed_dim, net.base_channel, net.input_channel
@@ -434,6 +437,7 @@ class UNetTrainer:
         self.params = [p for p in net.parameters()]
 
     def forward(self, x, t, cond):
+        draw_dropout_masks(self.fwd)
         self.x_in.tensor.copy_(x)
         self.t_in.tensor.copy_(t)
         if self.c_in is not None:
@@ -465,10 +469,11 @@ class _UNetFn(torch.autograd.Function):
 def unet_train_forward(net, x, t, cond):
     B, C, H, W = x.shape
     cache = net.__dict__.setdefault("_train_cache", {})
-    tr = cache.get((B, H, W))
+    key = (B, H, W, net.training)
+    tr = cache.get(key)
     if tr is None or tr.fwd.stale() or tr.bwd.stale():
         tr = UNetTrainer(net, B, H, W)
-        cache[(B, H, W)] = tr
+        cache[key] = tr
     return _UNetFn.apply(tr, x, t, cond, *tr.params)
 
 

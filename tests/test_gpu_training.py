@@ -146,3 +146,47 @@ def test_regular_dpm_training_step(name):
             worst = max(worst, (r, k))
     print(name, "worst grad rel-L2:", worst)
     assert not bad, "gradients off: " + "; ".join(map(str, bad[:30]))
+
+
+def test_training_with_dropout_matches_oracle_given_the_same_masks():
+    """nn.Dropout(p=0.1) inside the trainable ResBlockShift blocks (module.py:259): masks are drawn on the GPU, then the SAME
+    masks are injected into the CPU oracle; loss and all gradients must agree."""
+    from pdae_b200.diffusion.gaussian_diffusion import GaussianDiffusion
+    from pdae_b200.model.shift_unet import ShiftUNet
+    from pdae_b200.utils.synth import fill_module_, synth_images
+    cfg, g = load_golden("train_representation_learning")
+    c = dict(cfg["cfg"], dropout=0.1)
+    dec = fill_module_(ShiftUNet(**c), seed=6)
+    enc, _ = cases.model_case({"kind": "encoder", "size": 64})
+    dsd = {k: v.requires_grad_(k.startswith(("label_emb", "shift_"))) for k, v in cases.sd_of(dec).items()}
+    esd = {k: v.requires_grad_(True) for k, v in cases.sd_of(enc).items()}
+    x0 = synth_images(2, 3, 64, 31)
+    dec, enc = dec.cuda().train(), enc.cuda().train()
+    dec.freeze()
+    dec.set_train_mode()
+    dec.precision = enc.precision = "fp32"
+    gd = GaussianDiffusion(cases.DIFF, torch.device("cuda"))
+    torch.manual_seed(5)
+    loss = _loss(gd, enc, dec, x0.cuda(), g["t"].cuda(), g["noise"].cuda())
+    loss.backward()
+    trainer = list(dec._train_cache.values())[0]
+    names = {id(m): n for n, m in dec.named_modules()}
+    masks = {names[id(blk)]: mk.tensor.permute(0, 3, 1, 2).contiguous().cpu() for blk, mk, p in trainer.fwd.dropout_masks}
+    assert len(masks) >= 5 and all(0.8 < float(m.mean()) < 0.98 for m in masks.values())
+    assert all(n.startswith("shift_") for n in masks)       # the frozen half stays in eval mode: no dropout there
+    O.DROPOUT_MASKS = dict(masks, p=0.1)
+    try:
+        D = O.DiffusionOracle(cases.DIFF)
+        ref = D.representation_learning_loss(lambda x: O.encoder_forward(esd, "celeba64", x),
+                                             lambda x, t, z: O.shiftunet_forward(dsd, c, x, t, z), x0, g["t"], g["noise"])
+        ref.backward()
+    finally:
+        O.DROPOUT_MASKS = None
+    assert_close(loss, ref, rtol=1e-4, atol=1e-7, what="loss with dropout")
+    gmax = max(float(v.grad.abs().max()) for v in list(dsd.values()) + list(esd.values()) if v.grad is not None)
+    for mod, sd in ((dec, dsd), (enc, esd)):
+        for k, p in mod.named_parameters():
+            if sd[k].grad is None:
+                continue
+            err = float((p.grad.cpu() - sd[k].grad).abs().max())
+            assert rel_l2(p.grad, sd[k].grad) < 2e-3 or err < 2e-3 * float(sd[k].grad.abs().max()) + 2e-4 * gmax, k
