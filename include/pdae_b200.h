@@ -194,6 +194,39 @@ int pdae_softmax_bf16(const float* S, void* P_bf16, int64_t rows, int cols, floa
 int pdae_transpose_v(const void* qkv_bf16, void* vT_bf16, int B, int T, int C, int heads, int legacy, pdae_stream_t stream);
 void pdae_conv_tc2_destroy(pdae_conv_tc2_plan* plan);
 
+/* ---- callers either side of the hot path -------------------------------------------------------------
+ * Fused multi-tensor Adam + EMA: replaces torch.optim.Adam.step() as configured at
+ * trainer/train_representation_learning.py:54-69 plus the per-parameter python EMA loop of :192-212
+ * (`ema.mul_(decay).add_(p, alpha=1-decay)`, run after the optimizer step).  `table` is a DEVICE array of n tensors;
+ * `block_map` a DEVICE array of n_blocks (tensor index, chunk index) int32 pairs covering every tensor in `chunk`-element
+ * pieces (chunk % 4 == 0).  g is multiplied by grad_scale first (1/world_size after a sum all-reduce, or 1/loss_scale).
+ * `step` is the 1-based Adam step count (bias corrections are evaluated in fp64 on the host like torch does).
+ * ema_decay < 0 or ema == NULL skips the EMA update.                                                                    */
+typedef struct pdae_adam_tensor {
+  float* p;        /* parameter, updated in place        */
+  const float* g;  /* gradient                           */
+  float* m;        /* exp_avg                            */
+  float* v;        /* exp_avg_sq                         */
+  float* ema;      /* EMA copy of p, or NULL             */
+  int64_t n;       /* elements                           */
+} pdae_adam_tensor;
+int pdae_adam_ema_step(const pdae_adam_tensor* table, const int32_t* block_map, int n_blocks, int chunk, float lr,
+                       float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                       float ema_decay, pdae_stream_t stream);
+/* Wire formats.  fp32 NCHW in [-1,1] -> uint8 NHWC with the reference's exact op sequence
+ * `x.mul(0.5).add(0.5).mul(255).add(0.5).clamp(0,255).permute(0,2,3,1).to(uint8)`
+ * (trainer/train_representation_learning.py:173-174, sampler/autoencoding_example.py:53 ...): bit-exact.
+ * uint8 NHWC -> fp32 NCHW `(x/255 - 0.5)/0.5` = torchvision ToTensor + Normalize(0.5,0.5) (dataset/ffhq.py:27-31).      */
+int pdae_images_to_u8_nhwc(const float* x_nchw, uint8_t* out_nhwc, int B, int C, int H, int W, pdae_stream_t stream);
+int pdae_u8_nhwc_to_images(const uint8_t* in_nhwc, float* out_nchw, int B, int C, int H, int W, pdae_stream_t stream);
+/* Per-image metrics over fp32 NCHW batches: calculate_mse (metric/utils.py:62-63) and calculate_ssim
+ * (metric/utils.py:35-60; `window_11x11` = the fp32 11x11 Gaussian window of :25-33, device memory).
+ * workspace: B doubles (device); out: B floats.                                                                        */
+int pdae_mse_per_image(const float* a, const float* b, int B, int64_t per_image, double* workspace, float* out,
+                       pdae_stream_t stream);
+int pdae_ssim_per_image(const float* img1, const float* img2, const float* window_11x11, int B, int C, int H, int W,
+                        double* workspace, float* out, pdae_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

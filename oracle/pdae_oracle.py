@@ -508,3 +508,67 @@ class DiffusionOracle:
             t = torch.full((z.shape[0],), i, dtype=torch.long)
             z = ddim_update(tabs, z, t, latent_fn(z, tmap[t]), None, "sample")
         return z
+
+
+# ------------------------------------------------------------------------------------------------
+# Caller-side steps: optimizer + EMA, wire formats, metrics
+
+def adam_ema_steps(params: List[torch.Tensor], grads_per_step: List[List[torch.Tensor]], lr: float, betas, eps: float,
+                   weight_decay: float, ema: Optional[List[torch.Tensor]] = None, ema_decay: float = 0.9999,
+                   ema_every: int = 1) -> None:
+    """torch.optim.Adam as configured at trainer/train_representation_learning.py:57-69, followed every `ema_every`
+    steps by the EMA loop of :192-212 (`ema.mul_(decay).add_(p, alpha=1-decay)`).  Updates params / ema IN PLACE."""
+    ps = [torch.nn.Parameter(p) for p in params]
+    opt = torch.optim.Adam(ps, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, foreach=False, fused=False)
+    for step, grads in enumerate(grads_per_step, 1):
+        for p, g in zip(ps, grads):
+            p.grad = g.clone()
+        opt.step()
+        if ema is not None and step % ema_every == 0:
+            for e, p in zip(ema, ps):
+                e.mul_(ema_decay).add_(p.data, alpha=1.0 - ema_decay)
+    for dst, p in zip(params, ps):
+        if dst.data_ptr() != p.data.data_ptr():
+            dst.copy_(p.data)
+
+
+def images_to_uint8_nhwc(images: torch.Tensor) -> torch.Tensor:
+    """trainer/train_representation_learning.py:173-174 (and every sampler): [-1,1] fp32 NCHW -> uint8 NHWC."""
+    images = images.mul(0.5).add(0.5).mul(255).add(0.5).clamp(0, 255)
+    return images.permute(0, 2, 3, 1).to(torch.uint8).contiguous()
+
+
+def uint8_nhwc_to_images(u8: torch.Tensor) -> torch.Tensor:
+    """dataset/ffhq.py:27-31: torchvision ToTensor (HWC uint8 -> CHW float, `.div(255)`) then
+    Normalize((0.5,)*3, (0.5,)*3) (`sub_(mean).div_(std)`)."""
+    x = u8.permute(0, 3, 1, 2).to(torch.float32).div(255)
+    return x.sub(0.5).div(0.5).contiguous()
+
+
+def calculate_mse(img1: torch.Tensor, img2: torch.Tensor) -> torch.Tensor:
+    """metric/utils.py:62-63."""
+    return (img1 - img2).pow(2).mean(dim=[1, 2, 3])
+
+
+def ssim_window(window_size: int = 11, sigma: float = 1.5) -> torch.Tensor:
+    """metric/utils.py:25-33: normalised 1-D Gaussian (fp32), outer product -> [ws, ws]."""
+    g = torch.tensor([math.exp(-(x - window_size // 2) ** 2 / float(2 * sigma ** 2)) for x in range(window_size)],
+                     dtype=torch.float32)
+    g = (g / g.sum()).unsqueeze(1)
+    return g.mm(g.t()).float()
+
+
+def calculate_ssim(img1: torch.Tensor, img2: torch.Tensor, window_size: int = 11) -> torch.Tensor:
+    """metric/utils.py:35-60."""
+    C = img1.shape[1]
+    window = ssim_window(window_size).expand(C, 1, window_size, window_size).contiguous()
+    pad = window_size // 2
+    mu1 = F.conv2d(img1, window, padding=pad, groups=C)
+    mu2 = F.conv2d(img2, window, padding=pad, groups=C)
+    mu1_sq, mu2_sq, mu1_mu2 = mu1.pow(2), mu2.pow(2), mu1 * mu2
+    s1 = F.conv2d(img1 * img1, window, padding=pad, groups=C) - mu1_sq
+    s2 = F.conv2d(img2 * img2, window, padding=pad, groups=C) - mu2_sq
+    s12 = F.conv2d(img1 * img2, window, padding=pad, groups=C) - mu1_mu2
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    ssim_map = ((2 * mu1_mu2 + C1) * (2 * s12 + C2)) / ((mu1_sq + mu2_sq + C1) * (s1 + s2 + C2))
+    return ssim_map.mean(1).mean(1).mean(1)

@@ -16,7 +16,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libpdae_b200.so")
-SOURCES = ["conv_simt.cu", "norm_elementwise.cu", "attention_simt.cu", "conv_tc.cu", "conv_tc2.cu", "backward_simt.cu"]
+SOURCES = ["conv_simt.cu", "norm_elementwise.cu", "attention_simt.cu", "conv_tc.cu", "conv_tc2.cu", "backward_simt.cu", "train_io.cu"]
 
 PDAE_F32, PDAE_BF16 = 0, 1
 RESAMPLE_NONE, RESAMPLE_UP2, RESAMPLE_DOWN2 = 0, 1, 2
@@ -99,6 +99,12 @@ _SIGS = {
     "pdae_softmax_bf16": (c_int, [_P, _P, c_int64, c_int, c_float, _P]),
     "pdae_transpose_v": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "pdae_conv_tc2_destroy": (None, [_P]),
+    "pdae_adam_ema_step": (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_int64, c_float,
+                                   c_float, _P]),
+    "pdae_images_to_u8_nhwc": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
+    "pdae_u8_nhwc_to_images": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
+    "pdae_mse_per_image": (c_int, [_P, _P, c_int, c_int64, _P, _P, _P]),
+    "pdae_ssim_per_image": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P]),
 }
 EXPORTS = tuple(_SIGS.keys())
 

@@ -205,6 +205,60 @@ __device__ __forceinline__ void load8(const T* p, float4& v0, float4& v1) {
   }
 }
 
+// raw (unconverted) 8-channel load: 16 B for bf16, 32 B for fp32 -- kept raw so a batch of loads is cheap in registers
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> { uint4 u; };
+template <> struct Raw8<float> { float4 a, b; };
+__device__ __forceinline__ void ld_raw8(const __nv_bfloat16* p, Raw8<__nv_bfloat16>& r) { r.u = __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void ld_raw8(const float* p, Raw8<float>& r) {
+  r.a = __ldg(reinterpret_cast<const float4*>(p));
+  r.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+}
+__device__ __forceinline__ void cvt_raw8(const Raw8<__nv_bfloat16>& r, float4& v0, float4& v1) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r.u);
+  const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]), f2 = __bfloat1622float2(h[2]),
+               f3 = __bfloat1622float2(h[3]);
+  v0 = make_float4(f0.x, f0.y, f1.x, f1.y);
+  v1 = make_float4(f2.x, f2.y, f3.x, f3.y);
+}
+__device__ __forceinline__ void cvt_raw8(const Raw8<float>& r, float4& v0, float4& v1) { v0 = r.a; v1 = r.b; }
+
+// One source, one channel octet per thread, pixels strided.  U loads are issued back to back before any dependent
+// math / store (the compiler serialises them otherwise: one 16-B load in flight per thread caps the kernel at ~4 TB/s).
+template <typename T, typename TRaw, int U>
+__device__ __forceinline__ void apply8_loop(const T* __restrict__ p, int Cs, __nv_bfloat16* __restrict__ po,
+                                            TRaw* __restrict__ pr, int C, int pix, int stride, int HW, float4 a0, float4 a1,
+                                            float4 b0, float4 b1, int silu) {
+  auto emit = [&](const Raw8<T>& r, int px) {
+    float4 v0, v1;
+    cvt_raw8(r, v0, v1);
+    const float4 r0 = affine_act<true>(v0, a0, b0, silu), r1 = affine_act<true>(v1, a1, b1, silu);
+    __nv_bfloat162 h[4] = {__floats2bfloat162_rn(r0.x, r0.y), __floats2bfloat162_rn(r0.z, r0.w),
+                           __floats2bfloat162_rn(r1.x, r1.y), __floats2bfloat162_rn(r1.z, r1.w)};
+    *reinterpret_cast<uint4*>(po + (long long)px * C) = *reinterpret_cast<uint4*>(h);
+    if (pr) {
+      if (sizeof(TRaw) == sizeof(T)) {  // same type: forward the raw bits
+        *reinterpret_cast<Raw8<T>*>(pr + (long long)px * C) = r;
+      } else {
+        store4<TRaw>(pr + (long long)px * C, v0);
+        store4<TRaw>(pr + (long long)px * C + 4, v1);
+      }
+    }
+  };
+  for (; pix + (U - 1) * stride < HW; pix += U * stride) {
+    Raw8<T> r[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) ld_raw8(p + (long long)(pix + u * stride) * Cs, r[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) emit(r[u], pix + u * stride);
+  }
+  for (; pix < HW; pix += stride) {
+    Raw8<T> r;
+    ld_raw8(p + (long long)pix * Cs, r);
+    emit(r, pix);
+  }
+}
+
 template <typename TSrc, typename TSrc2, typename TRaw>
 __global__ void __launch_bounds__(256) gn_apply8_kernel(const TSrc* __restrict__ s1, int C1, const TSrc2* __restrict__ s2,
                                                         int C2, const float* __restrict__ ab, int silu, int HW,
@@ -222,26 +276,13 @@ __global__ void __launch_bounds__(256) gn_apply8_kernel(const TSrc* __restrict__
     a0 = *reinterpret_cast<const float4*>(pa); a1 = *reinterpret_cast<const float4*>(pa + 4);
     b0 = *reinterpret_cast<const float4*>(pb); b1 = *reinterpret_cast<const float4*>(pb + 4);
   }
-  const bool first = c < C1;
-  const TSrc* p1 = s1 + (long long)b * HW * C1 + c;
-  const TSrc2* p2 = s2 + (long long)b * HW * C2 + (c - C1);
   __nv_bfloat16* po = out_act + (long long)b * HW * C + c;
   TRaw* pr = out_raw ? out_raw + (long long)b * HW * C + c : nullptr;
-  const int stride = gridDim.x * ppc;
-#pragma unroll 4
-  for (int pix = blockIdx.x * ppc + prow; pix < HW; pix += stride) {
-    float4 v0, v1;
-    if (first) load8<TSrc>(p1 + (long long)pix * C1, v0, v1);
-    else load8<TSrc2>(p2 + (long long)pix * C2, v0, v1);
-    const float4 r0 = affine_act<true>(v0, a0, b0, silu), r1 = affine_act<true>(v1, a1, b1, silu);
-    __nv_bfloat162 h[4] = {__floats2bfloat162_rn(r0.x, r0.y), __floats2bfloat162_rn(r0.z, r0.w),
-                           __floats2bfloat162_rn(r1.x, r1.y), __floats2bfloat162_rn(r1.z, r1.w)};
-    *reinterpret_cast<uint4*>(po + (long long)pix * C) = *reinterpret_cast<uint4*>(h);
-    if (pr) {
-      store4<TRaw>(pr + (long long)pix * C, v0);
-      store4<TRaw>(pr + (long long)pix * C + 4, v1);
-    }
-  }
+  const int stride = gridDim.x * ppc, pix0 = blockIdx.x * ppc + prow;
+  if (c < C1)
+    apply8_loop<TSrc, TRaw, 4>(s1 + (long long)b * HW * C1 + c, C1, po, pr, C, pix0, stride, HW, a0, a1, b0, b1, silu);
+  else
+    apply8_loop<TSrc2, TRaw, 4>(s2 + (long long)b * HW * C2 + (c - C1), C2, po, pr, C, pix0, stride, HW, a0, a1, b0, b1, silu);
 }
 
 template <typename TSrc, typename TSrc2, typename TAct, typename TRaw, int RS>

@@ -103,9 +103,14 @@ class DDIM:
             return img
         # fast path: drive the network's static plan buffers in place
         H, W = x.shape[2], x.shape[3]
+        tail = None   # (plan, x_in, t_in, eps) of the epsilon-only plan used once the shift is switched off
         if isinstance(net, ShiftUNet):
             plan, (x_in, t_in, z_in, eps, grad) = net.plan_for(B, H, W)
             z_in.tensor.copy_(cond)
+            if shift and direction == "sample" and stop_step > 0:
+                # ddim.py:119: steps with (i-1) < stop_step ignore the shift -> replay only the frozen epsilon half there
+                p2, (x2, t2, _, eps2, _) = net.plan_for(B, H, W, with_shift=False)
+                tail = (p2, x2, t2, eps2)
         else:
             plan, (x_in, t_in, c_in, eps) = net._get_plan(("unet", B, H, W), lambda P: net._build(P, B, H, W))
             grad = None
@@ -113,18 +118,23 @@ class DDIM:
                 c_in.tensor.copy_(cond)
         if self.use_cuda_graph:
             plan.capture_graph()
+            if tail is not None:
+                tail[0].capture_graph()
+        plan.run_prologue()   # step-invariant ops (label_emb(z), emb_z_layers): once per loop, not once per step
         x_in.tensor.copy_(x)
         t_loc = torch.empty(B, device=self.device, dtype=torch.int64)
-        eps_t = eps.tensor
         C = x.shape[1]
-        eps_used = eps_t if eps_t.shape[1] == C else None
         for i in self._steps(direction):
+            use_shift = shift and (direction == "encode" or (i - 1) >= stop_step)
+            if tail is not None and not use_shift and plan is not tail[0]:
+                tail[1].tensor.copy_(x_in.tensor)
+                plan, x_in, t_in, eps = tail
             t_loc.fill_(i)
             torch.index_select(self.timestep_map, 0, t_loc, out=t_in.tensor)
-            plan.run()
-            e = eps_used if eps_used is not None else eps_t[:, :C].contiguous()
-            g = grad.tensor if (shift and (direction == "encode" or (i - 1) >= stop_step)) else None
-            self._update(x_in.tensor, t_loc, e, g, direction, out=x_in.tensor)
+            plan.run(prologue=False)
+            eps_t = eps.tensor
+            e = eps_t if eps_t.shape[1] == C else eps_t[:, :C].contiguous()
+            self._update(x_in.tensor, t_loc, e, grad.tensor if use_shift else None, direction, out=x_in.tensor)
         return x_in.tensor.clone()
 
     def ddim_sample_loop(self, denoise_fn, x_T, condition=None):

@@ -106,6 +106,10 @@ class Plan:
         self.stream_bf16 = self.tc and self.v2 and os.environ.get("PDAE_STREAM_BF16", "1") == "1"
         self.L = _native.lib()
         self.ops: List[Tuple[str, list]] = []
+        # ops recorded inside `with P.prologue():` depend only on inputs that are constant over a sampling loop (z):
+        # a loop runs them once (run_prologue) and replays the remaining ops per step (run(prologue=False))
+        self.op_pro: List[bool] = []
+        self._in_prologue = False
         self.bufs: List[Buf] = []
         self.packed: List[Packed] = []
         self.params: List[Tuple[torch.Tensor, int]] = []
@@ -168,9 +172,23 @@ class Plan:
         return b
 
     # ---- recording --------------------------------------------------------------------------
+    def prologue(self):
+        """Context manager: ops recorded inside are step-invariant.  Every buffer they produce
+        for the per-step ops must be `keep` (private storage) -- asserted at finalize."""
+        plan = self
+
+        class _Ctx:
+            def __enter__(self):
+                plan._in_prologue = True
+
+            def __exit__(self, *exc):
+                plan._in_prologue = False
+        return _Ctx()
+
     def call(self, fn: str, *args, flops: float = 0.0) -> None:
         idx = len(self.ops)
         self.flops.append(float(flops))
+        self.op_pro.append(self._in_prologue)
         for a in args:
             b = a.buf if isinstance(a, BufView) else a
             if isinstance(b, Buf) and not b.fixed:
@@ -189,6 +207,7 @@ class Plan:
         if self._stats_elems:
             self.ops.insert(0, ("zero", [self._stats_arena, ctypes.c_int64(self._stats_elems * 4), _STREAM]))
             self.flops.insert(0, 0.0)
+            self.op_pro.insert(0, False)
             for b in self.bufs:  # op indices shift by one
                 if b is not self._stats_arena and b.first is not None:
                     b.first += 1
@@ -253,7 +272,12 @@ class Plan:
                     cargs.append(self._resolve(a))
             compiled.append((getattr(self.L, "pdae_" + fn), cargs, sidx, fn))
         self._compiled = compiled
-        self.n_launch = sum(_LAUNCHES.get(fn, 1) for fn, _ in self.ops)
+        self._pro_idx = [i for i, p in enumerate(self.op_pro) if p]
+        self._main_idx = [i for i, p in enumerate(self.op_pro) if not p]
+        for b in self.bufs:  # a recycled buffer must not carry data from the prologue into the per-step ops
+            if b.first is not None and not b.keep and not b.fixed and self.op_pro[b.first] and not self.op_pro[b.last]:
+                raise AssertionError(f"plan buffer {b.name!r} crosses the prologue boundary but is not `keep`")
+        self.n_launch = sum(_LAUNCHES.get(fn, 1) for (fn, _), p in zip(self.ops, self.op_pro) if not p)
         return self
 
     @staticmethod
@@ -323,17 +347,27 @@ class Plan:
     def stale(self) -> bool:
         return any(p.data_ptr() != ptr for p, ptr in self.params)
 
-    def _launch_all(self) -> None:
+    def _launch_all(self, idx: Optional[List[int]] = None) -> None:
         stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        for cfn, cargs, sidx, name in self._compiled:
+        for i in (self._main_idx if idx is None else idx):
+            cfn, cargs, sidx, name = self._compiled[i]
             cargs[sidx] = stream
             rc = cfn(*cargs)
             if rc != 0:
                 _native.check(rc, "pdae_" + name)
 
-    def run(self) -> None:
+    def run_prologue(self) -> None:
+        """Launch only the step-invariant ops (after the loop's constant inputs have been written)."""
         for pk in self.packed:
             pk.refresh()
+        if self._pro_idx:
+            self._launch_all(self._pro_idx)
+
+    def run(self, prologue: bool = True) -> None:
+        for pk in self.packed:
+            pk.refresh()
+        if prologue and self._pro_idx:
+            self._launch_all(self._pro_idx)
         if self.graph is not None:
             self.graph.replay()
         else:
@@ -346,6 +380,7 @@ class Plan:
             return self
         for pk in self.packed:
             pk.refresh()
+        self._launch_all(self._pro_idx)
         self._launch_all()  # warm-up outside capture (lazy module loading, cudaFuncSetAttribute, ...)
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
@@ -363,19 +398,22 @@ class Plan:
         stream = ctypes.c_void_p(st.cuda_stream)
         n = len(self._compiled)
         acc = [0.0] * n
+        self._launch_all(self._pro_idx)
         for _ in range(reps):
-            evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(self._main_idx) + 1)]
             evs[0].record(st)
-            for i, (cfn, cargs, sidx, name) in enumerate(self._compiled):
+            for k, i in enumerate(self._main_idx):
+                cfn, cargs, sidx, name = self._compiled[i]
                 cargs[sidx] = stream
                 _native.check(cfn(*cargs), "pdae_" + name)
-                evs[i + 1].record(st)
+                evs[k + 1].record(st)
             st.synchronize()
-            for i in range(n):
-                acc[i] += evs[i].elapsed_time(evs[i + 1]) / reps
-        self.last_op_ms = acc  # per recorded op, same order as self.ops
+            for k, i in enumerate(self._main_idx):
+                acc[i] += evs[k].elapsed_time(evs[k + 1]) / reps
+        self.last_op_ms = acc  # per recorded op, same order as self.ops (0 for prologue ops: not part of a step)
         out: Dict[str, Dict[str, float]] = {}
-        for i, (_, _, _, name) in enumerate(self._compiled):
+        for i in self._main_idx:
+            name = self._compiled[i][3]
             d = out.setdefault(name, {"ms": 0.0, "flops": 0.0, "launches": 0})
             d["ms"] += acc[i]
             d["flops"] += self.flops[i]

@@ -61,7 +61,9 @@ class ShiftUNet(PlannedModule):
             m.requires_grad_(requires_grad=False)
 
     # ---- plan ---------------------------------------------------------------------------------------
-    def _build(self, P: Plan, B: int, H: int, W: int):
+    def _build(self, P: Plan, B: int, H: int, W: int, with_shift: bool = True):
+        """with_shift=False records only the frozen epsilon half (== the plain UNet): the plan a sampling loop replays on
+        its `use_shift=False` tail steps (ddim.py:119, stop_percent > 0), skipping ~45 % of the FLOPs."""
         dev = self._device()
         E, base = self.time_embed_dim, self.base_channel
         x_in = P.new((B, self.input_channel, H, W), torch.float32, "x_nchw")
@@ -69,13 +71,20 @@ class ShiftUNet(PlannedModule):
         z_in = P.new((B, self.latent_dim), torch.float32, "z")
         for b in (x_in, t_in, z_in):
             b.keep = True
+        shift_blocks = res_blocks_of(self.shift_middle_block, self.shift_output_blocks) if with_shift else []
+        bank_z = None
+        if with_shift:
+            # z is constant over a sampling loop: label_emb(z) and every emb_z_layers Linear are step-invariant
+            #  -- recorded as the plan's prologue, run once per loop instead of once per step
+            with P.prologue():
+                shift_emb = P.new((B, E), torch.float32, "shift_emb")
+                shift_emb.keep = True
+                P.linear(z_in, self.label_emb.weight, self.label_emb.bias, shift_emb, B=B, Cin=self.latent_dim, Cout=E)
+                bank_z = EmbBank(P, shift_blocks, "z", shift_emb, B, E, "shift_z")
+                bank_z.out.keep = True
         emb = emit_time_embed(P, self.time_embed, t_in, B, base, E, dev)
-        shift_emb = P.new((B, E), torch.float32, "shift_emb")
-        P.linear(z_in, self.label_emb.weight, self.label_emb.bias, shift_emb, B=B, Cin=self.latent_dim, Cout=E)
-        shift_blocks = res_blocks_of(self.shift_middle_block, self.shift_output_blocks)
         bank_t = EmbBank(P, res_blocks_of(self.input_blocks, self.middle_block, self.output_blocks) + shift_blocks, "t",
-                         emb, B, E, "shift_t")
-        bank_z = EmbBank(P, shift_blocks, "z", shift_emb, B, E, "shift_z")
+                         emb, B, E, "shift_t" if with_shift else "eps_t")
 
         stem = self.input_blocks[0][0]
         c0 = stem.weight.shape[0]
@@ -88,21 +97,27 @@ class ShiftUNet(PlannedModule):
             h = stage.emit(P, h, bank_t)
             hs.append(h)
         eps_h = self.middle_block.emit(P, h, bank_t)
-        shift_h = self.shift_middle_block.emit(P, h, bank_t, bank_z)
+        shift_h = self.shift_middle_block.emit(P, h, bank_t, bank_z) if with_shift else None
         for stage, shift_stage in zip(self.output_blocks, self.shift_output_blocks):
             skip = hs.pop()
             eps_h = stage.emit(P, eps_h.cat(skip), bank_t)
-            shift_h = shift_stage.emit(P, shift_h.cat(skip), bank_t, bank_z)
+            if with_shift:
+                shift_h = shift_stage.emit(P, shift_h.cat(skip), bank_t, bank_z)
         eps = P.new((B, self.output_channel, H, W), torch.float32, "eps_nchw")
-        grad = P.new((B, self.input_channel, H, W), torch.float32, "shift_nchw")
-        eps.keep = grad.keep = True
+        eps.keep = True
         emit_head(P, self.out, eps_h, eps)
-        emit_head(P, self.shift_out, shift_h, grad)
+        grad = None
+        if with_shift:
+            grad = P.new((B, self.input_channel, H, W), torch.float32, "shift_nchw")
+            grad.keep = True
+            emit_head(P, self.shift_out, shift_h, grad)
         return x_in, t_in, z_in, eps, grad
 
-    def plan_for(self, B: int, H: int, W: int):
-        """(plan, (x_in, t_in, z_in, eps, grad)) -- static buffers a sampling loop can drive directly."""
-        return self._get_plan(("shiftunet", B, H, W, self.training), lambda P: self._build(P, B, H, W))
+    def plan_for(self, B: int, H: int, W: int, with_shift: bool = True):
+        """(plan, (x_in, t_in, z_in, eps, grad)) -- static buffers a sampling loop can drive directly.
+        with_shift=False: the epsilon-only plan (grad is None, z_in unused)."""
+        return self._get_plan(("shiftunet" if with_shift else "shiftunet_eps", B, H, W, self.training),
+                              lambda P: self._build(P, B, H, W, with_shift))
 
     def forward(self, x, time, condition):
         """x [N,3,H,W], time int64 [N], condition = z [N, latent_dim] -> (epsilon, shift), both NCHW fp32."""

@@ -39,8 +39,10 @@ def all_gather_images(local: torch.Tensor, n_total: int) -> torch.Tensor:
 
 
 def sharded_autoencode(gd, encoder, decoder, x0_all: torch.Tensor, enc_style: str = "ddim100", dec_style: str = "ddim100",
-                       device=None) -> torch.Tensor:
-    """Autoencode a global batch: every rank runs the hot path on its shard, then one all-gather."""
+                       device=None, as_uint8: bool = False) -> torch.Tensor:
+    """Autoencode a global batch: every rank runs the hot path on its shard, then one all-gather.
+    as_uint8: convert each shard to the reference's wire format first (uint8 NHWC,
+    trainer/train_representation_learning.py:173-174) so the gather moves 4x fewer bytes."""
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     s, e = shard_range(x0_all.shape[0], rank, world)
@@ -48,4 +50,41 @@ def sharded_autoencode(gd, encoder, decoder, x0_all: torch.Tensor, enc_style: st
     if device is not None:
         x = x.to(device)
     rec = gd.representation_learning_autoencoding(enc_style, dec_style, encoder, decoder, x)
+    if as_uint8:
+        from ..metric import images_to_uint8
+        rec = images_to_uint8(rec)
     return all_gather_images(rec, x0_all.shape[0])
+
+
+def allreduce_grads_(params, bucket_bytes: int = 32 << 20) -> float:
+    """DDP-equivalent gradient exchange for the trainable parameters (encoder + label_emb, shift_middle_block,
+    shift_output_blocks, shift_out; trainer/train_representation_learning.py:44-49 wraps them in DDP): SUM all-reduce of
+    every `.grad` in flat buckets, issued asynchronously so bucket k's collective overlaps bucket k+1's packing.
+    Returns the factor the caller must fold into the optimizer (`FusedAdamEMA.step(grad_scale=...)`) = 1 / world_size
+    -- the mean is never materialised as a separate pass over the gradients."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return 1.0
+    grads = [p.grad for p in params if p.grad is not None]
+    buckets: List[List[torch.Tensor]] = []
+    cur: List[torch.Tensor] = []
+    size = 0
+    for g in grads:
+        nb = g.numel() * g.element_size()
+        if cur and (size + nb > bucket_bytes or g.dtype != cur[0].dtype):
+            buckets.append(cur)
+            cur, size = [], 0
+        cur.append(g)
+        size += nb
+    if cur:
+        buckets.append(cur)
+    pending = []
+    for bk in buckets:
+        flat = torch.cat([g.reshape(-1) for g in bk])
+        pending.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True), flat, bk))
+    for work, flat, bk in pending:
+        work.wait()
+        off = 0
+        for g in bk:
+            g.copy_(flat[off: off + g.numel()].view_as(g))
+            off += g.numel()
+    return 1.0 / dist.get_world_size()

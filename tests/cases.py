@@ -52,3 +52,19 @@ def model_case(cfg):
 
 def sd_of(module):
     return {k: v.detach().float().cpu().clone() for k, v in module.state_dict().items()}
+
+
+def caller_io_inputs(cfg):
+    """Inputs of tests/golden/make_golden.py::caller_cases (metrics + wire formats)."""
+    a = synth_images(cfg["n"], 3, cfg["size"], 41)
+    b = (a + 0.1 * synth_normal((cfg["n"], 3, cfg["size"], cfg["size"]), 42)).clamp(-1, 1)
+    return a, b
+
+
+def adam_case(cfg):
+    """Initial params and per-step grads of the caller_adam_* fixtures."""
+    shapes = [tuple(s) for s in cfg["shapes"]]
+    params = [synth_normal(s, 50 + i) * 0.1 for i, s in enumerate(shapes)]
+    scale = (lambda i: 10.0 ** (i - 2)) if cfg["ema_decay"] >= 0 else (lambda i: 1.0)
+    grads = [[synth_normal(s, 100 + 10 * step + i) * scale(i) for i, s in enumerate(shapes)] for step in range(cfg["steps"])]
+    return params, grads

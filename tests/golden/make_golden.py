@@ -195,8 +195,53 @@ def training_cases():
     torch.set_grad_enabled(False)
 
 
+def caller_cases():
+    """optimizer + EMA, wire formats, metrics -- the callers either side of the hot path."""
+    from metric.utils import calculate_mse, calculate_ssim  # noqa: E402 (reference; imports torch + PIL only)
+    import torchvision.transforms as T
+    a = synth_images(3, 3, 40, 41)
+    b = (a + 0.1 * synth_normal((3, 3, 40, 40), 42)).clamp(-1, 1)
+    # the trainers' / samplers' image conversion, trainer/train_representation_learning.py:173-174 (expression as used there)
+    u8 = (b * 1.3).mul(0.5).add(0.5).mul(255).add(0.5).clamp(0, 255).permute(0, 2, 3, 1).to("cpu", torch.uint8)
+    # dataset/ffhq.py:27-31 (no Resize: the fixture is already at size): ToTensor + Normalize on each HWC uint8 image
+    tf = T.Compose([T.ToTensor(), T.Normalize((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))])
+    back = torch.stack([tf(img.numpy()) for img in u8])
+    save("caller_metrics_io", dict(kind="caller_io", n=3, size=40), mse=calculate_mse(a, b), ssim=calculate_ssim(a, b),
+         u8=u8, back=back)
+    # Adam exactly as trainer/train_representation_learning.py:57-69 builds it (config/ffhq_representation_learning.yml:33-37)
+    # and the EMA loop of :192-212 with ema_every=1, ema_decay=0.9999 (:46-47)
+    torch.set_grad_enabled(True)
+    shapes = [(64, 3, 3, 3), (64,), (37,), (128, 64), (5, 7, 3)]
+    ps = [torch.nn.Parameter(synth_normal(s, 50 + i) * 0.1) for i, s in enumerate(shapes)]
+    ema = [p.detach().clone() for p in ps]
+    opt = torch.optim.Adam([{"params": ps[:2]}, {"params": ps[2:]}], lr=float("1e-4"), betas=eval("(0.9, 0.999)"),
+                           eps=float("1e-8"), weight_decay=float("0.0"))
+    for step in range(4):
+        for i, p in enumerate(ps):
+            p.grad = synth_normal(tuple(p.shape), 100 + 10 * step + i) * (10.0 ** (i - 2))
+        opt.step()
+        for e, p in zip(ema, ps):
+            e.data.mul_(0.9999).add_(p.data, alpha=1.0 - 0.9999)
+    torch.set_grad_enabled(False)
+    save("caller_adam_ema", dict(kind="caller_adam", shapes=shapes, steps=4, lr=1e-4, betas=[0.9, 0.999], eps=1e-8,
+                                 weight_decay=0.0, ema_decay=0.9999),
+         **{f"p{i}": p.detach() for i, p in enumerate(ps)}, **{f"e{i}": e for i, e in enumerate(ema)})
+    # weight decay + a larger lr so every term of the update is exercised
+    ps = [torch.nn.Parameter(synth_normal(s, 50 + i) * 0.1) for i, s in enumerate(shapes)]
+    opt = torch.optim.Adam(ps, lr=3e-3, betas=(0.8, 0.95), eps=1e-6, weight_decay=0.01)
+    torch.set_grad_enabled(True)
+    for step in range(3):
+        for i, p in enumerate(ps):
+            p.grad = synth_normal(tuple(p.shape), 100 + 10 * step + i)
+        opt.step()
+    torch.set_grad_enabled(False)
+    save("caller_adam_wd", dict(kind="caller_adam", shapes=shapes, steps=3, lr=3e-3, betas=[0.8, 0.95], eps=1e-6,
+                                weight_decay=0.01, ema_decay=-1.0), **{f"p{i}": p.detach() for i, p in enumerate(ps)})
+
+
 if __name__ == "__main__":
     block_cases()
     model_cases()
     diffusion_cases()
     training_cases()
+    caller_cases()

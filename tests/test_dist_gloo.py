@@ -30,6 +30,14 @@ def _worker(rank, world, port, n_total, q):
             return x + 1.0
     got2 = sharded_autoencode(FakeGD(), None, None, full)
     ok = ok and torch.equal(got2, full + 1.0)
+    # gradient exchange: bucketed SUM all-reduce, 1/world returned for the optimizer to fold in
+    from pdae_b200.utils.dist import allreduce_grads_
+    ps = [torch.nn.Parameter(torch.zeros(n)) for n in (5, 70000, 3, 12)] + [torch.nn.Parameter(torch.zeros(2))]
+    for i, p in enumerate(ps[:-1]):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    scale = allreduce_grads_(ps, bucket_bytes=4096)          # last param has no grad; several buckets
+    ok = ok and scale == 1.0 / world and ps[-1].grad is None
+    ok = ok and all(torch.equal(p.grad, torch.full_like(p, 3.0 * (i + 1))) for i, p in enumerate(ps[:-1]))
     q.put((rank, ok, (s, e)))
     dist.destroy_process_group()
 

@@ -60,3 +60,28 @@ def test_host_cores_respects_quota():
     from pdae_b200.utils.host import host_cores
     import os
     assert 1 <= host_cores() <= (os.cpu_count() or 1)
+
+
+def test_prologue_ops_are_split_out_and_their_outputs_must_be_private():
+    """Step-invariant ops are recorded in a prologue: run once per loop, excluded from the
+    per-step launch list; a buffer crossing the boundary must be `keep` or the arena could recycle it."""
+    import pytest
+
+    def build(keep):
+        P = Plan(torch.device("cpu"), "fp32", check_device=False)
+        z = P.new((2, 8), name="z")
+        z.keep = True
+        with P.prologue():
+            zc = P.new((2, 8), name="z_cached")
+            zc.keep = keep
+            P.call("copy_cols", z, zc, 8, 0, 2, 8, _STREAM)
+        out = P.new((2, 8), name="out")
+        out.keep = True
+        P.call("copy_cols", zc, out, 8, 0, 2, 8, _STREAM)
+        P.call("copy_cols", zc, out, 8, 0, 2, 4, _STREAM)
+        return P
+
+    P = build(True).finalize()
+    assert P._pro_idx == [0] and P._main_idx == [1, 2] and P.n_launch == 2
+    with pytest.raises(AssertionError):
+        build(False).finalize()

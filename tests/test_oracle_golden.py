@@ -162,3 +162,25 @@ def test_loop_sensitivity():
         b = D.representation_learning_ddim_sample("ddim10", dec, xT + 1e-5 * synth_normal((2, 3, 16, 16), 99), z)
     amp = float((a - b).abs().max()) / 1e-5
     assert 1.0 < amp < 1e3, amp
+
+
+def test_caller_metrics_and_wire_formats():
+    cfg, g = load_golden("caller_metrics_io")
+    a, b = cases.caller_io_inputs(cfg)
+    assert_close(O.calculate_mse(a, b), g["mse"], rtol=1e-6, atol=0, what="mse")
+    assert_close(O.calculate_ssim(a, b), g["ssim"], rtol=1e-6, atol=1e-7, what="ssim")
+    u8 = O.images_to_uint8_nhwc(b * 1.3)
+    assert u8.dtype == torch.uint8 and torch.equal(u8, g["u8"])
+    assert torch.equal(O.uint8_nhwc_to_images(g["u8"]), g["back"])
+
+
+@pytest.mark.parametrize("name", ["caller_adam_ema", "caller_adam_wd"])
+def test_caller_adam_ema(name):
+    cfg, g = load_golden(name)
+    params, grads = cases.adam_case(cfg)
+    ema = [p.clone() for p in params] if cfg["ema_decay"] >= 0 else None
+    O.adam_ema_steps(params, grads, cfg["lr"], tuple(cfg["betas"]), cfg["eps"], cfg["weight_decay"], ema, cfg["ema_decay"])
+    for i, p in enumerate(params):
+        assert_close(p, g[f"p{i}"], rtol=1e-6, atol=1e-8, what=f"p{i}")
+        if ema is not None:
+            assert_close(ema[i], g[f"e{i}"], rtol=1e-6, atol=1e-8, what=f"e{i}")

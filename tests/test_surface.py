@@ -86,3 +86,26 @@ def test_dropin_aliases():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr
+
+
+def test_fused_adam_surface_and_no_cpu_fallback():
+    """FusedAdamEMA keeps torch.optim.Adam's constructor / param_groups / state_dict surface
+    (trainer/train_representation_learning.py:54-69) and refuses CPU parameters instead of falling back."""
+    import torch
+    from pdae_b200 import _native
+    from pdae_b200.metric import calculate_mse, images_to_uint8
+    from pdae_b200.optim import FusedAdamEMA
+    a, b = torch.nn.Parameter(torch.zeros(4)), torch.nn.Parameter(torch.zeros(3))
+    opt = FusedAdamEMA([{"params": [a]}, {"params": [b], "lr": 5e-4}], lr=float("1e-4"), betas=eval("(0.9, 0.999)"),
+                       eps=float("1e-8"), weight_decay=float("0.0"))
+    assert [g["lr"] for g in opt.param_groups] == [1e-4, 5e-4]
+    assert set(opt.state_dict()) == {"state", "param_groups"}
+    opt.zero_grad()
+    opt.step()                       # no grads: nothing to do, no native call needed
+    a.grad = torch.ones(4)
+    with pytest.raises(_native.NativeError):
+        opt.step()
+    with pytest.raises(_native.NativeError):
+        calculate_mse(torch.zeros(1, 3, 4, 4), torch.zeros(1, 3, 4, 4))
+    with pytest.raises(_native.NativeError):
+        images_to_uint8(torch.zeros(1, 3, 4, 4))
