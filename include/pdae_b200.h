@@ -80,6 +80,15 @@ int pdae_gn_apply(const void* src1, int src1_dtype, int C1, const void* src2, in
                   int silu, int resample, int B, int H, int W, void* out_act, int act_dtype, void* out_raw, int raw_dtype,
                   pdae_stream_t stream);
 
+/* GroupNorm(32) + affine/AdaGN + SiLU in ONE launch (the gn_coef_ch + gn_apply pair): coefficients are derived in each
+ * CTA's prologue from the per-channel (sum, sum^2) of the sources ([B][C][2] fp32, as accumulated by the conv epilogue or
+ * pdae_ch_stats).  No resampling; out_act is bf16 NHWC [B][H][W][C1+C2]; out_raw (optional) the un-normalised concat in
+ * raw_dtype.  Replaces nn.GroupNorm + scale/shift + nn.SiLU of model/module.py:241-243,255-258,291-293,380-381.
+ * C1, C2 multiples of 8, 64 <= C1+C2 <= 2048, (C1+C2) % 32 == 0.                                                        */
+int pdae_gn_norm_apply(const void* src1, int src1_dtype, int C1, const float* chs1, const void* src2, int src2_dtype, int C2,
+                       const float* chs2, const float* gamma, const float* beta, float eps, const float* emb, int emb_ld,
+                       const float* embz, int embz_ld, int silu, int B, int H, int W, void* out_act, void* out_raw,
+                       int raw_dtype, pdae_stream_t stream);
 /* Per-channel variant of the statistics (what the tensor-core conv epilogue accumulates): chs[b][c] = (sum, sum^2)
  * in fp32.  pdae_ch_stats fills it for a tensor that no conv epilogue produced; pdae_gn_coef_ch forms the 32 group
  * statistics over the virtual concat [chs1 | chs2] (groups may straddle the seam) and folds the affine / AdaGN terms. */
@@ -182,6 +191,12 @@ int pdae_conv_tc2_create(pdae_conv_tc2_plan** plan, const void* in_bf16, const v
 int pdae_conv_tc2_create_skip(pdae_conv_tc2_plan** plan, const void* in_bf16, const void* w_bf16, const float* bias,
                               const void* in2_bf16, const void* w2_bf16, int Cin2, void* out, int out_dtype, float* ch_stats,
                               int B, int H, int W, int Cin, int Cout, int ksize, int bn_override);
+/* Same, the skip conv's input being cat([in2a (Cin2a ch), in2b (Cin2b ch)], channel) of two NHWC bf16 tensors, never
+ * materialised (unet.py:199 `torch.cat([h, hs.pop()], dim=1)` feeding module.py:297); Cin2a, Cin2b multiples of 64.     */
+int pdae_conv_tc2_create_skip2(pdae_conv_tc2_plan** plan, const void* in_bf16, const void* w_bf16, const float* bias,
+                               const void* in2a_bf16, int Cin2a, const void* in2b_bf16, int Cin2b, const void* w2_bf16,
+                               void* out, int out_dtype, float* ch_stats, int B, int H, int W, int Cin, int Cout, int ksize,
+                               int bn_override);
 /* Batched GEMM on the same kernel (tensor-core attention, model/module.py:452-456,483-487): for each batch item
  * out[M x N] = A[M x K] * Bm[N x K]^T, both operands bf16 K-major; *_ld = elements between rows, *_bs = between items.
  * M % 128 == 0, N % 64 == 0, K % 64 == 0.                                                                             */

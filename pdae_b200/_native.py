@@ -93,12 +93,16 @@ _SIGS = {
                                      c_int, c_int]),
     "pdae_conv_tc2_create_skip": (c_int, [POINTER(c_void_p), _P, _P, _P, _P, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int,
                                           c_int, c_int, c_int]),
+    "pdae_conv_tc2_create_skip2": (c_int, [POINTER(c_void_p), _P, _P, _P, _P, c_int, _P, c_int, _P, _P, c_int, _P, c_int, c_int,
+                                           c_int, c_int, c_int, c_int, c_int]),
     "pdae_gemm_tc2_create": (c_int, [POINTER(c_void_p), _P, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int, c_int64, c_int64,
                                      c_int, c_int, c_int, c_int]),
     "pdae_conv_tc2_run": (c_int, [_P, _P]),
     "pdae_softmax_bf16": (c_int, [_P, _P, c_int64, c_int, c_float, _P]),
     "pdae_transpose_v": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "pdae_conv_tc2_destroy": (None, [_P]),
+    "pdae_gn_norm_apply": (c_int, [_P, c_int, c_int, _P, _P, c_int, c_int, _P, _P, _P, c_float, _P, c_int, _P, c_int, c_int, c_int,
+                                   c_int, c_int, _P, _P, c_int, _P]),
     "pdae_adam_ema_step": (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_int64, c_float,
                                    c_float, _P]),
     "pdae_images_to_u8_nhwc": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),

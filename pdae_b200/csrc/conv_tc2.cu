@@ -36,6 +36,7 @@ struct ConvTc2Args {
   int has_res, out_bf16, cout_valid;
   int w_batched;  // B operand is a per-image matrix (batched GEMM): 3rd TMA coordinate = image index
   int kblocks2;   // fused 1x1 skip conv: extra K blocks from a second (activation, weight) pair, accumulated into the same tile
+  int kblocks2a;  // ... of which the first kblocks2a come from tmA2, the rest from tmA3 (virtual channel concat of two tensors)
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -129,7 +130,8 @@ template <int BN>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
-                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, ConvTc2Args p) {
+                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                const __grid_constant__ CUtensorMap tmA3, ConvTc2Args p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[T2_MAX_STAGES], bar_empty[T2_MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2], bar_res[2];
@@ -215,7 +217,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t full = s_u32(&bar_full[s]);
           mb_expect_tx(full, T2_A_BYTES + B_BYTES);
           const uint32_t sa = smem0 + (uint32_t)s * STAGE_BYTES;
-          tma_ld4(sa, &tmA2, full, kb2 * T2_BK, x0, y0, b0);
+          if (kb2 < p.kblocks2a) tma_ld4(sa, &tmA2, full, kb2 * T2_BK, x0, y0, b0);
+          else tma_ld4(sa, &tmA3, full, (kb2 - p.kblocks2a) * T2_BK, x0, y0, b0);
           tma_ld3(sa + T2_A_BYTES, &tmB2, full, kb2 * T2_BK, n0, 0);
           if (++s == S) { s = 0; ph ^= 1u; }
         }
@@ -493,15 +496,15 @@ static int pow2_tile(int W, int cap) {
 
 template <int BN>
 static cudaError_t launch_tc2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& r,
-                              const CUtensorMap& a2, const CUtensorMap& b2, const ConvTc2Args& args, int grid, size_t smem,
-                              cudaStream_t s) {
+                              const CUtensorMap& a2, const CUtensorMap& b2, const CUtensorMap& a3, const ConvTc2Args& args,
+                              int grid, size_t smem, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);  // + static (barriers, stats) <= 227 KB
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  conv_tc2_kernel<BN><<<grid, T2_THREADS, smem, s>>>(a, b, o, r, a2, b2, args);
+  conv_tc2_kernel<BN><<<grid, T2_THREADS, smem, s>>>(a, b, o, r, a2, b2, a3, args);
   return cudaPeekAtLastError();
 }
 
@@ -510,7 +513,7 @@ static cudaError_t launch_tc2(const CUtensorMap& a, const CUtensorMap& b, const 
 using namespace pdae;
 
 struct pdae_conv_tc2_plan {
-  CUtensorMap tmA, tmB, tmO, tmR, tmA2, tmB2;
+  CUtensorMap tmA, tmB, tmO, tmR, tmA2, tmB2, tmA3;
   ConvTc2Args args;
   int BN, grid;
   size_t smem;
@@ -528,6 +531,7 @@ struct Tc2Desc {
   long long w_ld, w_bs;
   long long out_ld, out_bs;   // elements between consecutive pixels / images of the output
   const void* in2 = nullptr; const void* w2 = nullptr; int Cin2 = 0;   // fused 1x1 skip conv (bf16 NHWC input, [Cout][Cin2] weights)
+  const void* in3 = nullptr; int Cin2a = 0;   // skip input = channel concat of in2 [..,Cin2a] and in3 [..,Cin2-Cin2a] (in3 == nullptr: in2 alone)
 };
 
 static int tc2_create(pdae_conv_tc2_plan** plan_out, const Tc2Desc& d) {
@@ -621,18 +625,26 @@ static int tc2_create(pdae_conv_tc2_plan** plan_out, const Tc2Desc& d) {
   pl->tmR = pl->tmA;
   pl->tmA2 = pl->tmA;
   pl->tmB2 = pl->tmB;
+  pl->tmA3 = pl->tmA;
   if (d.Cin2 > 0) {
-    if (!d.in2 || !d.w2 || d.Cin2 % T2_BK != 0 || head || d.w_batched || ((uintptr_t)d.in2 & 15) || ((uintptr_t)d.w2 & 15)) {
+    const int Ca = d.in3 ? d.Cin2a : d.Cin2, Cb = d.Cin2 - Ca;
+    if (!d.in2 || !d.w2 || d.Cin2 % T2_BK != 0 || head || d.w_batched || ((uintptr_t)d.in2 & 15) || ((uintptr_t)d.w2 & 15) ||
+        (d.in3 && (Ca <= 0 || Cb <= 0 || Ca % T2_BK != 0 || ((uintptr_t)d.in3 & 15)))) {
       delete pl;
-      PDAE_REQUIRE(false, "conv_tc2_create: bad fused-skip operands (Cin2=%d)", d.Cin2);
+      PDAE_REQUIRE(false, "conv_tc2_create: bad fused-skip operands (Cin2=%d, Cin2a=%d)", d.Cin2, d.Cin2a);
     }
-    cuuint64_t dims[4] = {(cuuint64_t)d.Cin2, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)d.Cin2 * 2, (cuuint64_t)W * d.Cin2 * 2, (cuuint64_t)H * W * d.Cin2 * 2};
+    a.kblocks2a = Ca / T2_BK;
     cuuint32_t box[4] = {(cuuint32_t)T2_BK, (cuuint32_t)a.tw, (cuuint32_t)a.th, (cuuint32_t)a.tn};
-    CUresult r = enc(&pl->tmA2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d.in2), dims, strides, box, estr4,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail("A2", (int)r);
+    CUresult r = CUDA_SUCCESS;
+    for (int part = 0; part < (d.in3 ? 2 : 1); ++part) {
+      const int Cp = part ? Cb : Ca;
+      cuuint64_t dims[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+      cuuint64_t strides[3] = {(cuuint64_t)Cp * 2, (cuuint64_t)W * Cp * 2, (cuuint64_t)H * W * Cp * 2};
+      r = enc(part ? &pl->tmA3 : &pl->tmA2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(part ? d.in3 : d.in2), dims,
+              strides, box, estr4, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(part ? "A3" : "A2", (int)r);
+    }
     cuuint64_t wd[3] = {(cuuint64_t)d.Cin2, (cuuint64_t)Cout, 1};
     cuuint64_t ws[2] = {(cuuint64_t)d.Cin2 * 2, (cuuint64_t)Cout * d.Cin2 * 2};
     cuuint32_t wb[3] = {(cuuint32_t)T2_BK, (cuuint32_t)BN, 1};
@@ -692,6 +704,24 @@ extern "C" int pdae_conv_tc2_create_skip(pdae_conv_tc2_plan** plan_out, const vo
   return tc2_create(plan_out, d);
 }
 
+// Same, the skip conv's input being the channel concat cat([in2a (Cin2a ch), in2b (Cin2b ch)]) of two NHWC bf16 tensors
+// that is never materialised (unet.py:199 `torch.cat([h, hs.pop()], dim=1)` feeding module.py:297 skip_connection).
+extern "C" int pdae_conv_tc2_create_skip2(pdae_conv_tc2_plan** plan_out, const void* in_bf16, const void* w_bf16,
+                                          const float* bias, const void* in2a_bf16, int Cin2a, const void* in2b_bf16, int Cin2b,
+                                          const void* w2_bf16, void* out, int out_dtype, float* ch_stats, int B, int H, int W,
+                                          int Cin, int Cout, int ksize, int bn_override) {
+  PDAE_REQUIRE(in2b_bf16 && Cin2b > 0, "conv_tc2_create_skip2: second skip source missing");
+  Tc2Desc d;
+  d.in = in_bf16; d.w = w_bf16; d.bias = bias; d.residual = nullptr; d.out = out; d.out_dtype = out_dtype;
+  d.ch_stats = ch_stats; d.B = B; d.H = H; d.W = W; d.Cin = Cin; d.Cout = Cout; d.ksize = ksize; d.cout_valid = 0;
+  d.bn_override = bn_override;
+  d.in_ld = Cin; d.in_bs = (long long)H * W * Cin;
+  d.w_batched = 0; d.w_ld = Cin; d.w_bs = (long long)Cout * Cin;
+  d.out_ld = Cout; d.out_bs = (long long)H * W * Cout;
+  d.in2 = in2a_bf16; d.w2 = w2_bf16; d.Cin2 = Cin2a + Cin2b; d.in3 = in2b_bf16; d.Cin2a = Cin2a;
+  return tc2_create(plan_out, d);
+}
+
 // Batched GEMM on the same kernel: for every batch item i,  out_i[M x N] = A_i[M x K] * Bm_i[N x K]^T  (both K-major bf16).
 // a_ld / b_ld / out_ld: elements between consecutive rows; *_bs: elements between consecutive batch items.
 extern "C" int pdae_gemm_tc2_create(pdae_conv_tc2_plan** plan_out, const void* a_bf16, long long a_ld, long long a_bs,
@@ -711,10 +741,10 @@ extern "C" int pdae_conv_tc2_run(const pdae_conv_tc2_plan* pl, pdae_stream_t str
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e;
   switch (pl->BN) {
-    case 16: e = launch_tc2<16>(pl->tmA, pl->tmB, pl->tmO, pl->tmR, pl->tmA2, pl->tmB2, pl->args, pl->grid, pl->smem, s); break;
-    case 64: e = launch_tc2<64>(pl->tmA, pl->tmB, pl->tmO, pl->tmR, pl->tmA2, pl->tmB2, pl->args, pl->grid, pl->smem, s); break;
-    case 128: e = launch_tc2<128>(pl->tmA, pl->tmB, pl->tmO, pl->tmR, pl->tmA2, pl->tmB2, pl->args, pl->grid, pl->smem, s); break;
-    default: e = launch_tc2<256>(pl->tmA, pl->tmB, pl->tmO, pl->tmR, pl->tmA2, pl->tmB2, pl->args, pl->grid, pl->smem, s); break;
+    case 16: e = launch_tc2<16>(pl->tmA, pl->tmB, pl->tmO, pl->tmR, pl->tmA2, pl->tmB2, pl->tmA3, pl->args, pl->grid, pl->smem, s); break;
+    case 64: e = launch_tc2<64>(pl->tmA, pl->tmB, pl->tmO, pl->tmR, pl->tmA2, pl->tmB2, pl->tmA3, pl->args, pl->grid, pl->smem, s); break;
+    case 128: e = launch_tc2<128>(pl->tmA, pl->tmB, pl->tmO, pl->tmR, pl->tmA2, pl->tmB2, pl->tmA3, pl->args, pl->grid, pl->smem, s); break;
+    default: e = launch_tc2<256>(pl->tmA, pl->tmB, pl->tmO, pl->tmR, pl->tmA2, pl->tmB2, pl->tmA3, pl->args, pl->grid, pl->smem, s); break;
   }
   if (e != cudaSuccess) {
     (void)cudaGetLastError();

@@ -92,6 +92,16 @@ class Packed:
             self.stamp = st
 
 
+class CoefSpec:
+    """GroupNorm coefficients not yet computed: the per-channel statistics and affine / AdaGN operands a later gn_apply
+    needs (Plan.gn_coef in fused-statistics mode)."""
+    __slots__ = ("stats1", "C1", "stats2", "C2", "gamma", "beta", "B", "HW", "emb", "emb_ld", "embz", "embz_ld")
+
+    def __init__(self, stats1, C1, stats2, C2, gamma, beta, B, HW, emb, emb_ld, embz, embz_ld):
+        self.stats1, self.C1, self.stats2, self.C2, self.gamma, self.beta = stats1, C1, stats2, C2, gamma, beta
+        self.B, self.HW, self.emb, self.emb_ld, self.embz, self.embz_ld = B, HW, emb, emb_ld, embz, embz_ld
+
+
 class Plan:
     def __init__(self, device: torch.device, precision: Optional[str] = None, check_device: bool = True):
         if check_device:  # False only in CPU unit tests of the recording / buffer-assignment logic (a plan cannot run there)
@@ -104,6 +114,7 @@ class Plan:
         # residual stream (block outputs / skip tensors) kept in bf16 instead of fp32: halves the HBM bytes of the
         # bandwidth-bound top-level layers.  "bf16" precision + v2 kernel only.
         self.stream_bf16 = self.tc and self.v2 and os.environ.get("PDAE_STREAM_BF16", "1") == "1"
+        self.fuse_coef = os.environ.get("PDAE_FUSE_COEF", "1") == "1"   # GN coefficients inside gn_apply (A/B aid)
         self.L = _native.lib()
         self.ops: List[Tuple[str, list]] = []
         # ops recorded inside `with P.prologue():` depend only on inputs that are constant over a sampling loop (z):
@@ -189,7 +200,10 @@ class Plan:
         idx = len(self.ops)
         self.flops.append(float(flops))
         self.op_pro.append(self._in_prologue)
+        flat = []
         for a in args:
+            flat.extend(a if isinstance(a, tuple) else (a,))
+        for a in flat:
             b = a.buf if isinstance(a, BufView) else a
             if isinstance(b, Buf) and not b.fixed:
                 if b.first is None:
@@ -310,6 +324,14 @@ class Plan:
     def _compile_tc2_skip(self, args):
         x, w, bias, x2, w2, Cin2, out, odt, stats, B, H, W, Cin, Cout, k, bn = args
         h = ctypes.c_void_p()
+        if isinstance(x2, tuple):   # skip input = virtual concat of two tensors
+            xa, Ca, xb, Cb = x2
+            rc = self.L.pdae_conv_tc2_create_skip2(ctypes.byref(h), self._resolve(x), self._resolve(w), self._resolve(bias),
+                                                   self._resolve(xa), Ca, self._resolve(xb), Cb, self._resolve(w2),
+                                                   self._resolve(out), odt, self._resolve(stats), B, H, W, Cin, Cout, k, bn)
+            _native.check(rc, "pdae_conv_tc2_create_skip2")
+            self._tc2_handles.append(h)
+            return (self.L.pdae_conv_tc2_run, [h, None], 1, "conv_tc2")
         rc = self.L.pdae_conv_tc2_create_skip(ctypes.byref(h), self._resolve(x), self._resolve(w), self._resolve(bias),
                                               self._resolve(x2), self._resolve(w2), Cin2, self._resolve(out), odt,
                                               self._resolve(stats), B, H, W, Cin, Cout, k, bn)
@@ -451,8 +473,12 @@ class Plan:
             stats = self.new_stats(B, Cout) if want_stats else None
             if skip is not None:
                 # fused 1x1 skip conv (model/module.py:268-276): extra K blocks accumulated into the same TMEM tile
-                sk_in, sw, sb, Cin2 = skip
-                assert residual is None and sk_in.dtype == torch.bfloat16
+                sk_in, sw, sb, Cin2 = skip   # sk_in: a bf16 buffer, or (buf_a, Ca, buf_b, Cb) = their channel concat
+                assert residual is None
+                if isinstance(sk_in, tuple):
+                    assert sk_in[0].dtype == sk_in[2].dtype == torch.bfloat16 and sk_in[1] + sk_in[3] == Cin2
+                else:
+                    assert sk_in.dtype == torch.bfloat16
                 w2 = self.pack((id(sw), "tc_skip"), [sw], lambda: sw.detach().reshape(Cout, Cin2).to(torch.bfloat16))
                 bsum = self.pack((id(bias), id(sb), "bias_sum"), [bias, sb], lambda: (bias.detach() + sb.detach()).float())
                 self.params.append((sb, sb.data_ptr()))
@@ -544,15 +570,14 @@ class Plan:
         """GroupNorm(32) statistics -> per-(b,c) affine coefficients.  bf16/v2 mode consumes the per-channel sums the
         conv epilogues accumulated (computing missing ones); fp32 mode keeps the fp64 two-kernel path."""
         C = C1 + C2
-        ab = self.new((B, 2, C), torch.float32, "gn_ab")
         if self.fused_stats:
             if stats1 is None:
                 stats1 = self.ch_stats(src1, C1, B=B, HW=HW)
             if src2 is not None and stats2 is None:
                 stats2 = self.ch_stats(src2, C2, B=B, HW=HW)
-            self.call("gn_coef_ch", stats1, C1, stats2, C2, self.param(gamma), self.param(beta), B, HW, ctypes.c_float(1e-5),
-                      emb, emb_ld, embz, embz_ld, ab, _STREAM)
-            return ab
+            # deferred: gn_apply folds the coefficient computation into its own launch when its kernel allows it
+            return CoefSpec(stats1, C1, stats2, C2, self.param(gamma), self.param(beta), B, HW, emb, emb_ld, embz, embz_ld)
+        ab = self.new((B, 2, C), torch.float32, "gn_ab")
         sums = self.new((B, 32, 2), torch.float64, "gn_sums")
         self.last_sums = sums
         self.call("gn_stats", src1, C1, src2, C2, B, HW, sums, _STREAM)
@@ -566,6 +591,18 @@ class Plan:
         Ho, Wo = (2 * H, 2 * W) if resample == RESAMPLE_UP2 else ((H // 2, W // 2) if resample == RESAMPLE_DOWN2 else (H, W))
         act = self.new((B, Ho, Wo, C), act_dtype, "act")
         raw = self.new((B, Ho, Wo, C), raw_dtype, "raw") if raw_dtype is not None else None
+        if isinstance(ab, CoefSpec):
+            c = ab
+            if (self.fuse_coef and resample == RESAMPLE_NONE and act_dtype == torch.bfloat16 and C1 % 8 == 0 and C2 % 8 == 0
+                    and 64 <= C <= 2048):
+                self.call("gn_norm_apply", src1, _DT[src1.dtype], C1, c.stats1, src2,
+                          _DT[src2.dtype] if src2 is not None else PDAE_F32, C2, c.stats2, c.gamma, c.beta, ctypes.c_float(1e-5),
+                          c.emb, c.emb_ld, c.embz, c.embz_ld, int(silu), B, H, W, act, raw,
+                          _DT[raw_dtype] if raw_dtype is not None else PDAE_F32, _STREAM)
+                return act, raw
+            ab = self.new((B, 2, C), torch.float32, "gn_ab")
+            self.call("gn_coef_ch", c.stats1, c.C1, c.stats2, c.C2, c.gamma, c.beta, c.B, c.HW, ctypes.c_float(1e-5),
+                      c.emb, c.emb_ld, c.embz, c.embz_ld, ab, _STREAM)
         self.call("gn_apply", src1, _DT[src1.dtype], C1, src2, _DT[src2.dtype] if src2 is not None else PDAE_F32, C2, ab, int(silu),
                   resample, B, H, W, act, _DT[act_dtype], raw, _DT[raw_dtype] if raw_dtype is not None else PDAE_F32, _STREAM)
         return act, raw

@@ -261,8 +261,15 @@ class _ResBase(PlannedModule):
         out_dt = P.stream_dtype if (tc1 and tc2 and (ident or tcs)) else torch.float32
         # raw (un-normalised) copy of the possibly concatenated / resampled input for the skip path
         plain = not self.updown and x.b2 is None        # x.b1 itself is the skip-path input
+        # a concatenated input whose 1x1 skip conv is folded into conv2 is read from its two source tensors directly
+        # (two TMA maps): the concat is never materialised
+        cat_skip = (not ident and not self.updown and x.b2 is not None and P.v2 and tcs and tc2
+                    and self.skip_connection.kernel_size[0] == 1 and x.b1.dtype == torch.bfloat16
+                    and x.b2.dtype == torch.bfloat16 and x.C1 % 64 == 0 and x.C2 % 64 == 0 and tape is None)
         raw_dtype = None
-        if ident:
+        if cat_skip:
+            pass
+        elif ident:
             if not (plain and x.b1.dtype == out_dt):
                 raw_dtype = out_dt                       # identity residual must have the output's dtype
         else:
@@ -297,8 +304,8 @@ class _ResBase(PlannedModule):
             resid = raw if raw is not None else x.b1
         else:
             sk = self.skip_connection
-            sk_in = raw if raw is not None else x.b1
-            if P.v2 and tcs and tc2 and sk.kernel_size[0] == 1 and sk_in.dtype == torch.bfloat16:
+            sk_in = (x.b1, x.C1, x.b2, x.C2) if cat_skip else (raw if raw is not None else x.b1)
+            if cat_skip or (P.v2 and tcs and tc2 and sk.kernel_size[0] == 1 and sk_in.dtype == torch.bfloat16):
                 resid, fused_skip = None, (sk_in, sk.weight, sk.bias, C)   # folded into conv2 as extra K blocks
             else:
                 resid = P.new((B, H2, W2, Co), out_dt, "res_skip")
