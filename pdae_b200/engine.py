@@ -114,7 +114,7 @@ class Plan:
         # residual stream (block outputs / skip tensors) kept in bf16 instead of fp32: halves the HBM bytes of the
         # bandwidth-bound top-level layers.  "bf16" precision + v2 kernel only.
         self.stream_bf16 = self.tc and self.v2 and os.environ.get("PDAE_STREAM_BF16", "1") == "1"
-        self.fuse_coef = os.environ.get("PDAE_FUSE_COEF", "1") == "1"   # GN coefficients inside gn_apply (A/B aid)
+        self.fuse_coef = os.environ.get("PDAE_FUSE_COEF", "0") == "1"   # GN coefficients inside gn_apply: measured 0.15 ms/step SLOWER under graph replay (profiles/README.md) -> off
         self.L = _native.lib()
         self.ops: List[Tuple[str, list]] = []
         # ops recorded inside `with P.prologue():` depend only on inputs that are constant over a sampling loop (z):

@@ -12,6 +12,7 @@ against the reference keep working; activations inside a plan are NHWC.
 from __future__ import annotations
 
 import ctypes
+import os
 import math
 from typing import Dict, List, Optional, Tuple
 
@@ -265,7 +266,8 @@ class _ResBase(PlannedModule):
         # (two TMA maps): the concat is never materialised
         cat_skip = (not ident and not self.updown and x.b2 is not None and P.v2 and tcs and tc2
                     and self.skip_connection.kernel_size[0] == 1 and x.b1.dtype == torch.bfloat16
-                    and x.b2.dtype == torch.bfloat16 and x.C1 % 64 == 0 and x.C2 % 64 == 0 and tape is None)
+                    and x.b2.dtype == torch.bfloat16 and x.C1 % 64 == 0 and x.C2 % 64 == 0 and tape is None
+                    and os.environ.get("PDAE_CAT_SKIP", "1") == "1")
         raw_dtype = None
         if cat_skip:
             pass
