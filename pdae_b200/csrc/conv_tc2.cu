@@ -408,6 +408,25 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               }
               atomicAdd(&st_acc[0][c * CW + col], s);
               atomicAdd(&st_acc[1][c * CW + col], qq);
+            } else if (ppi % CW == 0) {
+              // several whole images per tile and this thread's CW rows lie inside ONE image
+              float s = 0.f, qq = 0.f;
+#pragma unroll 8
+              for (int rr = r0; rr < r0 + CW; ++rr) {
+                const float x = ldv(rr);
+                s += x;
+                qq = fmaf(x, x, qq);
+              }
+              const int cur = r0 / ppi;
+              if (b0 + cur < p.B) {
+                float* dst = p.ch_stats + ((long long)(b0 + cur) * p.Cout + n0 + c * CW + col) * 2;
+                if (ppi == CW) {   // the only contributor to this (image, channel): plain store, no atomic
+                  *reinterpret_cast<float2*>(dst) = make_float2(s, qq);
+                } else {
+                  atomicAdd(dst, s);
+                  atomicAdd(dst + 1, qq);
+                }
+              }
             } else {
               float s = 0.f, qq = 0.f;
               int cur = r0 / ppi, nxt = (cur + 1) * ppi;  // `nxt` = first row of the next image
