@@ -259,6 +259,25 @@ __device__ __forceinline__ void apply8_loop(const T* __restrict__ p, int Cs, __n
   }
 }
 
+// Source selection for a virtual concat: with both sources of one type the (pointer, pitch) pair is SELECTED, so a warp
+// whose lanes straddle the two sources runs the pixel loop once (a branch would run it twice with half the lanes idle).
+template <typename TSrc, typename TSrc2, typename TRaw>
+__device__ __forceinline__ void apply8_dispatch(const TSrc* __restrict__ s1, int C1, const TSrc2* __restrict__ s2, int C2, int b,
+                                                int c, __nv_bfloat16* __restrict__ po, TRaw* __restrict__ pr, int C, int pix0,
+                                                int stride, int HW, float4 a0, float4 a1, float4 b0, float4 b1, int silu) {
+  if constexpr (sizeof(TSrc) == sizeof(TSrc2)) {
+    const bool first = c < C1;
+    const TSrc* p = first ? s1 + (long long)b * HW * C1 + c
+                          : reinterpret_cast<const TSrc*>(s2) + (long long)b * HW * C2 + (c - C1);
+    apply8_loop<TSrc, TRaw, 4>(p, first ? C1 : C2, po, pr, C, pix0, stride, HW, a0, a1, b0, b1, silu);
+  } else {
+    if (c < C1)
+      apply8_loop<TSrc, TRaw, 4>(s1 + (long long)b * HW * C1 + c, C1, po, pr, C, pix0, stride, HW, a0, a1, b0, b1, silu);
+    else
+      apply8_loop<TSrc2, TRaw, 4>(s2 + (long long)b * HW * C2 + (c - C1), C2, po, pr, C, pix0, stride, HW, a0, a1, b0, b1, silu);
+  }
+}
+
 template <typename TSrc, typename TSrc2, typename TRaw>
 __global__ void __launch_bounds__(256) gn_apply8_kernel(const TSrc* __restrict__ s1, int C1, const TSrc2* __restrict__ s2,
                                                         int C2, const float* __restrict__ ab, int silu, int HW,
@@ -279,10 +298,7 @@ __global__ void __launch_bounds__(256) gn_apply8_kernel(const TSrc* __restrict__
   __nv_bfloat16* po = out_act + (long long)b * HW * C + c;
   TRaw* pr = out_raw ? out_raw + (long long)b * HW * C + c : nullptr;
   const int stride = gridDim.x * ppc, pix0 = blockIdx.x * ppc + prow;
-  if (c < C1)
-    apply8_loop<TSrc, TRaw, 4>(s1 + (long long)b * HW * C1 + c, C1, po, pr, C, pix0, stride, HW, a0, a1, b0, b1, silu);
-  else
-    apply8_loop<TSrc2, TRaw, 4>(s2 + (long long)b * HW * C2 + (c - C1), C2, po, pr, C, pix0, stride, HW, a0, a1, b0, b1, silu);
+  apply8_dispatch<TSrc, TSrc2, TRaw>(s1, C1, s2, C2, b, c, po, pr, C, pix0, stride, HW, a0, a1, b0, b1, silu);
 }
 
 // GroupNorm coefficients computed in the CTA prologue from the per-channel (sum, sum^2) the conv epilogues accumulated:
@@ -353,10 +369,7 @@ __global__ void __launch_bounds__(256) gn_norm_apply8_kernel(const TSrc* __restr
   __nv_bfloat16* po = out_act + (long long)b * HW * C + c;
   TRaw* pr = out_raw ? out_raw + (long long)b * HW * C + c : nullptr;
   const int stride = gridDim.x * ppc, pix0 = blockIdx.x * ppc + prow;
-  if (c < C1)
-    apply8_loop<TSrc, TRaw, 4>(s1 + (long long)b * HW * C1 + c, C1, po, pr, C, pix0, stride, HW, a0, a1, b0, b1, silu);
-  else
-    apply8_loop<TSrc2, TRaw, 4>(s2 + (long long)b * HW * C2 + (c - C1), C2, po, pr, C, pix0, stride, HW, a0, a1, b0, b1, silu);
+  apply8_dispatch<TSrc, TSrc2, TRaw>(s1, C1, s2, C2, b, c, po, pr, C, pix0, stride, HW, a0, a1, b0, b1, silu);
 }
 
 template <typename TSrc, typename TSrc2, typename TAct, typename TRaw, int RS>
