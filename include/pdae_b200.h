@@ -173,6 +173,14 @@ int pdae_dsilu_mul(const float* g, const float* x, float* out, int64_t n, pdae_s
 int pdae_add_inplace(float* a, const float* b, int64_t n, pdae_stream_t stream);
 /* inverted dropout (nn.Dropout in out_layers, module.py:259): a *= mask * scale with a caller-drawn 0/1 mask.            */
 int pdae_mul_mask(float* a, const float* mask, float scale, int64_t n, pdae_stream_t stream);
+/* MLPLNAct backward (model/mlp_skip_net.py:123-141; latent DPM training, gaussian_diffusion.py:373-398): given
+ * dy = grad of y = SiLU(LN(h*(1+cond))) (read with leading dimension dy_ld) -> dh, dcond [B][N] and the LayerNorm
+ * parameter gradients accumulated into d_ln_w / d_ln_b (zero them first).  ln_w == NULL: no LayerNorm.                  */
+int pdae_mlp_mod_ln_act_bwd(const float* h, const float* cond, const float* ln_w, const float* ln_b, float eps, int silu,
+                            const float* dy, int dy_ld, float* dh, float* dcond, float* d_ln_w, float* d_ln_b, int B, int N,
+                            pdae_stream_t stream);
+/* a[b][0..N) *= mask[b][0..N) * scale on a row-major [B][ld] matrix (dropout, mlp_skip_net.py:140, on the concat buffer). */
+int pdae_mul_mask_cols(float* a, int ld, const float* mask, float scale, int B, int N, pdae_stream_t stream);
 int pdae_nchw_to_nhwc(const float* src, float* dst, int B, int C, int HW, pdae_stream_t stream);
 int pdae_gemm_batched_simt(const float* A, int64_t lda, int64_t a_bs, int64_t a_hs, int transA, const float* Bm, int64_t ldb,
                            int64_t b_bs, int64_t b_hs, int transB, float* C, int64_t ldc, int64_t c_bs, int64_t c_hs, int M,

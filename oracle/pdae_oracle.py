@@ -316,6 +316,8 @@ def mlp_skip_net_forward(sd: SD, cfg: dict, x: torch.Tensor, t: torch.Tensor) ->
             if cfg["use_norm"]:
                 h = F.layer_norm(h, (h.shape[1],), sd[p + ".norm.weight"], sd[p + ".norm.bias"], eps=1e-5)
             h = F.silu(h)
+            if DROPOUT_MASKS is not None and p in DROPOUT_MASKS:   # MLPLNAct dropout after the activation (:139-140)
+                h = h * DROPOUT_MASKS[p] / (1.0 - DROPOUT_MASKS["p"])
     return h
 
 
@@ -497,6 +499,15 @@ class DiffusionOracle:
     def regular_loss(self, denoise_fn, x_0, t, noise, condition=None):
         """regular_train_one_batch (gaussian_diffusion.py:199-211) with (t, noise) given."""
         return torch.mean((noise - denoise_fn(self.q_sample(x_0, t, noise), t, condition)) ** 2)
+
+    def latent_diffusion_loss(self, latent_fn, z_0, t, noise):
+        """latent_diffusion_train_one_batch (gaussian_diffusion.py:373-398) with (t, noise) given and z_0 already
+        normalised: constant beta = 0.008 schedule (:336-357), L1 loss."""
+        ac = np.cumprod(1.0 - np.array([0.008] * 1000))
+        c1 = torch.tensor(np.sqrt(ac), dtype=torch.float32)
+        c2 = torch.tensor(np.sqrt(1.0 - ac), dtype=torch.float32)
+        z_t = c1[t].reshape(-1, 1) * z_0 + c2[t].reshape(-1, 1) * noise
+        return (noise - latent_fn(z_t, t)).abs().mean()
 
     def latent_ddim_sample(self, style, latent_fn, z_T):
         """latent_diffusion_sample's latent loop (gaussian_diffusion.py:400-411, ddim.py:200-207):

@@ -406,6 +406,117 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __rest
   dst[((long long)b * HW + p) * C + c] = src[i];
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// MLPLNAct backward (model/mlp_skip_net.py:123-141):  v = h*(1+c);  u = (v-mean)*rstd;  y0 = u*lw+lb;  y = SiLU(y0)
+// one CTA per row; mean / rstd recomputed like the forward kernel.  dy is read with leading dimension dy_ld (the
+// gradient of the skip-concat buffer's left columns).  dlw / dlb accumulate over rows with atomics (zero them first).
+__global__ void __launch_bounds__(256) mlp_mod_ln_act_bwd_kernel(const float* __restrict__ h, const float* __restrict__ cond,
+                                                                 const float* __restrict__ lw, const float* __restrict__ lb,
+                                                                 float eps, int silu, const float* __restrict__ dy, int dy_ld,
+                                                                 float* __restrict__ dh, float* __restrict__ dcond,
+                                                                 float* __restrict__ dlw, float* __restrict__ dlb, int N) {
+  __shared__ float red[2][8];
+  __shared__ float bc[2];
+  const int b = blockIdx.x;
+  const float* hr = h + (long long)b * N;
+  const float* cr = cond ? cond + (long long)b * N : nullptr;
+  const float* gr = dy + (long long)b * dy_ld;
+  auto block_sum2 = [&](float a, float c2, float& oa, float& oc) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = c2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double da = 0.0, dc = 0.0;
+      for (int w = 0; w < 8; ++w) { da += red[0][w]; dc += red[1][w]; }
+      bc[0] = (float)da; bc[1] = (float)dc;
+    }
+    __syncthreads();
+    oa = bc[0]; oc = bc[1];
+  };
+  float mean = 0.f, rstd = 1.f;
+  if (lw) {
+    float s = 0.f, q = 0.f;
+    for (int j = threadIdx.x; j < N; j += 256) {
+      float v = hr[j];
+      if (cr) v = v * (1.0f + cr[j]);
+      s += v;
+      q = fmaf(v, v, q);
+    }
+    __syncthreads();
+    if (true) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+      }
+      if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = q; }
+      __syncthreads();
+      double ds = 0.0, dq = 0.0;
+      for (int w = 0; w < 8; ++w) { ds += red[0][w]; dq += red[1][w]; }
+      const double m = ds / N;
+      double var = dq / N - m * m;
+      var = var < 0.0 ? 0.0 : var;
+      mean = (float)m;
+      rstd = (float)(1.0 / sqrt(var + (double)eps));
+    }
+  }
+  // pass 1: du = dy * dSiLU(y0) * lw ; sums of du and du*u
+  float s1 = 0.f, s2 = 0.f;
+  for (int j = threadIdx.x; j < N; j += 256) {
+    float v = hr[j];
+    if (cr) v = v * (1.0f + cr[j]);
+    const float u = lw ? (v - mean) * rstd : v;
+    const float y0 = lw ? u * lw[j] + lb[j] : u;
+    float g = gr[j];
+    if (silu) {
+      const float sg = 1.0f / (1.0f + expf(-y0));
+      g *= sg * (1.0f + y0 * (1.0f - sg));
+    }
+    if (lw) {
+      if (dlw) atomicAdd(dlw + j, g * u);
+      if (dlb) atomicAdd(dlb + j, g);
+      const float du = g * lw[j];
+      s1 += du;
+      s2 = fmaf(du, u, s2);
+    }
+  }
+  float m1 = 0.f, m2 = 0.f;
+  if (lw) {
+    block_sum2(s1, s2, m1, m2);
+    m1 /= N; m2 /= N;
+  }
+  for (int j = threadIdx.x; j < N; j += 256) {
+    const float hv = hr[j];
+    const float cv = cr ? cr[j] : 0.f;
+    const float v = hv * (1.0f + cv);
+    const float u = lw ? (v - mean) * rstd : v;
+    const float y0 = lw ? u * lw[j] + lb[j] : u;
+    float g = gr[j];
+    if (silu) {
+      const float sg = 1.0f / (1.0f + expf(-y0));
+      g *= sg * (1.0f + y0 * (1.0f - sg));
+    }
+    float dv = g;
+    if (lw) dv = rstd * (g * lw[j] - m1 - u * m2);
+    dh[(long long)b * N + j] = dv * (1.0f + cv);
+    if (dcond) dcond[(long long)b * N + j] = dv * hv;
+  }
+}
+
+// a[b][j] *= mask[b][j] * scale for the first N columns of a row-major [B][ld] matrix (dropout on a concat buffer)
+__global__ void mul_mask_cols_kernel(float* __restrict__ a, int ld, const float* __restrict__ mask, float scale, int B, int N) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * N) return;
+  const int b = (int)(i / N), j = (int)(i % N);
+  a[(long long)b * ld + j] *= mask[i] * scale;
+}
+
 }  // namespace pdae
 
 using namespace pdae;
@@ -539,5 +650,24 @@ extern "C" int pdae_nchw_to_nhwc(const float* src, float* dst, int B, int C, int
   PDAE_REQUIRE(src && dst, "nchw_to_nhwc: null pointer");
   nchw_to_nhwc_kernel<<<cdiv((long long)B * C * HW, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, B, C, HW);
   PDAE_LAUNCH_CHECK("nchw_to_nhwc_kernel");
+  return PDAE_OK;
+}
+
+extern "C" int pdae_mlp_mod_ln_act_bwd(const float* h, const float* cond, const float* ln_w, const float* ln_b, float eps, int silu,
+                                       const float* dy, int dy_ld, float* dh, float* dcond, float* d_ln_w, float* d_ln_b, int B,
+                                       int N, pdae_stream_t stream) {
+  PDAE_REQUIRE(h && dy && dh && B > 0 && N > 0 && dy_ld >= N, "mlp_mod_ln_act_bwd: bad args");
+  PDAE_REQUIRE(!ln_w || ln_b, "mlp_mod_ln_act_bwd: LayerNorm weight without bias");
+  PDAE_REQUIRE(!dcond || cond, "mlp_mod_ln_act_bwd: dcond without cond");
+  mlp_mod_ln_act_bwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(h, cond, ln_w, ln_b, eps, silu, dy, dy_ld, dh, dcond, d_ln_w,
+                                                                 d_ln_b, N);
+  PDAE_LAUNCH_CHECK("mlp_mod_ln_act_bwd_kernel");
+  return PDAE_OK;
+}
+
+extern "C" int pdae_mul_mask_cols(float* a, int ld, const float* mask, float scale, int B, int N, pdae_stream_t stream) {
+  PDAE_REQUIRE(a && mask && B > 0 && N > 0 && ld >= N, "mul_mask_cols: bad args");
+  mul_mask_cols_kernel<<<cdiv((long long)B * N, 256), 256, 0, (cudaStream_t)stream>>>(a, ld, mask, scale, B, N);
+  PDAE_LAUNCH_CHECK("mul_mask_cols_kernel");
   return PDAE_OK;
 }

@@ -72,7 +72,8 @@ class MLPSkipNet(PlannedModule):
         n = len(self.layers)
         for i, layer in enumerate(self.layers):
             if layer.training and isinstance(layer.dropout, nn.Dropout):
-                raise NotImplementedError("pdae_b200: MLPSkipNet dropout in train mode needs the training kernels")
+                raise NotImplementedError("pdae_b200: MLPSkipNet dropout is only active on the training path (grad enabled); "
+                                          "call .eval() for sampling")
             last = i == n - 1
             co = layer.linear.weight.shape[0]
             h = P.new((B, co), torch.float32, "mlp_h")
@@ -93,6 +94,12 @@ class MLPSkipNet(PlannedModule):
 
     def forward(self, x, t, condition=None):
         """x = z_t [N, input_channel], t int64 [N] -> predicted noise [N, input_channel]."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # latent DPM training step (diffusion/gaussian_diffusion.py:373-398): hand-written backward for every parameter
+            if x.requires_grad:
+                raise NotImplementedError("pdae_b200: gradients w.r.t. z_t are not provided (the reference detaches z_0)")
+            from ..train import mlp_train_forward
+            return mlp_train_forward(self, x.contiguous(), t)
         self._check_no_grad(x)
         B = x.shape[0]
         plan, (x_in, t_in, out) = self._get_plan(("mlp", B, self.training), lambda P: self._build(P, B))

@@ -597,3 +597,138 @@ def encoder_train_forward(enc, x):
         tr = EncoderTrainer(enc, B, H, W)
         cache[(B, H, W)] = tr
     return _EncoderFn.apply(tr, x, *tr.params)
+
+
+# ======================================================================================================================
+# MLPSkipNet (latent DPM training, diffusion/gaussian_diffusion.py:373-398)
+# ======================================================================================================================
+class MLPTrainer:
+    """Forward plan keeping every layer's (input, pre-activation, modulation) + backward plan for all parameters of the
+    MLPSkipNet; no gradient w.r.t. z_t (the reference's z_t is built from detached latents)."""
+
+    def __init__(self, net, B: int):
+        self.net = net
+        dev = net._device()
+        D, Wd, Te = net.input_channel, net.model_channel, net.time_emb_channel
+        from .model.module import timestep_freqs
+        P = Plan(dev, "fp32")
+        P.keep_all = True
+        self.x_in = P.new((B, D), torch.float32, "z_t")
+        self.t_in = P.new((B,), torch.int64, "t")
+        temb = P.new((B, Te), torch.float32, "temb")
+        P.call("timestep_embedding", self.t_in, B, Te, P.fixed(timestep_freqs(Te, dev)), temb, _STREAM)
+        c0 = P.new((B, D), torch.float32, "cond_h")
+        P.linear(temb, net.time_embed[0].weight, net.time_embed[0].bias, c0, B=B, Cin=Te, Cout=D)
+        cond = P.new((B, D), torch.float32, "cond")
+        P.linear(c0, net.time_embed[2].weight, net.time_embed[2].bias, cond, B=B, Cin=D, Cout=D, a_silu=True)
+        scond = P.new((B, D), torch.float32, "silu_cond")    # SiLU(cond): the input of every linear_emb
+        P.call("mlp_mod_ln_act", cond, None, None, None, F32(1e-5), 1, scond, D, B, D, _STREAM)
+        cur, cin = self.x_in, D
+        n = len(net.layers)
+        tape = []
+        for i, layer in enumerate(net.layers):
+            last = i == n - 1
+            co = layer.linear.weight.shape[0]
+            h = P.new((B, co), torch.float32, "mlp_h")
+            P.linear(cur, layer.linear.weight, layer.linear.bias, h, B=B, Cin=cin, Cout=co)
+            if last:
+                self.out = h
+                tape.append(dict(layer=layer, x=cur, cin=cin, co=co, last=True))
+                break
+            cnd = P.new((B, co), torch.float32, "mlp_cond")
+            P.linear(scond, layer.linear_emb.weight, layer.linear_emb.bias, cnd, B=B, Cin=D, Cout=co)
+            dst = P.new((B, Wd + D), torch.float32, f"cat{i}")   # one concat buffer per layer: the backward reads them all
+            P.call("copy_cols", self.x_in, dst, Wd + D, Wd, B, D, _STREAM)
+            ln = layer.norm if isinstance(layer.norm, nn.LayerNorm) else None
+            P.call("mlp_mod_ln_act", h, cnd, P.param(ln.weight) if ln else None, P.param(ln.bias) if ln else None,
+                   F32(ln.eps if ln else 1e-5), 1, dst, Wd + D, B, co, _STREAM)
+            mask = None
+            pdrop = float(layer.dropout.p) if isinstance(layer.dropout, nn.Dropout) else 0.0
+            if net.training and pdrop > 0:
+                mask = P.new((B, co), torch.float32, "drop_mask")
+                P.dropout_masks.append((layer, mask, pdrop))
+                P.call("mul_mask_cols", dst, Wd + D, mask, F32(1.0 / (1.0 - pdrop)), B, co, _STREAM)
+            tape.append(dict(layer=layer, x=cur, cin=cin, co=co, last=False, h=h, cnd=cnd, ln=ln, mask=mask, pdrop=pdrop))
+            cur, cin = dst, Wd + D
+        P.finalize()
+        self.fwd = P
+
+        BP = Plan(dev, "fp32")
+        self.sink = GradSink()
+        bw = Backward(BP, self.sink)
+        self.d_out = BP.new((B, D), torch.float32, "d_eps")
+        self.d_out.keep = True
+        d_scond = BP.new_zeroed(B * D)          # sum over layers of d SiLU(cond)
+        dy, dy_ld = self.d_out, D
+        for sv in reversed(tape):
+            layer, co, cin = sv["layer"], sv["co"], sv["cin"]
+            if sv["last"]:
+                dh = dy
+            else:
+                if sv["mask"] is not None:
+                    BP.call("mul_mask_cols", dy, dy_ld, bw.fx(sv["mask"]), F32(1.0 / (1.0 - sv["pdrop"])), B, co, _STREAM)
+                ln = sv["ln"]
+                dlw = dlb = None
+                if ln is not None:
+                    dlw, dlb = BP.new_zeroed(co), BP.new_zeroed(co)
+                    self.sink.add(ln.weight, dlw, co, lambda t: t)
+                    self.sink.add(ln.bias, dlb, co, lambda t: t)
+                dh = BP.new((B, co), torch.float32, "d_mlp_h")
+                dcnd = BP.new((B, co), torch.float32, "d_mlp_cond")
+                BP.call("mlp_mod_ln_act_bwd", bw.fx(sv["h"]), bw.fx(sv["cnd"]), BP.param(ln.weight) if ln else None,
+                        BP.param(ln.bias) if ln else None, F32(ln.eps if ln else 1e-5), 1, dy, dy_ld, dh, dcnd, dlw, dlb, B, co,
+                        _STREAM)
+                g = bw.conv(scond, dcnd, layer.linear_emb.weight, layer.linear_emb.bias, B=B, H=1, W=1, Cin=D, Cout=co, k=1)
+                BP.call("add_inplace", d_scond, g, ctypes.c_int64(B * D), _STREAM)
+            first = sv["x"] is self.x_in
+            dx = bw.conv(sv["x"], dh, layer.linear.weight, layer.linear.bias, B=B, H=1, W=1, Cin=cin, Cout=co, k=1,
+                         need_dx=not first)
+            if not first:
+                dy, dy_ld = dx, cin                       # left Wd columns = grad of the previous layer's activation
+        d_cond = BP.new((B, D), torch.float32, "d_cond")
+        BP.call("dsilu_mul", d_scond, bw.fx(cond), d_cond, ctypes.c_int64(B * D), _STREAM)
+        g = bw.conv(c0, d_cond, net.time_embed[2].weight, net.time_embed[2].bias, B=B, H=1, W=1, Cin=D, Cout=D, k=1, a_silu=True)
+        d_c0 = BP.new((B, D), torch.float32, "d_c0")
+        BP.call("dsilu_mul", g, bw.fx(c0), d_c0, ctypes.c_int64(B * D), _STREAM)
+        bw.conv(temb, d_c0, net.time_embed[0].weight, net.time_embed[0].bias, B=B, H=1, W=1, Cin=Te, Cout=D, k=1, need_dx=False)
+        BP.finalize()
+        self.bwd = BP
+        self.params = [p for p in net.parameters() if p.requires_grad]
+
+    def forward(self, x, t):
+        self.x_in.tensor.copy_(x)
+        self.t_in.tensor.copy_(t)
+        draw_dropout_masks(self.fwd)
+        self.fwd.run()
+        return self.out.tensor.clone()
+
+    def backward(self, d_out):
+        self.d_out.tensor.copy_(d_out)
+        self.bwd.run()
+        grads = self.sink.collect()
+        return [grads.get(id(p)) for p in self.params]
+
+
+class _MLPFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, trainer: MLPTrainer, x, t, *params):
+        ctx.trainer = trainer
+        with torch.no_grad():
+            return trainer.forward(x, t)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        with torch.no_grad():
+            pg = ctx.trainer.backward(d_out.contiguous())
+        return (None, None, None, *pg)
+
+
+def mlp_train_forward(net, x, t):
+    B = x.shape[0]
+    cache = net.__dict__.setdefault("_train_cache", {})
+    key = (B, net.training)
+    tr = cache.get(key)
+    if tr is None or tr.fwd.stale() or tr.bwd.stale():
+        tr = MLPTrainer(net, B)
+        cache[key] = tr
+    return _MLPFn.apply(tr, x, t, *tr.params)

@@ -192,7 +192,33 @@ def training_cases():
     t = torch.randint(0, 1000, (2,), dtype=torch.long)
     noise = torch.randn_like(x0)
     save("train_regular", dict(kind="train_regular", cfg=TINY_UNET, size=16), t=t, noise=noise, loss=loss.detach())
+    latent_training_case(gd)
     torch.set_grad_enabled(False)
+
+
+def latent_training_case(gd):
+    """latent_diffusion_train_one_batch (gaussian_diffusion.py:373-398): frozen encoder, trainable MLPSkipNet, L1 loss."""
+    cfg = dict(TINY_MLP, input_channel=512, model_channel=256, num_layers=5)
+    mlp = fill_module_(MLPSkipNet(**cfg), seed=9)
+    enc = fill_module_(CELEBA64Encoder(latent_dim=512), seed=7).requires_grad_(False).eval()
+    x0 = synth_images(3, 3, 64, 33)
+    mean, std = synth_normal((1, 512), 34) * 0.1, synth_normal((1, 512), 35).abs() + 0.5
+    torch.manual_seed(779)
+    loss = gd.latent_diffusion_train_one_batch(mlp, enc, x0, mean, std)["prediction_loss"]
+    loss.backward()
+    with torch.no_grad():
+        z0 = gd.normalize(enc(x0), mean, std)
+    torch.manual_seed(779)
+    t = torch.randint(0, 1000, (3,), dtype=torch.long)
+    noise = torch.randn_like(z0)
+    keys = ("time_embed.0.weight", "time_embed.2.bias", "layers.0.linear.weight", "layers.1.linear_emb.weight",
+            "layers.2.norm.weight", "layers.3.norm.bias", "layers.4.linear.weight", "layers.4.linear.bias")
+    grads = {k: p.grad for k, p in mlp.named_parameters() if k in keys}
+    assert len(grads) == len(keys)
+    n_grad = sum(1 for p in mlp.parameters() if p.grad is not None)
+    save("train_latent", dict(kind="train_latent", cfg=cfg, n_params_with_grad=n_grad), t=t, noise=noise, z0=z0,
+         loss=loss.detach(), **{"g_" + k.replace(".", "_"): v.flatten()[:512] for k, v in grads.items()},
+         **{"n_" + k.replace(".", "_"): v.double().norm().float() for k, v in grads.items()})
 
 
 def caller_cases():

@@ -190,3 +190,88 @@ def test_training_with_dropout_matches_oracle_given_the_same_masks():
                 continue
             err = float((p.grad.cpu() - sd[k].grad).abs().max())
             assert rel_l2(p.grad, sd[k].grad) < 2e-3 or err < 2e-3 * float(sd[k].grad.abs().max()) + 2e-4 * gmax, k
+
+
+def _latent_setup(cfg, dropout=0.0):
+    from pdae_b200.model.mlp_skip_net import MLPSkipNet
+    from pdae_b200.utils.synth import fill_module_
+    c = dict(cfg["cfg"], dropout=dropout)
+    mlp = fill_module_(MLPSkipNet(**c), seed=9)
+    sd = {k: v.requires_grad_(True) for k, v in cases.sd_of(mlp).items() if ".cond_layers." not in k}
+    return c, mlp, sd
+
+
+def _latent_loss(gd, mlp, z0, t, noise):
+    lc = gd.latent_diffusion_config
+    z_t = gd.extract_coef_at_t(lc["sqrt_alphas_cumprod"], t, z0.shape) * z0 + \
+        gd.extract_coef_at_t(lc["sqrt_one_minus_alphas_cumprod"], t, z0.shape) * noise
+    return gd.p_loss(noise, mlp(z_t, t), loss_type=lc["loss_type"])
+
+
+def test_latent_training_step_matches_reference_and_oracle():
+    """latent_diffusion_train_one_batch (gaussian_diffusion.py:373-398): L1 loss and the gradient of EVERY MLPSkipNet
+    parameter from the hand-written backward vs the reference fixture and vs oracle autograd."""
+    from pdae_b200.diffusion.gaussian_diffusion import GaussianDiffusion
+    cfg, g = load_golden("train_latent")
+    c, mlp, sd = _latent_setup(cfg)
+    D = O.DiffusionOracle(cases.DIFF)
+    ref = D.latent_diffusion_loss(lambda z, t: O.mlp_skip_net_forward(sd, c, z, t), g["z0"], g["t"], g["noise"])
+    ref.backward()
+    mlp = mlp.cuda().train()
+    mlp.precision = "fp32"
+    gd = GaussianDiffusion(cases.DIFF, torch.device("cuda"))
+    loss = _latent_loss(gd, mlp, g["z0"].cuda(), g["t"].cuda(), g["noise"].cuda())
+    assert_close(loss, g["loss"], rtol=1e-5, atol=1e-7, what="latent loss vs reference fixture")
+    loss.backward()
+    named = dict(mlp.named_parameters())
+    assert sum(1 for p in named.values() if p.grad is not None) == cfg["n_params_with_grad"]
+    for k, p in named.items():
+        assert rel_l2(p.grad, sd[k].grad) < 1e-4, (k, rel_l2(p.grad, sd[k].grad))
+    for k in ("time_embed.0.weight", "layers.1.linear_emb.weight", "layers.2.norm.weight", "layers.4.linear.bias"):
+        kk = k.replace(".", "_")
+        assert_close(named[k].grad.flatten()[:512], g["g_" + kk], rtol=1e-3, atol=1e-7, what=k + " vs reference")
+    # second step through the cached plans after an in-place weight update: gradients change, stay finite
+    with torch.no_grad():
+        for p in mlp.parameters():
+            p.add_(p.grad, alpha=-1e-2)
+            p.grad = None
+    loss2 = _latent_loss(gd, mlp, g["z0"].cuda(), g["t"].cuda(), g["noise"].cuda())
+    loss2.backward()
+    assert float(loss2) < float(loss) and all(torch.isfinite(p.grad).all() for p in mlp.parameters())
+
+
+def test_latent_training_with_dropout_and_full_api_call():
+    from pdae_b200.diffusion.gaussian_diffusion import GaussianDiffusion
+    from pdae_b200.utils.synth import synth_images, synth_normal
+    cfg, g = load_golden("train_latent")
+    c, mlp, sd = _latent_setup(cfg, dropout=0.1)
+    mlp = mlp.cuda().train()
+    mlp.precision = "fp32"
+    gd = GaussianDiffusion(cases.DIFF, torch.device("cuda"))
+    torch.manual_seed(3)
+    loss = _latent_loss(gd, mlp, g["z0"].cuda(), g["t"].cuda(), g["noise"].cuda())
+    loss.backward()
+    trainer = list(mlp._train_cache.values())[0]
+    names = {id(m): n for n, m in mlp.named_modules()}
+    masks = {names[id(layer)]: mk.tensor.cpu().clone() for layer, mk, p in trainer.fwd.dropout_masks}
+    assert len(masks) == c["num_layers"] - 1 and all(0.8 < float(m.mean()) < 0.98 for m in masks.values())
+    O.DROPOUT_MASKS = dict(masks, p=0.1)
+    try:
+        ref = O.DiffusionOracle(cases.DIFF).latent_diffusion_loss(lambda z, t: O.mlp_skip_net_forward(sd, c, z, t), g["z0"], g["t"],
+                                                                  g["noise"])
+        ref.backward()
+    finally:
+        O.DROPOUT_MASKS = None
+    assert_close(loss, ref, rtol=1e-5, atol=1e-7, what="latent loss with dropout")
+    for k, p in mlp.named_parameters():
+        assert rel_l2(p.grad, sd[k].grad) < 1e-4, (k, rel_l2(p.grad, sd[k].grad))
+    # the reference-facing call: frozen encoder in eval mode, trainable latent net
+    enc, _ = cases.model_case({"kind": "encoder", "size": 64})
+    enc = enc.cuda().requires_grad_(False).eval()
+    enc.precision = "fp32"
+    for p in mlp.parameters():
+        p.grad = None
+    mean, std = (synth_normal((1, 512), 34) * 0.1).cuda(), (synth_normal((1, 512), 35).abs() + 0.5).cuda()
+    out = gd.latent_diffusion_train_one_batch(mlp, enc, synth_images(3, 3, 64, 33).cuda(), mean, std)["prediction_loss"]
+    out.backward()
+    assert torch.isfinite(out) and all(p.grad is not None and torch.isfinite(p.grad).all() for p in mlp.parameters())

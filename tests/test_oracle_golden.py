@@ -147,6 +147,25 @@ def test_training_losses():
     assert_close(loss, g["loss"], what="regular loss", rtol=1e-5, atol=1e-7)
 
 
+def test_latent_training_loss_and_grads():
+    """latent_diffusion_train_one_batch (gaussian_diffusion.py:373-398): oracle loss + autograd grads vs the reference."""
+    from pdae_b200.model.mlp_skip_net import MLPSkipNet
+    from pdae_b200.utils.synth import fill_module_
+    cfg, g = load_golden("train_latent")
+    sd = {k: v.requires_grad_(True) for k, v in cases.sd_of(fill_module_(MLPSkipNet(**cfg["cfg"]), seed=9)).items()
+          if not k.startswith("layers.") or ".cond_layers." not in k}
+    D = O.DiffusionOracle(cases.DIFF)
+    loss = D.latent_diffusion_loss(lambda z, t: O.mlp_skip_net_forward(sd, cfg["cfg"], z, t), g["z0"], g["t"], g["noise"])
+    assert_close(loss, g["loss"], what="latent loss", rtol=1e-5, atol=1e-7)
+    loss.backward()
+    assert sum(1 for v in sd.values() if v.grad is not None) == cfg["n_params_with_grad"]
+    for k in ("time_embed.0.weight", "time_embed.2.bias", "layers.0.linear.weight", "layers.1.linear_emb.weight",
+              "layers.2.norm.weight", "layers.3.norm.bias", "layers.4.linear.weight", "layers.4.linear.bias"):
+        kk = k.replace(".", "_")
+        assert_close(sd[k].grad.flatten()[:512], g["g_" + kk], what=k, rtol=1e-3, atol=1e-8)
+        assert_close(sd[k].grad.double().norm().float(), g["n_" + kk], what=k + " norm", rtol=1e-4, atol=0)
+
+
 def test_loop_sensitivity():
     """How much a 10-step shift-DDIM loop on random weights amplifies an input perturbation (justifies the stated
     bf16 loop tolerance in tests/test_gpu_diffusion.py): 1e-5 in -> between 1e-5 and 1e-2 out, no sign flips."""
