@@ -21,7 +21,7 @@ constexpr int T2_BK = 64;
 constexpr int T2_A_BYTES = T2_BM * T2_BK * 2;  // 16 KB
 constexpr int T2_STG_BYTES = 128 * 128;        // staging tile: 128 rows x 128 B
 constexpr int T2_MAX_STAGES = 8;
-constexpr int T2_THREADS = 192;
+constexpr int T2_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-5 / 6-9 = two epilogue groups (one per TMEM accumulator)
 constexpr int T2_EPI_THREADS = 128;
 
 struct ConvTc2Args {
@@ -101,7 +101,7 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a, uint64_t b, ui
 __device__ __forceinline__ void umma_commit_to(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar(int g) { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
@@ -136,15 +136,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __shared__ __align__(8) uint64_t bar_full[T2_MAX_STAGES], bar_empty[T2_MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2], bar_res[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ float st_acc[2][BN < 32 ? 32 : BN];  // per-channel (sum, sum^2) of the current (image, n-tile)
+  __shared__ float st_acc[2][2][BN < 32 ? 32 : BN];  // [epilogue group][sum | sum^2][channel] of the group's current (image, n-tile)
 
   constexpr int B_BYTES = BN * T2_BK * 2;
   constexpr int STAGE_BYTES = T2_A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
   constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   const uint32_t smem0 = (s_u32(smem_raw) + 1023u) & ~1023u;
   const int S = p.stages;
-  const uint32_t stg_out = smem0 + (uint32_t)S * STAGE_BYTES;   // 2 x 16 KB output staging
-  const uint32_t stg_res = stg_out + 2u * T2_STG_BYTES;         // 2 x 16 KB residual staging (only if has_res)
+  const uint32_t stg_out = smem0 + (uint32_t)S * STAGE_BYTES;   // 2 x 16 KB output staging   (one per epilogue group)
+  const uint32_t stg_res = stg_out + 2u * T2_STG_BYTES;         // 2 x 16 KB residual staging (one per group; only if has_res)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_k = p.taps * p.kblocks;          // main conv
   const int total_all = total_k + p.kblocks2;      // + fused 1x1 skip conv
@@ -155,8 +155,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int tile_end = min(p.tiles_total, tile_begin + per_cta);
 
   for (int j = threadIdx.x; j < (BN < 32 ? 32 : BN); j += T2_THREADS) {
-    st_acc[0][j] = 0.f;
-    st_acc[1][j] = 0.f;
+    st_acc[0][0][j] = 0.f; st_acc[0][1][j] = 0.f;
+    st_acc[1][0][j] = 0.f; st_acc[1][1][j] = 0.f;
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
@@ -251,14 +251,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else {
-    // ================= epilogue (128 threads) =================
-    const int et = threadIdx.x - 64;           // 0..127
+    // ================= epilogue: two groups of 128 threads; group g drains accumulator buffer g =================
+    // (tile tl of this CTA lands in accumulator tl & 1, so the groups work on alternate tiles concurrently: the per-tile
+    //  epilogue chain -- tcgen05.ld, residual, staging, TMA store, statistics -- has twice the throughput)
+    const int eg = (warp - 2) >> 2;            // epilogue group 0 | 1
+    const int et = threadIdx.x - 64 - eg * 128;  // 0..127 inside the group
     const bool elected = et == 0;
     const int q = warp & 3;                    // TMEM lane quadrant of this warp
     const int r = q * 32 + lane;               // accumulator row = pixel index in the tile
     const int ppi = p.th * p.tw;               // pixels per image inside a tile
-    int tl = 0, sc = 0, rc = 0;                // tile / staging-buffer / residual-buffer counters
-    for (int tile = tile_begin; tile < tile_end; ++tile, ++tl) {
+    int rc = 0;                                // residual loads consumed by this group (mbarrier phase)
+    const uint32_t obuf = stg_out + (uint32_t)eg * T2_STG_BYTES, rbuf = stg_res + (uint32_t)eg * T2_STG_BYTES;
+    const uint32_t rbar = s_u32(&bar_res[eg]);
+    for (int tile = tile_begin + eg, tl = eg; tile < tile_end; tile += 2, tl += 2) {
       const int nt = tile / p.tiles_m;
       int mt = tile - nt * p.tiles_m;
       const int tx = mt % p.tiles_x;
@@ -290,9 +295,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int CW = p.out_bf16 ? 64 : 32;  // accumulator columns per staging tile (128-byte rows)
         const int nch = BN / CW;
         if (p.has_res && elected) {            // residual chunk 0 of this tile (issued before the accumulator is needed)
-          const uint32_t rb = s_u32(&bar_res[rc & 1]);
-          mb_expect_tx(rb, T2_STG_BYTES);
-          tma_ld4(stg_res + (uint32_t)(rc & 1) * T2_STG_BYTES, &tmR, rb, n0, x0, y0, b0);
+          mb_expect_tx(rbar, T2_STG_BYTES);
+          tma_ld4(rbuf, &tmR, rbar, n0, x0, y0, b0);
         }
         for (int c = 0; c < nch; ++c) {
           float val[64];
@@ -320,13 +324,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
           if (p.has_res) {                      // the residual has the output's dtype: CW columns = one 128-byte row
-            if (elected && c + 1 < nch) {
-              const uint32_t rb = s_u32(&bar_res[(rc + 1) & 1]);
-              mb_expect_tx(rb, T2_STG_BYTES);
-              tma_ld4(stg_res + (uint32_t)((rc + 1) & 1) * T2_STG_BYTES, &tmR, rb, n0 + (c + 1) * CW, x0, y0, b0);
-            }
-            mb_wait(s_u32(&bar_res[rc & 1]), (uint32_t)((rc >> 1) & 1));
-            const uint32_t rbuf = stg_res + (uint32_t)(rc & 1) * T2_STG_BYTES;
+            mb_wait(rbar, (uint32_t)(rc & 1));
             if (p.out_bf16) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -350,10 +348,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             ++rc;
           }
-          // staging buffer (sc & 1) must no longer be read by the TMA store issued two chunks ago
-          if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          epi_bar();
-          const uint32_t obuf = stg_out + (uint32_t)(sc & 1) * T2_STG_BYTES;
+          // the group's staging buffer must no longer be read by its previous TMA store
+          if (elected) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          epi_bar(eg);                          // (also: every thread has consumed the residual buffer)
+          if (p.has_res && elected && c + 1 < nch) {   // residual for the next chunk overlaps this chunk's store + statistics
+            mb_expect_tx(rbar, T2_STG_BYTES);
+            tma_ld4(rbuf, &tmR, rbar, n0 + (c + 1) * CW, x0, y0, b0);
+          }
           if (p.out_bf16) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -375,7 +376,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                            : "memory");
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          epi_bar();
+          epi_bar(eg);
           if (elected) {
             tma_st4(&tmO, obuf, n0 + c * CW, x0, y0, b0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -406,8 +407,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 s += x;
                 qq = fmaf(x, x, qq);
               }
-              atomicAdd(&st_acc[0][c * CW + col], s);
-              atomicAdd(&st_acc[1][c * CW + col], qq);
+              atomicAdd(&st_acc[eg][0][c * CW + col], s);
+              atomicAdd(&st_acc[eg][1][c * CW + col], qq);
             } else if (ppi % CW == 0) {
               // several whole images per tile and this thread's CW rows lie inside ONE image
               float s = 0.f, qq = 0.f;
@@ -451,30 +452,29 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               }
             }
           }
-          ++sc;
         }
       }
       // accumulator buffer fully read by every epilogue thread -> hand it back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      epi_bar();
+      epi_bar(eg);
       if (elected) mb_arrive(s_u32(&bar_acc_empty[ab]));
       if constexpr (BN != 16) {
         if (p.ch_stats && p.tn == 1) {
-          bool flush = tile + 1 >= tile_end;
+          bool flush = tile + 2 >= tile_end;     // this group's next tile is tile + 2
           if (!flush) {
-            const int nt2 = (tile + 1) / p.tiles_m;
-            const int bt2 = ((tile + 1) - nt2 * p.tiles_m) / (p.tiles_x * p.tiles_y);
+            const int nt2 = (tile + 2) / p.tiles_m;
+            const int bt2 = ((tile + 2) - nt2 * p.tiles_m) / (p.tiles_x * p.tiles_y);
             flush = nt2 != nt || bt2 != bt;
           }
           if (flush) {  // (the epi_bar above ordered every thread's shared-memory atomics before these reads)
             for (int j = et; j < BN; j += 128) {
               float* dst = p.ch_stats + ((long long)b0 * p.Cout + n0 + j) * 2;
-              atomicAdd(dst, st_acc[0][j]);
-              atomicAdd(dst + 1, st_acc[1][j]);
-              st_acc[0][j] = 0.f;
-              st_acc[1][j] = 0.f;
+              atomicAdd(dst, st_acc[eg][0][j]);
+              atomicAdd(dst + 1, st_acc[eg][1][j]);
+              st_acc[eg][0][j] = 0.f;
+              st_acc[eg][1][j] = 0.f;
             }
-            epi_bar();
+            epi_bar(eg);
           }
         }
       }
@@ -519,7 +519,7 @@ static cudaError_t launch_tc2(const CUtensorMap& a, const CUtensorMap& b, const 
                               int grid, size_t smem, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);  // + static (barriers, stats) <= 227 KB
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024);  // + static (barriers, 2 x per-group stats <= 4 KB) <= 227 KB
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
