@@ -217,6 +217,13 @@ int pdae_softmax_bf16(const float* S, void* P_bf16, int64_t rows, int cols, floa
 int pdae_transpose_v(const void* qkv_bf16, void* vT_bf16, int B, int T, int C, int heads, int legacy, pdae_stream_t stream);
 void pdae_conv_tc2_destroy(pdae_conv_tc2_plan* plan);
 
+/* Stem: nn.Conv2d(input_channel, base, 3, padding=1) on the NCHW fp32 image (unet.py:62-64, shift_unet.py:64-66), written
+ * straight into the bf16 NHWC residual stream; ch_stats (optional, [B][Cout][2] fp32, zero it first) accumulates the
+ * per-channel (sum, sum^2) of the stored values for the GroupNorms that read it.  w_packed fp32 [9][Cin][Cout].
+ * Cin <= 4, Cout % 8 == 0, Cout <= 256.                                                                                */
+int pdae_stem_conv_bf16(const float* x_nchw, const float* w_packed, const float* bias, void* out_bf16_nhwc, float* ch_stats,
+                        int B, int H, int W, int Cin, int Cout, pdae_stream_t stream);
+
 /* ---- callers either side of the hot path -------------------------------------------------------------
  * Fused multi-tensor Adam + EMA: replaces torch.optim.Adam.step() as configured at
  * trainer/train_representation_learning.py:54-69 plus the per-parameter python EMA loop of :192-212

@@ -135,23 +135,33 @@ __global__ void softmax_rows_bf16_kernel(const float* __restrict__ S, __nv_bfloa
   }
 }
 
-// vT[z][c][t] = qkv[b][t][voff + h*hs + c]   (z = b*heads + h): 32x32 shared-memory tile transpose, bf16
-__global__ void transpose_v_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ vT, int T, int C3,
-                                   int ch, int heads, long long voff, long long hs) {
-  __shared__ __nv_bfloat16 tile[32][34];
+// vT[z][c][t] = qkv[b][t][voff + h*hs + c]   (z = b*heads + h): 64x64 shared-memory tile transpose, bf16 pairs:
+// every warp access is 32 x 4 B = 128 contiguous bytes on both the read (channel pairs) and the write (token pairs) side.
+// T, ch even; the per-head channel offset even (host checks).
+__global__ void __launch_bounds__(256) transpose_v_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ vT,
+                                                          int T, int C3, int ch, int heads, long long voff, long long hs) {
+  __shared__ uint32_t tile[64][33];   // [t][channel pair]
   const int z = blockIdx.z, b = z / heads, h = z % heads;
-  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int t0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const __nv_bfloat16* src = qkv + (long long)b * T * C3 + voff + h * hs;
-  for (int i = ty; i < 32; i += 8) {
-    const int t = t0 + i, c = c0 + tx;
-    tile[i][tx] = (t < T && c < ch) ? src[(long long)t * C3 + c] : __float2bfloat16(0.f);
+#pragma unroll
+  for (int i = ty; i < 64; i += 8) {
+    const int t = t0 + i, c = c0 + 2 * tx;
+    uint32_t w = 0;
+    if (t < T && c < ch) w = *reinterpret_cast<const uint32_t*>(src + (long long)t * C3 + c);
+    tile[i][tx] = w;
   }
   __syncthreads();
   __nv_bfloat16* dst = vT + (long long)z * ch * T;
-  for (int i = ty; i < 32; i += 8) {
-    const int c = c0 + i, t = t0 + tx;
-    if (c < ch && t < T) dst[(long long)c * T + t] = tile[tx][i];
+#pragma unroll
+  for (int i = ty; i < 64; i += 8) {
+    const int c = c0 + i, t = t0 + 2 * tx;
+    if (c < ch && t < T) {
+      const uint32_t w0 = tile[2 * tx][i >> 1], w1 = tile[2 * tx + 1][i >> 1];
+      const uint32_t lo = (i & 1) ? (w0 >> 16) : (w0 & 0xffffu), hi = (i & 1) ? (w1 & 0xffff0000u) : (w1 << 16);
+      *reinterpret_cast<uint32_t*>(dst + (long long)c * T + t) = lo | hi;
+    }
   }
 }
 
@@ -171,7 +181,8 @@ extern "C" int pdae_transpose_v(const void* qkv_bf16, void* vT_bf16, int B, int 
   PDAE_REQUIRE(qkv_bf16 && vT_bf16 && heads > 0 && C % heads == 0, "transpose_v: bad args");
   const int ch = C / heads;
   const long long voff = legacy ? 2LL * ch : 2LL * C, hs = legacy ? 3LL * ch : ch;
-  dim3 grid(cdiv(T, 32), cdiv(ch, 32), B * heads);
+  PDAE_REQUIRE(T % 2 == 0 && ch % 2 == 0, "transpose_v: T=%d and C/heads=%d must be even", T, ch);
+  dim3 grid(cdiv(T, 64), cdiv(ch, 64), B * heads);
   PDAE_REQUIRE(grid.z <= 65535, "transpose_v: B*heads too large");
   transpose_v_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)qkv_bf16, (__nv_bfloat16*)vT_bf16, T, 3 * C,
                                                             ch, heads, voff, hs);

@@ -223,6 +223,99 @@ __global__ void __launch_bounds__(256) conv3x3_smalln_kernel(const TIn* __restri
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Stem: 3x3 conv, pad 1, of the NCHW fp32 image (Cin <= 4) straight into the bf16 NHWC residual stream, with the
+// per-channel (sum, sum^2) of the STORED (rounded) values accumulated for the first GroupNorms (unet.py:62-64, 195).
+// HBM-bound on the output write (2 B x Cout per pixel); the image itself is tiny.  One CTA = pixels of ONE image;
+// thread -> (pixel slot, channel octet); weights [27][Cout] in shared memory.
+template <int CIN>
+__global__ void __launch_bounds__(256) stem_conv_bf16_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
+                                                             float* __restrict__ stats, int H, int W, int Cout) {
+  extern __shared__ float sm[];
+  float* ws = sm;                          // [9*CIN][Cout]
+  float* acc = sm + 9 * CIN * Cout;        // [2][Cout] per-CTA statistics
+  const int b = blockIdx.y, HW = H * W;
+  for (int i = threadIdx.x; i < 9 * CIN * Cout; i += 256) ws[i] = w[i];
+  for (int i = threadIdx.x; i < 2 * Cout; i += 256) acc[i] = 0.f;
+  __syncthreads();
+  const int L = Cout >> 3, ppc = 256 / L;  // channel octets, pixel QUADS per CTA pass
+  const int oct = threadIdx.x % L, slot = threadIdx.x / L;
+  const int c = oct * 8;
+  float bv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bv[j] = bias ? bias[c + j] : 0.f;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  const float* xb = x + (long long)b * CIN * HW;
+  const int W4 = W >> 2, nquad = H * W4;   // W % 4 == 0 (host checks): a thread owns 4 horizontally adjacent pixels,
+  if (slot < ppc) {                        // so every weight vector read from shared memory feeds 4 x 8 FMAs
+    for (int qd = blockIdx.x * ppc + slot; qd < nquad; qd += gridDim.x * ppc) {
+      const int y = qd / W4, x0 = (qd - y * W4) * 4;
+      float a[4][8];
+#pragma unroll
+      for (int pp = 0; pp < 4; ++pp)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[pp][j] = bv[j];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = y + ky - 1;
+        if (iy < 0 || iy >= H) continue;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+          const float* row = xb + (long long)ci * HW + (long long)iy * W + x0;
+          float v[6];
+          const float4 mid = __ldg(reinterpret_cast<const float4*>(row));
+          v[0] = x0 > 0 ? __ldg(row - 1) : 0.f;
+          v[1] = mid.x; v[2] = mid.y; v[3] = mid.z; v[4] = mid.w;
+          v[5] = x0 + 4 < W ? __ldg(row + 4) : 0.f;
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const float4 w0 = *reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * CIN + ci) * Cout + c);
+            const float4 w1 = *reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * CIN + ci) * Cout + c + 4);
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp) {
+              const float vv = v[pp + kx];
+              a[pp][0] = fmaf(vv, w0.x, a[pp][0]); a[pp][1] = fmaf(vv, w0.y, a[pp][1]);
+              a[pp][2] = fmaf(vv, w0.z, a[pp][2]); a[pp][3] = fmaf(vv, w0.w, a[pp][3]);
+              a[pp][4] = fmaf(vv, w1.x, a[pp][4]); a[pp][5] = fmaf(vv, w1.y, a[pp][5]);
+              a[pp][6] = fmaf(vv, w1.z, a[pp][6]); a[pp][7] = fmaf(vv, w1.w, a[pp][7]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int pp = 0; pp < 4; ++pp) {
+        __nv_bfloat162 h[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          h[j] = __floats2bfloat162_rn(a[pp][2 * j], a[pp][2 * j + 1]);
+          const float2 r = __bfloat1622float2(h[j]);
+          s1[2 * j] += r.x; s2[2 * j] = fmaf(r.x, r.x, s2[2 * j]);
+          s1[2 * j + 1] += r.y; s2[2 * j + 1] = fmaf(r.y, r.y, s2[2 * j + 1]);
+        }
+        *reinterpret_cast<uint4*>(out + ((long long)b * HW + (long long)y * W + x0 + pp) * Cout + c) = *reinterpret_cast<uint4*>(h);
+      }
+    }
+    if (stats) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(acc + c + j, s1[j]);
+        atomicAdd(acc + Cout + c + j, s2[j]);
+      }
+    }
+  }
+  if (stats) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < Cout; i += 256) {
+      atomicAdd(stats + ((long long)b * Cout + i) * 2, acc[i]);
+      atomicAdd(stats + ((long long)b * Cout + i) * 2 + 1, acc[Cout + i]);
+    }
+  }
+}
+
 }  // namespace pdae
 
 using namespace pdae;
@@ -283,5 +376,30 @@ extern "C" int pdae_conv3x3_smalln(const void* in, int in_dtype, const float* w_
     PDAE_REQUIRE(false, "conv3x3_smalln: bad dtype");
   }
   PDAE_LAUNCH_CHECK("conv3x3_smalln_kernel");
+  return PDAE_OK;
+}
+
+extern "C" int pdae_stem_conv_bf16(const float* x_nchw, const float* w_packed, const float* bias, void* out_bf16_nhwc,
+                                   float* ch_stats, int B, int H, int W, int Cin, int Cout, pdae_stream_t stream) {
+  PDAE_REQUIRE(x_nchw && w_packed && out_bf16_nhwc && B > 0 && H > 0 && W > 0, "stem_conv_bf16: bad args");
+  PDAE_REQUIRE(Cin >= 1 && Cin <= 4, "stem_conv_bf16: Cin=%d (image channels) must be 1..4", Cin);
+  PDAE_REQUIRE(Cout % 8 == 0 && Cout >= 8 && Cout <= 256, "stem_conv_bf16: Cout=%d must be a multiple of 8 in [8, 256]", Cout);
+  PDAE_REQUIRE(B <= 65535, "stem_conv_bf16: B too large for grid.y");
+  PDAE_REQUIRE(W % 4 == 0 && ((uintptr_t)x_nchw & 15) == 0, "stem_conv_bf16: W=%d must be a multiple of 4 (16-byte aligned rows)", W);
+  const int ppc = 256 / (Cout / 8);
+  int gx = cdiv((long long)H * (W / 4), (long long)ppc * 2);   // ~2 pixel quads per thread: amortises the weight load and the flush
+  if (gx > 148 * 8) gx = 148 * 8;
+  if (gx < 1) gx = 1;
+  const size_t smem = (size_t)(9 * Cin + 2) * Cout * sizeof(float);
+  dim3 grid(gx, B);
+  cudaStream_t s = (cudaStream_t)stream;
+  __nv_bfloat16* o = (__nv_bfloat16*)out_bf16_nhwc;
+  switch (Cin) {
+    case 1: stem_conv_bf16_kernel<1><<<grid, 256, smem, s>>>(x_nchw, w_packed, bias, o, ch_stats, H, W, Cout); break;
+    case 2: stem_conv_bf16_kernel<2><<<grid, 256, smem, s>>>(x_nchw, w_packed, bias, o, ch_stats, H, W, Cout); break;
+    case 3: stem_conv_bf16_kernel<3><<<grid, 256, smem, s>>>(x_nchw, w_packed, bias, o, ch_stats, H, W, Cout); break;
+    default: stem_conv_bf16_kernel<4><<<grid, 256, smem, s>>>(x_nchw, w_packed, bias, o, ch_stats, H, W, Cout); break;
+  }
+  PDAE_LAUNCH_CHECK("stem_conv_bf16_kernel");
   return PDAE_OK;
 }

@@ -11,7 +11,7 @@ import torch.nn as nn
 
 from ..engine import Plan
 from .module import PlannedModule, Slots, Src, TimestepSequential, conv_nd, linear
-from .unet import EmbBank, emit_head, emit_time_embed, level_plan, make_head, make_middle, make_stage, res_blocks_of
+from .unet import EmbBank, emit_head, emit_stem, emit_time_embed, level_plan, make_head, make_middle, make_stage, res_blocks_of
 
 
 class ShiftUNet(PlannedModule):
@@ -86,12 +86,7 @@ class ShiftUNet(PlannedModule):
         bank_t = EmbBank(P, res_blocks_of(self.input_blocks, self.middle_block, self.output_blocks) + shift_blocks, "t",
                          emb, B, E, "shift_t" if with_shift else "eps_t")
 
-        stem = self.input_blocks[0][0]
-        c0 = stem.weight.shape[0]
-        h0 = P.new((B, H, W, c0), torch.float32, "stem")
-        P.conv(x_in, stem.weight, stem.bias, h0, B=B, H=H, W=W, Cin=self.input_channel, Cout=c0, k=3, in_nchw=True)
-        st0 = P.ch_stats(h0, c0, B=B, HW=H * W) if P.fused_stats else None
-        h = Src(P.to_stream(h0, c0, B=B, H=H, W=W), c0, B, H, W, s1=st0)
+        h = emit_stem(P, self.input_blocks[0][0], x_in, B, H, W, self.input_channel)
         hs = [h]
         for stage in list(self.input_blocks)[1:]:
             h = stage.emit(P, h, bank_t)

@@ -110,6 +110,26 @@ def emit_time_embed(P: Plan, time_embed: Slots, t: Buf, B: int, base: int, E: in
     return emb
 
 
+def emit_stem(P: Plan, stem: nn.Module, x_in: Buf, B: int, H: int, W: int, Cin: int) -> Src:
+    """First conv of the network on the NCHW image (model/unet.py:62-64).  With the bf16 residual stream it is ONE launch
+    writing bf16 NHWC plus the per-channel sums the first GroupNorms need (the stem output is a skip tensor read by three
+    of them); otherwise the generic CUDA-core conv (+ a statistics pass in fused-statistics mode)."""
+    c0 = stem.weight.shape[0]
+    if (P.fused_stats and P.stream_bf16 and Cin <= 4 and c0 % 8 == 0 and c0 <= 256 and stem.kernel_size[0] == 3
+            and W % 4 == 0):
+        wt = stem.weight
+        wp = P.pack((id(wt), "stem"), [wt], lambda: wt.detach().reshape(c0, Cin, 9).permute(2, 1, 0).float())   # [9][Cin][Cout]
+        h0 = P.new((B, H, W, c0), torch.bfloat16, "stem")
+        st0 = P.new_stats(B, c0)
+        P.call("stem_conv_bf16", x_in, wp, P.param(stem.bias), h0, st0, B, H, W, Cin, c0, _STREAM,
+               flops=2.0 * B * H * W * c0 * Cin * 9)
+        return Src(h0, c0, B, H, W, s1=st0)
+    h0 = P.new((B, H, W, c0), torch.float32, "stem")
+    P.conv(x_in, stem.weight, stem.bias, h0, B=B, H=H, W=W, Cin=Cin, Cout=c0, k=3, in_nchw=True)
+    st0 = P.ch_stats(h0, c0, B=B, HW=H * W) if P.fused_stats else None
+    return Src(P.to_stream(h0, c0, B=B, H=H, W=W), c0, B, H, W, s1=st0)
+
+
 def emit_head(P: Plan, head: Slots, x: Src, out: Buf, tape=None) -> None:
     gn, conv = head[0], head[2]
     B, H, W, C = x.B, x.H, x.W, x.C
@@ -168,14 +188,7 @@ class UNet(PlannedModule):
             P.call("embedding_add", emb, P.param(self.label_emb.weight), c_in, B, E, _STREAM)
         bank = EmbBank(P, res_blocks_of(self.input_blocks, self.middle_block, self.output_blocks), "t", emb, B, E, "unet_t")
 
-        stem = self.input_blocks[0][0]
-        h0 = P.new((B, H, W, stem.weight.shape[0]), torch.float32, "stem")
-        P.conv(x_in, stem.weight, stem.bias, h0, B=B, H=H, W=W, Cin=self.input_channel, Cout=stem.weight.shape[0], k=3,
-               in_nchw=True)
-        # the stem output is a skip tensor read by three GroupNorms: compute its per-channel sums once
-        c0_ = stem.weight.shape[0]
-        st0 = P.ch_stats(h0, c0_, B=B, HW=H * W) if P.fused_stats else None
-        h = Src(P.to_stream(h0, c0_, B=B, H=H, W=W), c0_, B, H, W, s1=st0)
+        h = emit_stem(P, self.input_blocks[0][0], x_in, B, H, W, self.input_channel)
         hs = [h]
         for stage in list(self.input_blocks)[1:]:
             h = stage.emit(P, h, bank)
