@@ -37,6 +37,8 @@ struct ConvTc2Args {
   int w_batched;  // B operand is a per-image matrix (batched GEMM): 3rd TMA coordinate = image index
   int kblocks2;   // fused 1x1 skip conv: extra K blocks from a second (activation, weight) pair, accumulated into the same tile
   int kblocks2a;  // ... of which the first kblocks2a come from tmA2, the rest from tmA3 (virtual channel concat of two tensors)
+  int w_stat;     // weights stationary: every B tile of the (single) n-tile is loaded ONCE per CTA into its own shared-memory
+                  // region and reused by all of the CTA's tiles; pipeline stages then hold A tiles only
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -134,7 +136,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmA3, ConvTc2Args p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[T2_MAX_STAGES], bar_empty[T2_MAX_STAGES];
-  __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2], bar_res[2];
+  __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2], bar_res[2], bar_w;
   __shared__ uint32_t tmem_slot;
   __shared__ float st_acc[2][2][BN < 32 ? 32 : BN];  // [epilogue group][sum | sum^2][channel] of the group's current (image, n-tile)
 
@@ -143,7 +145,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   const uint32_t smem0 = (s_u32(smem_raw) + 1023u) & ~1023u;
   const int S = p.stages;
-  const uint32_t stg_out = smem0 + (uint32_t)S * STAGE_BYTES;   // 2 x 16 KB output staging   (one per epilogue group)
+  const uint32_t stage_stride = p.w_stat ? (uint32_t)T2_A_BYTES : (uint32_t)STAGE_BYTES;
+  const uint32_t wbase = smem0 + (uint32_t)S * stage_stride;                       // stationary weights (w_stat only)
+  const uint32_t stg_out = wbase + (p.w_stat ? (uint32_t)((p.taps * p.kblocks + p.kblocks2) * B_BYTES) : 0u);   // 2 x 16 KB output staging   (one per epilogue group)
   const uint32_t stg_res = stg_out + 2u * T2_STG_BYTES;         // 2 x 16 KB residual staging (one per group; only if has_res)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_k = p.taps * p.kblocks;          // main conv
@@ -168,6 +172,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mb_init(s_u32(&bar_acc_empty[i]), 1);
       mb_init(s_u32(&bar_res[i]), 1);
     }
+    mb_init(s_u32(&bar_w), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -189,6 +194,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // ================= TMA producer =================
       int s = 0;
       uint32_t ph = 0;
+      const bool ws = p.w_stat != 0;
+      const uint32_t stage_tx = ws ? (uint32_t)T2_A_BYTES : (uint32_t)(T2_A_BYTES + B_BYTES);
+      if (ws && tile_begin < tile_end) {   // all B tiles of the layer, once (single n-tile: n0 = 0)
+        const uint32_t wb = s_u32(&bar_w);
+        mb_expect_tx(wb, (uint32_t)(total_all * B_BYTES));
+        for (int it = 0; it < total_k; ++it)
+          tma_ld3(wbase + (uint32_t)(it * B_BYTES), &tmB, wb, (it % p.kblocks) * T2_BK, 0, it / p.kblocks);
+        for (int kb2 = 0; kb2 < p.kblocks2; ++kb2)
+          tma_ld3(wbase + (uint32_t)((total_k + kb2) * B_BYTES), &tmB2, wb, kb2 * T2_BK, 0, 0);
+      }
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         const int nt = tile / p.tiles_m;
         int mt = tile - nt * p.tiles_m;
@@ -201,10 +216,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int it = 0; it < total_k; ++it) {
           mb_wait(s_u32(&bar_empty[s]), ph ^ 1u);
           const uint32_t full = s_u32(&bar_full[s]);
-          mb_expect_tx(full, T2_A_BYTES + B_BYTES);
-          const uint32_t sa = smem0 + (uint32_t)s * STAGE_BYTES;
+          mb_expect_tx(full, stage_tx);
+          const uint32_t sa = smem0 + (uint32_t)s * stage_stride;
           tma_ld4(sa, &tmA, full, kb * T2_BK, x0 + dx, y0 + dy, b0);
-          tma_ld3(sa + T2_A_BYTES, &tmB, full, kb * T2_BK, n0, p.w_batched ? b0 : tap);
+          if (!ws) tma_ld3(sa + T2_A_BYTES, &tmB, full, kb * T2_BK, n0, p.w_batched ? b0 : tap);
           if (++kb == p.kblocks) {
             kb = 0;
             ++tap;
@@ -215,11 +230,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int kb2 = 0; kb2 < p.kblocks2; ++kb2) {   // fused 1x1 skip conv: un-normalised input, centre tap
           mb_wait(s_u32(&bar_empty[s]), ph ^ 1u);
           const uint32_t full = s_u32(&bar_full[s]);
-          mb_expect_tx(full, T2_A_BYTES + B_BYTES);
-          const uint32_t sa = smem0 + (uint32_t)s * STAGE_BYTES;
+          mb_expect_tx(full, stage_tx);
+          const uint32_t sa = smem0 + (uint32_t)s * stage_stride;
           if (kb2 < p.kblocks2a) tma_ld4(sa, &tmA2, full, kb2 * T2_BK, x0, y0, b0);
           else tma_ld4(sa, &tmA3, full, (kb2 - p.kblocks2a) * T2_BK, x0, y0, b0);
-          tma_ld3(sa + T2_A_BYTES, &tmB2, full, kb2 * T2_BK, n0, 0);
+          if (!ws) tma_ld3(sa + T2_A_BYTES, &tmB2, full, kb2 * T2_BK, n0, 0);
           if (++s == S) { s = 0; ph ^= 1u; }
         }
       }
@@ -231,6 +246,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(T2_BM >> 4) << 24);
       int s = 0, tl = 0;
       uint32_t ph = 0;
+      if (p.w_stat && tile_begin < tile_end) mb_wait(s_u32(&bar_w), 0u);   // stationary weights have landed
       for (int tile = tile_begin; tile < tile_end; ++tile, ++tl) {
         const int ab = tl & 1;
         mb_wait(s_u32(&bar_acc_empty[ab]), (uint32_t)(((tl >> 1) & 1) ^ 1));  // epilogue drained this accumulator
@@ -239,8 +255,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int it = 0; it < total_all; ++it) {
           mb_wait(s_u32(&bar_full[s]), ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t sa = smem0 + (uint32_t)s * STAGE_BYTES;
-          const uint64_t ad = sw128_desc(sa), bd = sw128_desc(sa + T2_A_BYTES);
+          const uint32_t sa = smem0 + (uint32_t)s * stage_stride;
+          const uint64_t ad = sw128_desc(sa), bd = sw128_desc(p.w_stat ? wbase + (uint32_t)(it * B_BYTES) : sa + T2_A_BYTES);
 #pragma unroll
           for (int k = 0; k < T2_BK / 16; ++k)
             umma(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), IDESC, (uint32_t)((it | k) != 0));
@@ -605,15 +621,31 @@ static int tc2_create(pdae_conv_tc2_plan** plan_out, const Tc2Desc& d) {
   pl->BN = BN;
   a.tiles_total = a.tiles_m * (head ? 1 : Cout / BN);
   const int b_bytes = ((BN * T2_BK * 2 + 1023) / 1024) * 1024;
-  const int stage_bytes = T2_A_BYTES + b_bytes;
+  int stage_bytes = T2_A_BYTES + b_bytes;
   const int staging = head ? 0 : (a.has_res ? 4 : 2) * T2_STG_BYTES;
-  int stages = (220 * 1024 - 1024 - staging) / stage_bytes;
+  const int total_all = a.taps * a.kblocks + a.kblocks2;
+  pl->grid = a.tiles_total < g_num_sms ? a.tiles_total : g_num_sms;
+  // Weights stationary in shared memory: when the whole layer's B operand fits beside >= 4 A-only stages and every CTA
+  // runs several tiles of the single n-tile, the weights are fetched once per CTA instead of once per tile (the narrow
+  // 64-channel layers are L2->SM bandwidth-bound: this removes a third of their bytes).  PDAE_TC_WSTAT=0 disables (A/B aid).
+  static int wstat_env = -1;
+  if (wstat_env < 0) { const char* e = getenv("PDAE_TC_WSTAT"); wstat_env = (e && e[0] == '0') ? 0 : 1; }
+  int wbytes = 0;
+  a.w_stat = 0;
+  if (wstat_env && !head && !d.w_batched && Cout == BN && b_bytes == BN * T2_BK * 2 && a.tiles_total >= 2 * pl->grid) {
+    const int wb = total_all * b_bytes;
+    if ((220 * 1024 - 1024 - staging - wb) / T2_A_BYTES >= 4) {
+      a.w_stat = 1;
+      wbytes = wb;
+      stage_bytes = T2_A_BYTES;
+    }
+  }
+  int stages = (220 * 1024 - 1024 - staging - wbytes) / stage_bytes;
   if (stages > T2_MAX_STAGES) stages = T2_MAX_STAGES;
-  if (stages > a.taps * a.kblocks + a.kblocks2) stages = a.taps * a.kblocks + a.kblocks2;
+  if (stages > total_all) stages = total_all;
   if (stages < 2) stages = 2;
   a.stages = stages;
-  pl->smem = (size_t)stages * stage_bytes + staging + 1024;
-  pl->grid = a.tiles_total < g_num_sms ? a.tiles_total : g_num_sms;
+  pl->smem = (size_t)stages * stage_bytes + wbytes + staging + 1024;
 
   auto fail = [&](const char* what, int code) {
     delete pl;
