@@ -39,6 +39,8 @@ struct ConvTc2Args {
   int kblocks2a;  // ... of which the first kblocks2a come from tmA2, the rest from tmA3 (virtual channel concat of two tensors)
   int w_stat;     // weights stationary: every B tile of the (single) n-tile is loaded ONCE per CTA into its own shared-memory
                   // region and reused by all of the CTA's tiles; pipeline stages then hold A tiles only
+  int dbg_shift;  // probe (scripts/desc_shift_probe.py): load the A box dbg_shift pixels EARLY and start the UMMA descriptor
+  int dbg_boff;   // dbg_shift rows (x 128 B) into it, with the descriptor's base_offset field = dbg_boff -- 0 in production
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -218,7 +220,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t full = s_u32(&bar_full[s]);
           mb_expect_tx(full, stage_tx);
           const uint32_t sa = smem0 + (uint32_t)s * stage_stride;
-          tma_ld4(sa, &tmA, full, kb * T2_BK, x0 + dx, y0 + dy, b0);
+          tma_ld4(sa, &tmA, full, kb * T2_BK, x0 + dx - p.dbg_shift, y0 + dy, b0);
           if (!ws) tma_ld3(sa + T2_A_BYTES, &tmB, full, kb * T2_BK, n0, p.w_batched ? b0 : tap);
           if (++kb == p.kblocks) {
             kb = 0;
@@ -256,7 +258,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           mb_wait(s_u32(&bar_full[s]), ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem0 + (uint32_t)s * stage_stride;
-          const uint64_t ad = sw128_desc(sa), bd = sw128_desc(p.w_stat ? wbase + (uint32_t)(it * B_BYTES) : sa + T2_A_BYTES);
+          const uint64_t ad = sw128_desc(sa + (uint32_t)p.dbg_shift * 128u) | ((uint64_t)p.dbg_boff << 49),
+                         bd = sw128_desc(p.w_stat ? wbase + (uint32_t)(it * B_BYTES) : sa + T2_A_BYTES);
 #pragma unroll
           for (int k = 0; k < T2_BK / 16; ++k)
             umma(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), IDESC, (uint32_t)((it | k) != 0));
@@ -609,6 +612,12 @@ static int tc2_create(pdae_conv_tc2_plan** plan_out, const Tc2Desc& d) {
   a.has_res = d.residual != nullptr; a.out_bf16 = d.out_dtype == PDAE_BF16; a.cout_valid = cout_valid;
   a.w_batched = d.w_batched;
   a.kblocks2 = d.Cin2 / T2_BK;
+  {   // descriptor row-shift probe knobs (never set in production)
+    const char* e1 = getenv("PDAE_TC_DBG_SHIFT");
+    const char* e2 = getenv("PDAE_TC_DBG_BOFF");
+    a.dbg_shift = e1 ? atoi(e1) : 0;
+    a.dbg_boff = e2 ? atoi(e2) : 0;
+  }
   int BN;
   if (head) BN = 16;
   else if (d.bn_override == 64 || d.bn_override == 128 || d.bn_override == 256) BN = d.bn_override;
