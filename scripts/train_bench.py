@@ -55,7 +55,7 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
 print(f"train_bench celeba64-proxy B={B}: {ms:.1f} ms/step  {B / ms * 1e3:.1f} img/s  (fp32 CUDA-core fwd+bwd + fused Adam/EMA; "
-      f"loss {float(loss):.4f})")
+      f"loss {float(loss.detach()):.4f})")
 e0.record()
 for _ in range(20):
     for p in enc.parameters():

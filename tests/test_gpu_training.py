@@ -98,7 +98,7 @@ def test_second_step_after_optimizer_update_uses_new_weights():
         loss = _loss(gd, enc, dec, x0, t, noise)
         loss.backward()
         opt.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     assert losses[2] < losses[0], losses   # same batch, three Adam steps: the loss must go down
 
 
