@@ -211,6 +211,11 @@ int pdae_conv_tc2_create_skip2(pdae_conv_tc2_plan** plan, const void* in_bf16, c
 int pdae_gemm_tc2_create(pdae_conv_tc2_plan** plan, const void* a_bf16, long long a_ld, long long a_bs, const void* b_bf16,
                          long long b_ld, long long b_bs, void* out, int out_dtype, long long out_ld, long long out_bs,
                          int batch, int M, int N, int K);
+/* P_i = softmax_rows(alpha * A_i * Bm_i^T) stored as bf16 (ld / batch strides as above): attention probabilities with the
+ * softmax (module.py:455, :486) folded into the GEMM epilogue -- the fp32 scores never leave TMEM.  N in {64,128,256}.     */
+int pdae_gemm_tc2_softmax_create(pdae_conv_tc2_plan** plan, const void* a_bf16, long long a_ld, long long a_bs,
+                                 const void* b_bf16, long long b_ld, long long b_bs, void* out_bf16, long long out_ld,
+                                 long long out_bs, int batch, int M, int N, int K, float alpha);
 int pdae_conv_tc2_run(const pdae_conv_tc2_plan* plan, pdae_stream_t stream);
 /* P = softmax(alpha * S) per row, fp32 in -> bf16 out.  vT[b*heads+h][c][t] = V part of qkv (bf16 [B][T][3C]).        */
 int pdae_softmax_bf16(const float* S, void* P_bf16, int64_t rows, int cols, float alpha, pdae_stream_t stream);

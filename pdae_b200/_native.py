@@ -97,6 +97,8 @@ _SIGS = {
                                            c_int, c_int, c_int, c_int, c_int]),
     "pdae_gemm_tc2_create": (c_int, [POINTER(c_void_p), _P, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int, c_int64, c_int64,
                                      c_int, c_int, c_int, c_int]),
+    "pdae_gemm_tc2_softmax_create": (c_int, [POINTER(c_void_p), _P, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int64, c_int64,
+                                             c_int, c_int, c_int, c_int, c_float]),
     "pdae_conv_tc2_run": (c_int, [_P, _P]),
     "pdae_softmax_bf16": (c_int, [_P, _P, c_int64, c_int, c_float, _P]),
     "pdae_transpose_v": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),

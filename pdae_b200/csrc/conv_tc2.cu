@@ -39,6 +39,8 @@ struct ConvTc2Args {
   int kblocks2a;  // ... of which the first kblocks2a come from tmA2, the rest from tmA3 (virtual channel concat of two tensors)
   int w_stat;     // weights stationary: every B tile of the (single) n-tile is loaded ONCE per CTA into its own shared-memory
                   // region and reused by all of the CTA's tiles; pipeline stages then hold A tiles only
+  float softmax_alpha;  // > 0: the epilogue stores softmax_row(alpha * acc) (bf16) instead of acc -- attention scores whose
+                        // whole row lives in this tile's TMEM accumulator (N == BN); model/module.py:452-455,483-486
   int dbg_shift;  // probe (scripts/desc_shift_probe.py): load the A box dbg_shift pixels EARLY and start the UMMA descriptor
   int dbg_boff;   // dbg_shift rows (x 128 B) into it, with the descriptor's base_offset field = dbg_boff -- 0 in production
 };
@@ -317,6 +319,29 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           mb_expect_tx(rbar, T2_STG_BYTES);
           tma_ld4(rbuf, &tmR, rbar, n0, x0, y0, b0);
         }
+        // softmax epilogue: three passes over the accumulator row held in TMEM (max, sum of exp, normalised store)
+        float sm_mx = 0.f, sm_inv = 1.f;
+        const float sm_a = p.softmax_alpha * 1.4426950408889634f;
+        if (p.softmax_alpha > 0.f) {
+          float mx = -3.0e38f;
+          for (int c2 = 0; c2 < BN / 32; ++c2) {
+            uint32_t v[32];
+            tmem_ld32(tmem_acc + (uint32_t)(c2 * 32), v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+          }
+          float sum = 0.f;
+          for (int c2 = 0; c2 < BN / 32; ++c2) {
+            uint32_t v[32];
+            tmem_ld32(tmem_acc + (uint32_t)(c2 * 32), v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum += exp2f((__uint_as_float(v[j]) - mx) * sm_a);
+          }
+          sm_mx = mx;
+          sm_inv = 1.0f / sum;
+        }
         for (int c = 0; c < nch; ++c) {
           float val[64];
           {
@@ -331,6 +356,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
               for (int j = 0; j < 32; ++j) val[32 + j] = __uint_as_float(v[j]);
             }
+          }
+          if (p.softmax_alpha > 0.f) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) val[j] = exp2f((val[j] - sm_mx) * sm_a) * sm_inv;
           }
           if (p.bias) {
             const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c * CW);
@@ -569,6 +598,7 @@ struct Tc2Desc {
   long long w_ld, w_bs;
   long long out_ld, out_bs;   // elements between consecutive pixels / images of the output
   const void* in2 = nullptr; const void* w2 = nullptr; int Cin2 = 0;   // fused 1x1 skip conv (bf16 NHWC input, [Cout][Cin2] weights)
+  float softmax_alpha = 0.f;  // batched GEMM only: store softmax_row(alpha * out) as bf16 (needs N == BN)
   const void* in3 = nullptr; int Cin2a = 0;   // skip input = channel concat of in2 [..,Cin2a] and in3 [..,Cin2-Cin2a] (in3 == nullptr: in2 alone)
 };
 
@@ -612,6 +642,12 @@ static int tc2_create(pdae_conv_tc2_plan** plan_out, const Tc2Desc& d) {
   a.has_res = d.residual != nullptr; a.out_bf16 = d.out_dtype == PDAE_BF16; a.cout_valid = cout_valid;
   a.w_batched = d.w_batched;
   a.kblocks2 = d.Cin2 / T2_BK;
+  a.softmax_alpha = d.softmax_alpha;
+  if (d.softmax_alpha > 0.f && !(d.w_batched && d.out_dtype == PDAE_BF16 && !d.residual && !d.bias && !d.ch_stats &&
+                                 d.bn_override == Cout)) {
+    delete pl;
+    PDAE_REQUIRE(false, "conv_tc2_create: the softmax epilogue needs a bf16 batched GEMM whose row fits one tile (N=%d)", Cout);
+  }
   {   // descriptor row-shift probe knobs (never set in production)
     const char* e1 = getenv("PDAE_TC_DBG_SHIFT");
     const char* e2 = getenv("PDAE_TC_DBG_BOFF");
@@ -793,6 +829,23 @@ extern "C" int pdae_gemm_tc2_create(pdae_conv_tc2_plan** plan_out, const void* a
   d.in_ld = a_ld; d.in_bs = a_bs;
   d.w_batched = 1; d.w_ld = b_ld; d.w_bs = b_bs;
   d.out_ld = out_ld; d.out_bs = out_bs;
+  return tc2_create(plan_out, d);
+}
+
+// P_i = softmax_rows(alpha * A_i * Bm_i^T) stored as bf16: the attention-probability GEMM with the softmax folded into the
+// epilogue (the fp32 score matrix never leaves TMEM).  N must be 64, 128 or 256 (one n-tile holds the whole row).
+extern "C" int pdae_gemm_tc2_softmax_create(pdae_conv_tc2_plan** plan_out, const void* a_bf16, long long a_ld, long long a_bs,
+                                            const void* b_bf16, long long b_ld, long long b_bs, void* out_bf16, long long out_ld,
+                                            long long out_bs, int batch, int M, int N, int K, float alpha) {
+  PDAE_REQUIRE(N == 64 || N == 128 || N == 256, "gemm_tc2_softmax_create: N=%d must be 64, 128 or 256", N);
+  PDAE_REQUIRE(alpha > 0.f, "gemm_tc2_softmax_create: alpha must be positive");
+  Tc2Desc d;
+  d.in = a_bf16; d.w = b_bf16; d.bias = nullptr; d.residual = nullptr; d.out = out_bf16; d.out_dtype = PDAE_BF16;
+  d.ch_stats = nullptr; d.B = batch; d.H = 1; d.W = M; d.Cin = K; d.Cout = N; d.ksize = 1; d.cout_valid = 0; d.bn_override = N;
+  d.in_ld = a_ld; d.in_bs = a_bs;
+  d.w_batched = 1; d.w_ld = b_ld; d.w_bs = b_bs;
+  d.out_ld = out_ld; d.out_bs = out_bs;
+  d.softmax_alpha = alpha;
   return tc2_create(plan_out, d);
 }
 

@@ -273,6 +273,9 @@ class Plan:
             if fn == "gemm_tc2":
                 compiled.append(self._compile_gemm(args))
                 continue
+            if fn == "gemm_tc2_softmax":
+                compiled.append(self._compile_gemm_softmax(args))
+                continue
             if fn == "conv_tc2_skip":
                 compiled.append(self._compile_tc2_skip(args))
                 continue
@@ -339,6 +342,15 @@ class Plan:
         self._tc2_handles.append(h)
         return (self.L.pdae_conv_tc2_run, [h, None], 1, "conv_tc2")
 
+    def _compile_gemm_softmax(self, args):
+        a, a_ld, a_bs, b, b_ld, b_bs, out, o_ld, o_bs, batch, M, N, K, alpha = args
+        h = ctypes.c_void_p()
+        rc = self.L.pdae_gemm_tc2_softmax_create(ctypes.byref(h), self._resolve(a), a_ld, a_bs, self._resolve(b), b_ld, b_bs,
+                                                 self._resolve(out), o_ld, o_bs, batch, M, N, K, alpha)
+        _native.check(rc, "pdae_gemm_tc2_softmax_create")
+        self._tc2_handles.append(h)
+        return (self.L.pdae_conv_tc2_run, [h, None], 1, "gemm_tc2")
+
     def _compile_gemm(self, args):
         a, a_ld, a_bs, b, b_ld, b_bs, out, odt, o_ld, o_bs, batch, M, N, K = args
         h = ctypes.c_void_p()
@@ -348,8 +360,15 @@ class Plan:
         self._tc2_handles.append(h)
         return (self.L.pdae_conv_tc2_run, [h, None], 1, "gemm_tc2")
 
-    def gemm_tc(self, a, a_ld, a_bs, b, b_ld, b_bs, out, out_ld, out_bs, *, batch, M, N, K, out_dtype) -> None:
-        """Batched out_i = A_i (MxK) * B_i (NxK)^T on the persistent tcgen05 kernel; a/b/out are Buf or BufView."""
+    def gemm_tc(self, a, a_ld, a_bs, b, b_ld, b_bs, out, out_ld, out_bs, *, batch, M, N, K, out_dtype,
+                softmax_alpha: Optional[float] = None) -> None:
+        """Batched out_i = A_i (MxK) * B_i (NxK)^T on the persistent tcgen05 kernel; a/b/out are Buf or BufView.
+        softmax_alpha: store softmax_rows(alpha * out_i) (bf16) instead -- needs N in {64,128,256} (row inside one tile)."""
+        if softmax_alpha is not None:
+            assert out_dtype == torch.bfloat16 and N in (64, 128, 256)
+            self.call("gemm_tc2_softmax", a, a_ld, a_bs, b, b_ld, b_bs, out, out_ld, out_bs, batch, M, N, K,
+                      ctypes.c_float(softmax_alpha), flops=2.0 * batch * M * N * K)
+            return
         self.call("gemm_tc2", a, a_ld, a_bs, b, b_ld, b_bs, out, _DT[out_dtype], out_ld, out_bs, batch, M, N, K,
                   flops=2.0 * batch * M * N * K)
 

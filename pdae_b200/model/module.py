@@ -422,15 +422,23 @@ class AttentionBlock(PlannedModule):
             P.conv(xn, self.qkv.weight, self.qkv.bias, qkv, B=B, H=H, W=W, Cin=C, Cout=3 * C, k=1)
             vT = P.new((B * heads, ch, T), torch.bfloat16, "vT")
             P.call("transpose_v", qkv, vT, B, T, C, heads, int(legacy), _STREAM)
-            S = P.new((B * heads, T, T), torch.float32, "att_scores")
             Pm = P.new((B * heads, T, T), torch.bfloat16, "att_probs")
             att = P.new((B, T, C), torch.bfloat16, "att")
             hs_ = 3 * ch if legacy else ch                  # channel stride between heads inside a qkv row
             ko = ch if legacy else C                        # offset of K relative to Q
+            alpha = 1.0 / math.sqrt(ch)                     # scale = ch^(-1/4) on both q and k (module.py:449-453)
+            fuse_sm = T in (64, 128, 256) and os.environ.get("PDAE_FUSE_SOFTMAX", "1") == "1"
+            S = None if fuse_sm else P.new((B * heads, T, T), torch.float32, "att_scores")
             for h in range(heads):
-                P.gemm_tc(qkv.at(h * hs_), 3 * C, T * 3 * C, qkv.at(h * hs_ + ko), 3 * C, T * 3 * C,
-                          S.at(h * T * T), T, heads * T * T, batch=B, M=T, N=T, K=ch, out_dtype=torch.float32)
-            P.call("softmax_bf16", S, Pm, ctypes.c_int64(B * heads * T), T, ctypes.c_float(1.0 / math.sqrt(ch)), _STREAM)
+                if fuse_sm:   # a whole score row sits in one TMEM accumulator tile: softmax in the GEMM epilogue
+                    P.gemm_tc(qkv.at(h * hs_), 3 * C, T * 3 * C, qkv.at(h * hs_ + ko), 3 * C, T * 3 * C,
+                              Pm.at(h * T * T), T, heads * T * T, batch=B, M=T, N=T, K=ch, out_dtype=torch.bfloat16,
+                              softmax_alpha=alpha)
+                else:
+                    P.gemm_tc(qkv.at(h * hs_), 3 * C, T * 3 * C, qkv.at(h * hs_ + ko), 3 * C, T * 3 * C,
+                              S.at(h * T * T), T, heads * T * T, batch=B, M=T, N=T, K=ch, out_dtype=torch.float32)
+            if not fuse_sm:
+                P.call("softmax_bf16", S, Pm, ctypes.c_int64(B * heads * T), T, ctypes.c_float(alpha), _STREAM)
             for h in range(heads):
                 P.gemm_tc(Pm.at(h * T * T), T, heads * T * T, vT.at(h * ch * T), T, heads * ch * T,
                           att.at(h * ch), C, T * C, batch=B, M=T, N=ch, K=T, out_dtype=torch.bfloat16)
