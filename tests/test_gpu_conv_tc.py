@@ -179,3 +179,74 @@ def test_head_conv_smalln():
         P.run()
         assert [o[0] for o in P.ops] == ["conv3x3_smalln"]
         assert_close(out.tensor, ref, rtol=1e-4, atol=1e-4, what=f"smalln {dt}")
+
+
+@pytest.mark.parametrize("T,K,batch", [(256, 128, 3), (128, 64, 5), (256, 512, 2)])
+def test_softmax_gemm_epilogue(T, K, batch):
+    """P = softmax_rows(alpha * Q K^T) with the softmax inside the tcgen05 GEMM epilogue (scores stay in TMEM) vs torch."""
+    from pdae_b200.engine import Plan
+    g = torch.Generator(device="cpu").manual_seed(17)
+    q = torch.randn(batch, T, K, generator=g).to(torch.bfloat16)
+    k = (torch.randn(batch, T, K, generator=g) * 1.5).to(torch.bfloat16)
+    alpha = 1.0 / K ** 0.5
+    ref = torch.softmax(alpha * torch.einsum("btc,bsc->bts", q.float(), k.float()), dim=-1)
+    P = Plan(torch.device("cuda"), "bf16")
+    out = P.new((batch, T, T), torch.bfloat16)
+    out.keep = True
+    P.gemm_tc(P.fixed(q.cuda()), K, T * K, P.fixed(k.cuda()), K, T * K, out, T, T * T, batch=batch, M=T, N=T, K=K,
+              out_dtype=torch.bfloat16, softmax_alpha=alpha)
+    P.finalize()
+    P.run()
+    got = out.tensor.float().cpu()
+    assert_close(got, ref, rtol=1e-2, atol=2e-3, what=f"softmax gemm T={T} K={K}")        # bf16 storage of probabilities
+    assert_close(got.sum(-1), torch.ones(batch, T), rtol=0, atol=6e-3, what="rows sum to 1")
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 128, 64, 128), (1, 64, 64, 64, 64, 64), (3, 8, 8, 256, 256, 128)])
+def test_fused_skip_conv_two_sources(shape):
+    """The 1x1 skip conv over cat([xa, xb]) folded into conv3x3 with the two halves read through separate TMA maps."""
+    from pdae_b200.engine import Plan
+    B, H, W, Cin, Ca, Cb = shape
+    Cout = Cin
+    g = torch.Generator(device="cpu").manual_seed(19)
+    x = torch.randn(B, H, W, Cin, generator=g).to(torch.bfloat16)
+    xa = torch.randn(B, H, W, Ca, generator=g).to(torch.bfloat16)
+    xb = torch.randn(B, H, W, Cb, generator=g).to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).to(torch.bfloat16).float()
+    w2 = (torch.randn(Cout, Ca + Cb, 1, 1, generator=g) / (Ca + Cb) ** 0.5).to(torch.bfloat16).float()
+    b, b2 = torch.randn(Cout, generator=g), torch.randn(Cout, generator=g)
+    cat = torch.cat([xa, xb], dim=-1).float().permute(0, 3, 1, 2)
+    ref = (F.conv2d(x.float().permute(0, 3, 1, 2), w, b, padding=1) + F.conv2d(cat, w2, b2)).permute(0, 2, 3, 1)
+    P = Plan(torch.device("cuda"), "bf16")
+    out = P.new((B, H, W, Cout), torch.float32)
+    out.keep = True
+    P.conv(P.fixed(x.cuda()), w.cuda(), b.cuda(), out, B=B, H=H, W=W, Cin=Cin, Cout=Cout, k=3,
+           skip=((P.fixed(xa.cuda()), Ca, P.fixed(xb.cuda()), Cb), w2.cuda(), b2.cuda(), Ca + Cb))
+    P.finalize()
+    P.run()
+    assert_close(out.tensor, ref, rtol=2e-3, atol=2e-3, what=f"two-source fused skip {shape}")
+
+
+@pytest.mark.parametrize("shape", [(3, 3, 32, 32, 64), (2, 1, 16, 40, 32), (2, 3, 64, 64, 128)])
+def test_stem_conv_bf16_with_stats(shape):
+    """Image stem: NCHW fp32 -> bf16 NHWC stream + per-channel sums of the stored values, vs torch."""
+    from pdae_b200.engine import Plan, _STREAM
+    B, Cin, H, W, Cout = shape
+    g = torch.Generator(device="cpu").manual_seed(23)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)
+    b = torch.randn(Cout, generator=g)
+    ref = F.conv2d(x, w, b, padding=1).permute(0, 2, 3, 1)
+    P = Plan(torch.device("cuda"), "bf16")
+    out = P.new((B, H, W, Cout), torch.bfloat16)
+    out.keep = True
+    st = P.new_stats(B, Cout)
+    wp = P.fixed(w.reshape(Cout, Cin, 9).permute(2, 1, 0).contiguous().cuda())
+    P.call("stem_conv_bf16", P.fixed(x.cuda()), wp, P.fixed(b.cuda()), out, st, B, H, W, Cin, Cout, _STREAM)
+    P.finalize()
+    P.run()
+    P.run()     # the statistics arena is re-zeroed on every replay
+    assert_close(out.tensor.float(), ref, rtol=1e-2, atol=1e-2, what=f"stem {shape}")
+    y = out.tensor.float().reshape(B, H * W, Cout)
+    got = st.buf.tensor[st.off: st.off + B * Cout * 2].reshape(B, Cout, 2)
+    assert_close(got, torch.stack([y.sum(1), (y * y).sum(1)], dim=-1), rtol=2e-3, atol=5e-2, what="stem stats")
