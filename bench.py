@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--workload", default="celeba64", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (0 = workload default)")
     ap.add_argument("--ddim-steps", type=int, default=100)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     return ap.parse_args()
@@ -282,7 +282,7 @@ def main():
     line = {
         "metric": "ddim100_autoencoding_images_per_sec", "value": round(value, 4), "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 3), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "bf16x3": "bf16x3 (split-operand bf16 MMAs, fp32-grade)", "fp32": "f32"}[args.precision], "data": "synthetic",
         "config": {"workload": f"{args.workload}-proxy ShiftUNet+encoder (proxy decoder config, SURVEY D4), {size}x{size}x3, "
                                f"DDIM-{S} encode + DDIM-{S} decode", "batch_per_gpu": B, "global_batch": world * B,
                    "parallelism": f"dp{world} batch-sharded, one all-gather of results", "precision": args.precision,
@@ -302,10 +302,43 @@ def main():
                                 "sample": f"oracle (torch-CPU restatement of the reference), batch {b}: 1 warm-up + 3 timed "
                                           f"ShiftUNet DDIM steps ({t_step:.2f} s/step) + 1 encoder forward, extrapolated to "
                                           f"{2 * S} steps per image"}
+        line["cpu_baseline"]["parity"] = parity_probe(gd, enc, dec, cfg, size, enc_kind, enc_size, enc_input, dev)
     print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def parity_probe(gd, enc, dec, cfg, size, enc_kind, enc_size, enc_input, dev):
+    """The oracle used as the CHECKER on a bounded sample of the bench workload: a short DDIM autoencoding of a few images
+    through the CPU oracle and through this package (fp32 parity mode, the split-operand tensor-core mode "bf16x3" and the
+    bf16 mode the bench times), same weights and
+    inputs.  Reports the reconstruction MSE of each (BASELINE.json: "recon MSE vs ref") and the relative L2 distance of
+    the reconstructions.  Random-init weights make the sampling chain chaotic (tests/test_oracle_golden.py::
+    test_loop_sensitivity), so the bf16 figure measures amplified rounding noise, not image quality."""
+    from pdae_b200.utils.synth import synth_images
+    n, s = (2, 10) if size <= 64 else ((1, 5) if size <= 128 else (1, 3))
+    style = f"ddim{s}"
+    x0 = synth_images(n, 3, size, 4242)
+    enc_o, dec_o, O = oracle_models(cfg, enc_kind)
+    D = O.DiffusionOracle(DIFFUSION)
+    with torch.inference_mode():
+        z = enc_o(enc_input(x0))
+        ref = D.representation_learning_ddim_sample(style, dec_o, D.representation_learning_ddim_encode(style, dec_o, x0, z), z)
+    out = {"sample": f"{n} image(s), {style} encode + {style} decode, same synthetic weights/inputs as the oracle",
+           "recon_mse_reference": float(((ref - x0) ** 2).mean())}
+    prev = (enc.precision if hasattr(enc, "precision") else None, dec.precision if hasattr(dec, "precision") else None)
+    for prec in ("fp32", "bf16x3", "bf16"):
+        enc.precision = dec.precision = prec
+        with torch.inference_mode():
+            xd = x0.to(dev)
+            zz = enc(enc_input(xd))
+            rec = gd.representation_learning_ddim_sample(style, None, dec, None,
+                                                         gd.representation_learning_ddim_encode(style, None, dec, xd, zz), zz).cpu()
+        out[f"recon_mse_{prec}"] = float(((rec - x0) ** 2).mean())
+        out[f"rel_l2_vs_reference_{prec}"] = float((rec - ref).norm() / ref.norm())
+    enc.precision, dec.precision = prev
+    return out
 
 
 if __name__ == "__main__":

@@ -80,6 +80,12 @@ int pdae_gn_apply(const void* src1, int src1_dtype, int C1, const void* src2, in
                   int silu, int resample, int B, int H, int W, void* out_act, int act_dtype, void* out_raw, int raw_dtype,
                   pdae_stream_t stream);
 
+/* "bf16x3" precision (fp32-grade results from bf16 tensor-core MMAs): like pdae_gn_apply with fp32 sources, but the
+ * activation is written as three bf16 channel blocks [hi | lo | hi] per pixel (out_act3: [B][Ho][Wo][3*(C1+C2)],
+ * hi = bf16(a), lo = bf16(a - hi)); a conv whose weights are packed [W_hi | W_hi | W_lo] along Cin then yields
+ * a_hi*W_hi + a_lo*W_hi + a_hi*W_lo.  out_raw (optional): fp32 plain [..][C] or bf16 split [..][3C] per raw_dtype.        */
+int pdae_gn_apply_split3(const float* src1, int C1, const float* src2, int C2, const float* ab, int silu, int resample, int B,
+                         int H, int W, void* out_act3_bf16, void* out_raw, int raw_dtype, pdae_stream_t stream);
 /* GroupNorm(32) + affine/AdaGN + SiLU in ONE launch (the gn_coef_ch + gn_apply pair): coefficients are derived in each
  * CTA's prologue from the per-channel (sum, sum^2) of the sources ([B][C][2] fp32, as accumulated by the conv epilogue or
  * pdae_ch_stats).  No resampling; out_act is bf16 NHWC [B][H][W][C1+C2]; out_raw (optional) the un-normalised concat in

@@ -106,6 +106,7 @@ _SIGS = {
     "pdae_mlp_mod_ln_act_bwd": (c_int, [_P, _P, _P, _P, c_float, c_int, _P, c_int, _P, _P, _P, _P, c_int, c_int, _P]),
     "pdae_mul_mask_cols": (c_int, [_P, c_int, _P, c_float, c_int, c_int, _P]),
     "pdae_stem_conv_bf16": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "pdae_gn_apply_split3": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P]),
     "pdae_gn_norm_apply": (c_int, [_P, c_int, c_int, _P, _P, c_int, c_int, _P, _P, _P, c_float, _P, c_int, _P, c_int, c_int, c_int,
                                    c_int, c_int, _P, _P, c_int, _P]),
     "pdae_adam_ema_step": (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_int64, c_float,

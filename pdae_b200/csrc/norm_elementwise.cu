@@ -436,6 +436,83 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const TSrc* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// "bf16x3" precision: activations are written as THREE bf16 channel blocks [hi | lo | hi] (hi = bf16(a), lo = bf16(a - hi))
+// so that a tensor-core conv whose weights are packed [W_hi | W_hi | W_lo] along Cin computes
+// a_hi*W_hi + a_lo*W_hi + a_hi*W_lo = a*W to ~2^-16 relative -- fp32-grade results from bf16 MMAs (3x the MMA work).
+// Sources fp32; raw output either fp32 (plain, C channels) or bf16 (split, 3C channels).
+__device__ __forceinline__ void store_split3(__nv_bfloat16* pix_base, int C, int c, float4 r) {
+  const __nv_bfloat162 h0 = __floats2bfloat162_rn(r.x, r.y), h1 = __floats2bfloat162_rn(r.z, r.w);
+  const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+  const __nv_bfloat162 l0 = __floats2bfloat162_rn(r.x - f0.x, r.y - f0.y), l1 = __floats2bfloat162_rn(r.z - f1.x, r.w - f1.y);
+  uint2 hi, lo;
+  hi.x = *reinterpret_cast<const uint32_t*>(&h0); hi.y = *reinterpret_cast<const uint32_t*>(&h1);
+  lo.x = *reinterpret_cast<const uint32_t*>(&l0); lo.y = *reinterpret_cast<const uint32_t*>(&l1);
+  *reinterpret_cast<uint2*>(pix_base + c) = hi;
+  *reinterpret_cast<uint2*>(pix_base + C + c) = lo;
+  *reinterpret_cast<uint2*>(pix_base + 2 * C + c) = hi;
+}
+
+template <typename TRaw, int RS>
+__global__ void __launch_bounds__(256) gn_apply_split3_kernel(const float* __restrict__ s1, int C1, const float* __restrict__ s2,
+                                                              int C2, const float* __restrict__ ab, int silu, int H, int W,
+                                                              __nv_bfloat16* __restrict__ out_act, TRaw* __restrict__ out_raw) {
+  const int C = C1 + C2, L = C >> 2;
+  const int b = blockIdx.y;
+  const int Hi = RS == PDAE_RESAMPLE_DOWN2 ? H / 2 : H, Wi = RS == PDAE_RESAMPLE_DOWN2 ? W / 2 : W;
+  const long long items = (long long)Hi * Wi * L;
+  const int Ho = RS == PDAE_RESAMPLE_UP2 ? 2 * H : Hi, Wo = RS == PDAE_RESAMPLE_UP2 ? 2 * W : Wi;
+  constexpr bool RAW_SPLIT = sizeof(TRaw) == 2;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.x * blockDim.x) {
+    const int cq = (int)(it % L);
+    const long long pix = it / L;
+    const int x = (int)(pix % Wi), y = (int)(pix / Wi);
+    const int c = cq * 4;
+    const bool first = c < C1;
+    const int cs = first ? C1 : C2, cc = first ? c : c - C1;
+    const float* src = (first ? s1 : s2) + (long long)b * H * W * cs + cc;
+    float4 a = make_float4(1.f, 1.f, 1.f, 1.f), bb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ab) {
+      a = *reinterpret_cast<const float4*>(ab + ((long long)b * 2 + 0) * C + c);
+      bb = *reinterpret_cast<const float4*>(ab + ((long long)b * 2 + 1) * C + c);
+    }
+    auto put = [&](int oy, int ox, float4 r, float4 v) {
+      const long long o = ((long long)b * Ho + oy) * Wo + ox;
+      store_split3(out_act + o * 3 * C, C, c, r);
+      if (out_raw) {
+        if (RAW_SPLIT) store_split3(reinterpret_cast<__nv_bfloat16*>(out_raw) + o * 3 * C, C, c, v);
+        else store4<float>(reinterpret_cast<float*>(out_raw) + o * C + c, v);
+      }
+    };
+    if (RS == PDAE_RESAMPLE_DOWN2) {
+      float4 accA = make_float4(0.f, 0.f, 0.f, 0.f), accR = accA;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const float4 v = *reinterpret_cast<const float4*>(src + ((long long)(2 * y + dy) * W + 2 * x + dx) * cs);
+          const float4 r = affine_act(v, a, bb, silu);
+          accA.x += r.x; accA.y += r.y; accA.z += r.z; accA.w += r.w;
+          accR.x += v.x; accR.y += v.y; accR.z += v.z; accR.w += v.w;
+        }
+      put(y, x, make_float4(accA.x * 0.25f, accA.y * 0.25f, accA.z * 0.25f, accA.w * 0.25f),
+          make_float4(accR.x * 0.25f, accR.y * 0.25f, accR.z * 0.25f, accR.w * 0.25f));
+    } else {
+      const float4 v = *reinterpret_cast<const float4*>(src + ((long long)y * W + x) * cs);
+      const float4 r = affine_act(v, a, bb, silu);
+      if (RS == PDAE_RESAMPLE_UP2) {
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) put(2 * y + dy, 2 * x + dx, r, v);
+      } else {
+        put(y, x, r, v);
+      }
+    }
+  }
+}
+
+
 // ---------------------------------------------------------------------------------------------
 __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, int B, int dim,
                                           const float* __restrict__ freqs, float* __restrict__ out) {
@@ -725,6 +802,36 @@ extern "C" int pdae_gn_apply(const void* src1, int src1_dtype, int C1, const voi
   }
   PDAE_REQUIRE(false, "gn_apply: unsupported dtype combination src1=%d src2=%d act=%d raw=%d", src1_dtype, src2_dtype, act_dtype,
                raw_dtype);
+}
+
+extern "C" int pdae_gn_apply_split3(const float* src1, int C1, const float* src2, int C2, const float* ab, int silu, int resample,
+                                    int B, int H, int W, void* out_act3_bf16, void* out_raw, int raw_dtype,
+                                    pdae_stream_t stream) {
+  PDAE_REQUIRE(src1 && out_act3_bf16, "gn_apply_split3: null pointer");
+  if (!src2) C2 = 0;
+  PDAE_REQUIRE(C1 % 4 == 0 && C2 % 4 == 0 && C1 + C2 > 0, "gn_apply_split3: C1=%d C2=%d unsupported", C1, C2);
+  PDAE_REQUIRE(resample >= 0 && resample <= 2, "gn_apply_split3: bad resample mode");
+  PDAE_REQUIRE(resample != PDAE_RESAMPLE_DOWN2 || (H % 2 == 0 && W % 2 == 0), "gn_apply_split3: odd dims for DOWN2");
+  const int Hi = resample == PDAE_RESAMPLE_DOWN2 ? H / 2 : H, Wi = resample == PDAE_RESAMPLE_DOWN2 ? W / 2 : W;
+  const long long items = (long long)Hi * Wi * ((C1 + C2) / 4);
+  int gx = cdiv(items, 256);
+  if (gx > 148 * 16) gx = 148 * 16;
+  dim3 grid(gx, B);
+  cudaStream_t s = (cudaStream_t)stream;
+  typedef __nv_bfloat16 bf;
+  bf* oa = (bf*)out_act3_bf16;
+  const bool rs_bf = out_raw && raw_dtype == PDAE_BF16;
+#define PDAE_SPLIT3(RS)                                                                                                   \
+  do {                                                                                                                     \
+    if (rs_bf) gn_apply_split3_kernel<bf, RS><<<grid, 256, 0, s>>>(src1, C1, src2, C2, ab, silu, H, W, oa, (bf*)out_raw);   \
+    else gn_apply_split3_kernel<float, RS><<<grid, 256, 0, s>>>(src1, C1, src2, C2, ab, silu, H, W, oa, (float*)out_raw);   \
+  } while (0)
+  if (resample == PDAE_RESAMPLE_NONE) PDAE_SPLIT3(PDAE_RESAMPLE_NONE);
+  else if (resample == PDAE_RESAMPLE_UP2) PDAE_SPLIT3(PDAE_RESAMPLE_UP2);
+  else PDAE_SPLIT3(PDAE_RESAMPLE_DOWN2);
+#undef PDAE_SPLIT3
+  PDAE_LAUNCH_CHECK("gn_apply_split3_kernel");
+  return PDAE_OK;
 }
 
 extern "C" int pdae_gn_norm_apply(const void* src1, int src1_dtype, int C1, const float* chs1, const void* src2, int src2_dtype,

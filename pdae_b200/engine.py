@@ -27,12 +27,17 @@ _DT = {torch.float32: PDAE_F32, torch.bfloat16: PDAE_BF16}
 _STREAM = object()  # placeholder replaced by the current stream at run time
 
 _default_precision = "bf16"
+# "fp32"   : CUDA-core fp32 arithmetic everywhere (parity / training mode)
+# "bf16"   : tcgen05 bf16 MMAs, bf16 activations and residual stream (the fast mode; stated tolerance rel-L2 <= 2e-2)
+# "bf16x3" : tcgen05 bf16 MMAs on split operands (a = hi + lo, three products per term), fp32 residual stream and GroupNorm
+#            inputs: fp32-grade results (meets the fp32 tolerance) at ~3x the MMA work of "bf16"
+PRECISIONS = ("fp32", "bf16", "bf16x3")
 
 
 def set_default_precision(p: str) -> None:
     global _default_precision
-    if p not in ("fp32", "bf16"):
-        raise ValueError("precision must be 'fp32' or 'bf16'")
+    if p not in PRECISIONS:
+        raise ValueError(f"precision must be one of {PRECISIONS}")
     _default_precision = p
 
 
@@ -42,7 +47,7 @@ def get_default_precision() -> str:
 
 class Buf:
     """A device buffer known to a plan: either plan-owned (arena) or fixed (parameter / caller tensor)."""
-    __slots__ = ("shape", "dtype", "tensor", "first", "last", "fixed", "keep", "name", "_block")
+    __slots__ = ("shape", "dtype", "tensor", "first", "last", "fixed", "keep", "name", "_block", "split3")
 
     def __init__(self, shape, dtype, tensor=None, name=""):
         self.shape = tuple(int(s) for s in shape)
@@ -53,6 +58,7 @@ class Buf:
         self.last = None
         self.keep = False
         self.name = name
+        self.split3 = False   # "bf16x3" activation: last dim holds three bf16 channel blocks [hi | lo | hi]
 
     @property
     def nbytes(self) -> int:
@@ -92,6 +98,14 @@ class Packed:
             self.stamp = st
 
 
+def split3_weights(w: torch.Tensor) -> torch.Tensor:
+    """[Cout][Cin][taps] fp32 -> [taps][Cout][3*Cin] bf16 = [W_hi | W_hi | W_lo] (pairs with activations [a_hi | a_lo | a_hi])."""
+    w = w.float()
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, hi, lo], dim=1).permute(2, 0, 1).contiguous()
+
+
 class CoefSpec:
     """GroupNorm coefficients not yet computed: the per-channel statistics and affine / AdaGN operands a later gn_apply
     needs (Plan.gn_coef in fused-statistics mode)."""
@@ -108,12 +122,15 @@ class Plan:
             _native.require_device()
         self.device = device
         self.precision = precision or _default_precision
-        self.tc = self.precision == "bf16"
-        self.v2 = os.environ.get("PDAE_TC_V1", "0") != "1"       # persistent v2 conv kernel (default) vs the simple v1
+        if self.precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {PRECISIONS}")
+        self.x3 = self.precision == "bf16x3"                     # split-operand tensor-core mode (fp32-grade results)
+        self.tc = self.precision in ("bf16", "bf16x3")
+        self.v2 = os.environ.get("PDAE_TC_V1", "0") != "1" or self.x3   # persistent v2 conv kernel (default) vs the simple v1
         self.bn_override = int(os.environ.get("PDAE_TC_BN", "0"))  # tuning aid: force the N tile of the v2 kernel
         # residual stream (block outputs / skip tensors) kept in bf16 instead of fp32: halves the HBM bytes of the
         # bandwidth-bound top-level layers.  "bf16" precision + v2 kernel only.
-        self.stream_bf16 = self.tc and self.v2 and os.environ.get("PDAE_STREAM_BF16", "1") == "1"
+        self.stream_bf16 = self.tc and self.v2 and not self.x3 and os.environ.get("PDAE_STREAM_BF16", "1") == "1"
         self.fuse_coef = os.environ.get("PDAE_FUSE_COEF", "0") == "1"   # GN coefficients inside gn_apply: measured 0.15 ms/step SLOWER under graph replay (profiles/README.md) -> off
         self.L = _native.lib()
         self.ops: List[Tuple[str, list]] = []
@@ -373,7 +390,7 @@ class Plan:
                   flops=2.0 * batch * M * N * K)
 
     def can_gemm_tc(self, M: int, N: int, K: int) -> bool:
-        return self.tc and self.v2 and M % 128 == 0 and N % 64 == 0 and K % 64 == 0
+        return self.tc and self.v2 and not self.x3 and M % 128 == 0 and N % 64 == 0 and K % 64 == 0
 
     def __del__(self):
         try:
@@ -482,9 +499,14 @@ class Plan:
         bias_b = self.param(bias)
         wkey = wkey or id(weight)
         if x.dtype == torch.bfloat16 and self.use_tc(Cin, Cout, k, stride, H, W) and not (in_nchw or out_nchw or a_silu):
-            wp = self.pack((wkey, "tc"), [weight],
-                           lambda: weight.detach().reshape(Cout, Cin, k * k).permute(2, 0, 1).to(torch.bfloat16))
-            fl = 2.0 * B * H * W * Cout * Cin * k * k
+            x3 = bool(x.split3)
+            fl = 2.0 * B * H * W * Cout * Cin * k * k     # algorithmic (the x3 mode issues 3x the MMAs for it)
+            if x3:   # activation blocks [a_hi | a_lo | a_hi] x weight blocks [W_hi | W_hi | W_lo]
+                wp = self.pack((wkey, "tc_x3"), [weight], lambda: split3_weights(weight.detach().reshape(Cout, Cin, k * k)))
+                Cin = 3 * Cin
+            else:
+                wp = self.pack((wkey, "tc"), [weight],
+                               lambda: weight.detach().reshape(Cout, Cin, k * k).permute(2, 0, 1).to(torch.bfloat16))
             if not self.v2:
                 assert out.dtype == torch.float32
                 self.call("conv_tc", x, wp, bias_b, residual, out, B, H, W, Cin, Cout, k, flops=fl)
@@ -495,14 +517,18 @@ class Plan:
                 sk_in, sw, sb, Cin2 = skip   # sk_in: a bf16 buffer, or (buf_a, Ca, buf_b, Cb) = their channel concat
                 assert residual is None
                 if isinstance(sk_in, tuple):
-                    assert sk_in[0].dtype == sk_in[2].dtype == torch.bfloat16 and sk_in[1] + sk_in[3] == Cin2
+                    assert sk_in[0].dtype == sk_in[2].dtype == torch.bfloat16 and sk_in[1] + sk_in[3] == Cin2 and not x3
                 else:
-                    assert sk_in.dtype == torch.bfloat16
-                w2 = self.pack((id(sw), "tc_skip"), [sw], lambda: sw.detach().reshape(Cout, Cin2).to(torch.bfloat16))
+                    assert sk_in.dtype == torch.bfloat16 and bool(sk_in.split3) == x3
+                if x3:
+                    w2 = self.pack((id(sw), "tc_skip_x3"), [sw], lambda: split3_weights(sw.detach().reshape(Cout, Cin2, 1))[0])
+                    Cin2 = 3 * Cin2
+                else:
+                    w2 = self.pack((id(sw), "tc_skip"), [sw], lambda: sw.detach().reshape(Cout, Cin2).to(torch.bfloat16))
                 bsum = self.pack((id(bias), id(sb), "bias_sum"), [bias, sb], lambda: (bias.detach() + sb.detach()).float())
                 self.params.append((sb, sb.data_ptr()))
                 self.call("conv_tc2_skip", x, wp, bsum, sk_in, w2, Cin2, out, _DT[out.dtype], stats, B, H, W, Cin, Cout, k,
-                          bn_override or self.bn_override, flops=fl + 2.0 * B * H * W * Cout * Cin2)
+                          bn_override or self.bn_override, flops=fl + 2.0 * B * H * W * Cout * (Cin2 // 3 if x3 else Cin2))
                 return stats
             self.call("conv_tc2", x, wp, bias_b, residual, out, _DT[out.dtype], stats, B, H, W, Cin, Cout, k, 0,
                       bn_override or self.bn_override, flops=fl)
@@ -528,13 +554,17 @@ class Plan:
         fl = 2.0 * B * H * W * Cout * Cin * 9
         if self.v2 and x.dtype == torch.bfloat16 and Cout <= 16 and self.use_tc(Cin, 64, 3, 1, H, W):
             # tensor-core head: Cout zero-padded to one 16-wide UMMA tile, NCHW fp32 planes written by the epilogue
+            x3 = bool(x.split3)
+            Ce = 3 * Cin if x3 else Cin
+
             def pack16():
-                w = weight.detach().reshape(Cout, Cin, 9).permute(2, 0, 1)
-                z = torch.zeros(9, 16, Cin, device=w.device, dtype=torch.bfloat16)
-                z[:, :Cout, :] = w.to(torch.bfloat16)
+                w = weight.detach().reshape(Cout, Cin, 9)
+                w = split3_weights(w) if x3 else w.permute(2, 0, 1).to(torch.bfloat16)     # [9][Cout][Ce]
+                z = torch.zeros(9, 16, Ce, device=w.device, dtype=torch.bfloat16)
+                z[:, :Cout, :] = w
                 return z
-            wp = self.pack((id(weight), "tc16"), [weight], pack16)
-            self.call("conv_tc2", x, wp, self.param(bias), None, out_nchw, PDAE_F32, None, B, H, W, Cin, 16, 3, Cout, 0, flops=fl)
+            wp = self.pack((id(weight), "tc16_x3" if x3 else "tc16"), [weight], pack16)
+            self.call("conv_tc2", x, wp, self.param(bias), None, out_nchw, PDAE_F32, None, B, H, W, Ce, 16, 3, Cout, 0, flops=fl)
         elif Cout <= 4 and Cin % 4 == 0:
             assert x.dtype in (torch.float32, torch.bfloat16)
 
@@ -553,7 +583,9 @@ class Plan:
         """dtype the normalised input of an image-head conv should be produced in (bf16 only if a bf16 kernel takes it)."""
         if not self.tc:
             return torch.float32
-        if (self.v2 and Cout <= 16 and self.use_tc(Cin, 64, 3, 1, H, W)) or (Cout <= 4 and Cin % 4 == 0):
+        if self.v2 and Cout <= 16 and self.use_tc(Cin, 64, 3, 1, H, W):
+            return torch.bfloat16
+        if Cout <= 4 and Cin % 4 == 0 and not self.x3:      # CUDA-core small-N head: plain bf16 input (fp32 in the x3 mode)
             return torch.bfloat16
         return torch.float32
 
@@ -608,6 +640,22 @@ class Plan:
                  B, H, W, act_dtype, raw_dtype=None) -> Tuple[Buf, Optional[Buf]]:
         C = C1 + C2
         Ho, Wo = (2 * H, 2 * W) if resample == RESAMPLE_UP2 else ((H // 2, W // 2) if resample == RESAMPLE_DOWN2 else (H, W))
+        if self.x3 and act_dtype == torch.bfloat16:
+            # split-operand mode: [hi | lo | hi] bf16 blocks for the tensor-core convs (fp32 sources only)
+            assert src1.dtype == torch.float32 and (src2 is None or src2.dtype == torch.float32)
+            if isinstance(ab, CoefSpec):
+                c, ab = ab, self.new((B, 2, C), torch.float32, "gn_ab")
+                self.call("gn_coef_ch", c.stats1, c.C1, c.stats2, c.C2, c.gamma, c.beta, c.B, c.HW, ctypes.c_float(1e-5),
+                          c.emb, c.emb_ld, c.embz, c.embz_ld, ab, _STREAM)
+            act = self.new((B, Ho, Wo, 3 * C), torch.bfloat16, "act_x3")
+            act.split3 = True
+            raw = None
+            if raw_dtype is not None:
+                raw = self.new((B, Ho, Wo, 3 * C if raw_dtype == torch.bfloat16 else C), raw_dtype, "raw_x3")
+                raw.split3 = raw_dtype == torch.bfloat16
+            self.call("gn_apply_split3", src1, C1, src2, C2, ab, int(silu), resample, B, H, W, act, raw,
+                      _DT[raw_dtype] if raw_dtype is not None else PDAE_F32, _STREAM)
+            return act, raw
         act = self.new((B, Ho, Wo, C), act_dtype, "act")
         raw = self.new((B, Ho, Wo, C), raw_dtype, "raw") if raw_dtype is not None else None
         if isinstance(ab, CoefSpec):

@@ -281,7 +281,7 @@ class _ResBase(PlannedModule):
         act1, raw = P.gn_apply(x.b1, x.C1, x.b2, x.C2, ab1, silu=True, resample=rs, B=B, H=H, W=W,
                                act_dtype=torch.bfloat16 if tc1 else torch.float32, raw_dtype=raw_dtype)
         # h only feeds GroupNorm-2: with the v2 kernel it is stored in bf16 and its statistics come from the epilogue
-        h_bf16 = tc1 and P.fused_stats
+        h_bf16 = tc1 and P.fused_stats and not P.x3     # (the split-operand mode keeps every conv output in fp32)
         h = P.new((B, H2, W2, Co), torch.bfloat16 if h_bf16 else torch.float32, "res_h")
         hs = P.conv(act1, conv1.weight, conv1.bias, h, B=B, H=H2, W=W2, Cin=C, Cout=Co, k=3, want_stats=True)
 

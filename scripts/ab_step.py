@@ -1,5 +1,5 @@
 """Graph-replay time of one ShiftUNet decoder step under the current env knobs (A/B aid: run variants as separate
-processes on the SAME box, alternating).  usage: [ENV=..] python scripts/ab_step.py [workload] [batch] [reps]"""
+processes on the SAME box, alternating).  usage: [ENV=..] python scripts/ab_step.py [workload] [batch] [reps] [precision]"""
 import os
 import sys
 
@@ -14,8 +14,9 @@ from pdae_b200.utils.synth import fill_module_, synth_normal
 wl = sys.argv[1] if len(sys.argv) > 1 else "celeba64"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 30
+prec = sys.argv[4] if len(sys.argv) > 4 else "bf16"
 cfg, size = WORKLOADS[wl][0], WORKLOADS[wl][1]
-pdae_b200.set_default_precision("bf16")
+pdae_b200.set_default_precision(prec)
 dev = torch.device("cuda")
 dec = fill_module_(ShiftUNet(latent_dim=512, **cfg), seed=0).eval().to(dev)
 x = synth_normal((B, 3, size, size), 1).to(dev)
@@ -41,4 +42,4 @@ for _ in range(3):
     best = min(best, ms)
     tot += ms / 3
 knobs = {k: v for k, v in os.environ.items() if k.startswith("PDAE_")}
-print(f"ab_step {wl} B={B}: {tot:.3f} ms/step avg, {best:.3f} best, {plan.n_launch} launches  {knobs}")
+print(f"ab_step {wl} B={B} {prec}: {tot:.3f} ms/step avg, {best:.3f} best, {plan.n_launch} launches  {knobs}")

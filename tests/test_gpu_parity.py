@@ -1,6 +1,6 @@
 """CUDA path vs the fixtures recorded from the real reference and vs the CPU oracle (same seeded inputs).
 
-fp32 mode: rtol 1e-3 / atol 1e-4 (BASELINE.json north_star).  bf16 tensor-core mode (stated tolerance): relative L2
+fp32 mode and the split-operand tensor-core mode "bf16x3": rtol 1e-3 / atol 1e-4 (BASELINE.json north_star).  bf16 tensor-core mode (stated tolerance): relative L2
 error <= 2e-2 and elementwise |err| <= 5e-2 * max|ref| -- bf16 operands carry 8 mantissa bits; accumulation, GroupNorm
 statistics, the residual stream and the DDIM update stay fp32."""
 import pytest
@@ -16,7 +16,9 @@ FP32 = dict(rtol=1e-3, atol=1e-4)
 
 
 def check(got, want, precision, what):
-    if precision == "fp32":
+    if precision in ("fp32", "bf16x3"):   # the split-operand tensor-core mode is held to the fp32 tolerance
+        if precision == "bf16x3":
+            print(f"[bf16x3] {what}: rel-L2 {rel_l2(got, want):.3e}")
         assert_close(got, want, what=what, **FP32)
     else:
         r = rel_l2(got, want)
@@ -29,7 +31,7 @@ def _cuda(d):
     return {k: v.cuda() for k, v in d.items()}
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16x3"])
 @pytest.mark.parametrize("name", golden_names("block_"))
 def test_blocks(name, precision):
     cfg, g = load_golden(name)
@@ -49,7 +51,7 @@ def test_timestep_embedding():
     assert_close(timestep_embedding(g["t"].cuda(), 33), g["e33"], rtol=1e-6, atol=2e-6, what="e33")
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16x3"])
 @pytest.mark.parametrize("name", golden_names("model_"))
 def test_models(name, precision):
     cfg, g = load_golden(name)
@@ -107,7 +109,7 @@ def test_oracle_agrees_on_gpu_inputs_at_larger_shape():
     with torch.no_grad():
         eps_ref, grad_ref = O.shiftunet_forward(cases.sd_of(m), cfg, x, t, z)
     m = m.cuda()
-    for precision in ("fp32", "bf16"):
+    for precision in ("fp32", "bf16", "bf16x3"):
         m.precision = precision
         with torch.no_grad():
             eps, grad = m(x.cuda(), t.cuda(), z.cuda())
