@@ -85,3 +85,23 @@ def test_prologue_ops_are_split_out_and_their_outputs_must_be_private():
     assert P._pro_idx == [0] and P._main_idx == [1, 2] and P.n_launch == 2
     with pytest.raises(AssertionError):
         build(False).finalize()
+
+
+def test_split3_weight_packing_reconstructs_fp32_products():
+    """"bf16x3" mode: weights [W_hi | W_hi | W_lo] against activations [a_hi | a_lo | a_hi] reproduce a*W to ~2^-16."""
+    from pdae_b200.engine import split3_weights
+    torch.manual_seed(0)
+    Cout, Cin, taps = 8, 16, 9
+    w = torch.randn(Cout, Cin, taps)
+    p = split3_weights(w)
+    assert p.shape == (taps, Cout, 3 * Cin) and p.dtype == torch.bfloat16
+    a = torch.randn(5, Cin)
+    a_hi = a.to(torch.bfloat16)
+    a_lo = (a - a_hi.float()).to(torch.bfloat16)
+    a3 = torch.cat([a_hi, a_lo, a_hi], dim=1).double()                 # what gn_apply_split3 writes
+    for t in (0, 4, 8):
+        got = a3 @ p[t].double().t()
+        want = a.double() @ w[:, :, t].double().t()
+        plain = a_hi.double() @ w[:, :, t].to(torch.bfloat16).double().t()
+        err, err_plain = (got - want).abs().max().item(), (plain - want).abs().max().item()
+        assert err < 2e-4 * want.abs().max().item() and err < err_plain / 50, (err, err_plain)

@@ -50,10 +50,12 @@ def test_ddim_update_matches_oracle_bitwise():
             assert_close(got, ref, rtol=1e-6, atol=1e-6, what=f"ddim {direction} shift={g_ is not None}")
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16x3"])
 def test_loops(precision):
     from pdae_b200.utils.synth import synth_images, synth_normal
-    tol = dict(rtol=1e-3, atol=2e-4) if precision == "fp32" else None
+    # chained random-weight steps amplify per-forward differences ~100x per 10 steps: fp32 (1e-6 per forward) gets atol 2e-4,
+    # the split-operand tensor-core mode (1e-5 per forward, test_gpu_parity) atol 2e-3
+    tol = dict(rtol=1e-3, atol=2e-4) if precision == "fp32" else (dict(rtol=1e-3, atol=2e-3) if precision == "bf16x3" else None)
     d = gd()
     xT, x0 = synth_normal((2, 3, 16, 16), 25).cuda(), synth_images(2, 3, 16, 26).cuda()
 
@@ -89,7 +91,7 @@ def test_loops(precision):
             assert_close(slow, fast, rtol=1e-3, atol=2e-4, what="generic vs fast loop")
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16x3"])
 def test_autoencoding_and_latent(precision):
     from pdae_b200.utils.synth import synth_images, synth_normal
     d = gd()
@@ -104,12 +106,15 @@ def test_autoencoding_and_latent(precision):
     if precision == "fp32":
         # 20 chained steps on random weights amplify the ~1e-6 per-forward fp32 differences by ~100x per 10 steps
         assert_close(rec, g["recon"], rtol=1e-3, atol=2e-3, what="autoencode")
+    elif precision == "bf16x3":
+        assert rel_l2(rec, g["recon"]) < 2e-2, rel_l2(rec, g["recon"])   # 1e-5 per forward, amplified over 20 steps
     else:
         assert rel_l2(rec, g["recon"]) < 0.35
     # reconstruction-MSE metric of the reference (metric/utils.py:62-63, images scaled to [0,1]); the 1e-5 bound of
     # BASELINE.json is asserted in fp32 mode; in bf16 mode on random (non-autoencoding) weights we assert 2e-2
     mse = lambda a, b: float((((a.cpu() + 1) / 2 - (b.cpu() + 1) / 2) ** 2).mean())
-    assert abs(mse(rec, x0) - mse(g["recon"], x0)) < (1e-5 if precision == "fp32" else 2e-2)
+    print(f"[{precision}] recon-MSE delta vs reference: {abs(mse(rec, x0) - mse(g['recon'], x0)):.3e}")
+    assert abs(mse(rec, x0) - mse(g["recon"], x0)) < {"fp32": 1e-5, "bf16x3": 1e-4, "bf16": 2e-2}[precision]
 
     cfg, g = load_golden("loop_latent_ddim10")
     m, _ = cases.model_case({"kind": "mlp", "cfg": cfg["cfg"]})
