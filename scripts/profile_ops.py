@@ -1,5 +1,5 @@
 """Per-op device times of one ShiftUNet decoder step (CUDA events around every launch; warm L2, no graph).
-usage: python scripts/profile_ops.py [workload] [batch] [top_n]"""
+usage: python scripts/profile_ops.py [workload] [batch] [top_n] [precision]"""
 import os
 import sys
 
@@ -14,8 +14,9 @@ from pdae_b200.utils.synth import fill_module_, synth_normal
 wl = sys.argv[1] if len(sys.argv) > 1 else "celeba64"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+prec = sys.argv[4] if len(sys.argv) > 4 else "bf16"
 cfg, size = WORKLOADS[wl][0], WORKLOADS[wl][1]
-pdae_b200.set_default_precision("bf16")
+pdae_b200.set_default_precision(prec)
 dev = torch.device("cuda")
 dec = fill_module_(ShiftUNet(latent_dim=512, **cfg), seed=0).eval().to(dev)
 x = synth_normal((B, 3, size, size), 1).to(dev)
