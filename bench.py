@@ -295,7 +295,7 @@ def main():
                                     "frac": round(value * flop_img / 1e12 / world / peak_tf, 4), "peak_source": peak_src},
         "roofline": roof, "kernels_per_decoder_step": kinds,
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # the CPU baseline and the parity probe are an N=1, rank-0 leg
         b = 8 if size <= 64 else 2
         ips, cores, t_step, t_enc = cpu_sample(cfg, size, enc_kind, enc_size, S, b, n_steps=3)
         line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
