@@ -23,7 +23,7 @@ torch.einsum / torch.softmax, exactly the calls at model/module.py:21-63,169,
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 import torch

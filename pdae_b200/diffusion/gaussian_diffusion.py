@@ -8,7 +8,6 @@ pdae_noise_p_sample, pdae_ddim_step); respaced DDIM objects are cached per style
 """
 from __future__ import annotations
 
-import ctypes
 import math
 from functools import partial
 from typing import Dict, Tuple

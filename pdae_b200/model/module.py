@@ -14,7 +14,7 @@ from __future__ import annotations
 import ctypes
 import os
 import math
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, Optional, Tuple
 
 import torch
 import torch.nn as nn

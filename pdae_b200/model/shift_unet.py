@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 
 from ..engine import Plan
-from .module import PlannedModule, Slots, Src, TimestepSequential, conv_nd, linear
+from .module import PlannedModule, Slots, TimestepSequential, conv_nd, linear
 from .unet import EmbBank, emit_head, emit_stem, emit_time_embed, level_plan, make_head, make_middle, make_stage, res_blocks_of
 
 

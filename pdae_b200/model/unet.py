@@ -6,7 +6,7 @@ Constructor keywords, attribute names (``time_embed``, ``label_emb``, ``input_bl
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, List, Optional, Tuple
+from typing import Dict, List, Tuple
 
 import torch
 import torch.nn as nn

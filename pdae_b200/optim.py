@@ -13,7 +13,7 @@ the reference trainer (`'optimizer'` entry) load unchanged.  No CPU fallback.
 from __future__ import annotations
 
 import ctypes
-from typing import Dict, Iterable, Optional
+from typing import Dict, Optional
 
 import numpy as np
 import torch

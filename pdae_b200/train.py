@@ -17,9 +17,8 @@ from typing import Callable, Dict, List, Optional, Tuple
 import torch
 import torch.nn as nn
 
-from . import _native
 from .engine import Buf, BufView, Plan, RESAMPLE_NONE, _STREAM
-from .model.module import AttentionBlock, ResBlock, ResBlockShift, Src
+from .model.module import AttentionBlock, Src
 
 F32 = ctypes.c_float
 
