@@ -469,7 +469,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               const int cur = r0 / ppi;
               if (b0 + cur < p.B) {
                 float* dst = p.ch_stats + ((long long)(b0 + cur) * p.Cout + n0 + c * CW + col) * 2;
-                if (ppi == CW) {   // the only contributor to this (image, channel): plain store, no atomic
+                if (ppi == CW && p.tiles_x * p.tiles_y == 1) {   // whole image inside this tile and this thread covers all of
+                                                                 // its rows: the only contributor -> plain store, no atomic
                   *reinterpret_cast<float2*>(dst) = make_float2(s, qq);
                 } else {
                   atomicAdd(dst, s);

@@ -133,7 +133,8 @@ def test_head_conv_tensor_core(shape):
     assert_close(out.tensor, ref, rtol=2e-3, atol=2e-3, what=f"tc head {shape}")
 
 
-@pytest.mark.parametrize("shape", [(2, 16, 16, 128, 64, 192), (3, 8, 8, 256, 256, 512), (1, 64, 64, 64, 64, 128)])
+@pytest.mark.parametrize("shape", [(2, 16, 16, 128, 64, 192), (3, 8, 8, 256, 256, 512), (1, 64, 64, 64, 64, 128),
+                                   (3, 24, 24, 64, 64, 64), (5, 12, 12, 64, 128, 64)])   # several images per tile AND several tiles per image
 def test_fused_skip_conv(shape):
     """conv3x3(act) + conv1x1(x) + biases in ONE tensor-core launch (skip conv folded in as extra K blocks) vs torch."""
     from pdae_b200.engine import Plan

@@ -134,3 +134,24 @@ def test_attention_tensor_core(C, heads, new_order):
         check(y, ref, precision, f"attention C={C} heads={heads} new={new_order}")
     plan = [v for k, v in m._plans().items() if k[1] == "bf16"][0][0]
     assert "gemm_tc2" in [op[0] for op in plan.ops], "tensor-core attention path not taken"
+
+
+@pytest.mark.parametrize("size,batch", [(24, 3), (48, 1), (40, 2)])
+def test_ragged_resolutions_and_batches(size, batch):
+    """Resolutions that are not powers of two (24 -> 12 -> 6, 48 -> 24 -> 12, 40 -> 20 -> 10: small or single-row tensor-core
+    tiles, several images per tile with a masked batch tail, CUDA-core fallbacks) and odd batches, every precision mode."""
+    from pdae_b200.model.shift_unet import ShiftUNet
+    from pdae_b200.utils.synth import fill_module_, synth_normal
+    cfg = dict(input_channel=3, base_channel=64, channel_multiplier=[1, 2, 2], num_residual_blocks_of_a_block=1,
+               attention_resolutions=[2], num_heads=2, head_channel=-1, use_new_attention_order=False, dropout=0.0, latent_dim=128)
+    m = fill_module_(ShiftUNet(**cfg), seed=41).eval()
+    x, z = synth_normal((batch, 3, size, size), 42), synth_normal((batch, 128), 43)
+    t = torch.tensor([5, 500, 999][:batch], dtype=torch.long)
+    eps_ref, grad_ref = O.shiftunet_forward(cases.sd_of(m), cfg, x, t, z)
+    m = m.cuda()
+    for precision in ("fp32", "bf16x3", "bf16"):
+        m.precision = precision
+        with torch.no_grad():
+            eps, grad = m(x.cuda(), t.cuda(), z.cuda())
+        check(eps, eps_ref, precision, f"{size}x{size} B={batch} eps")
+        check(grad, grad_ref, precision, f"{size}x{size} B={batch} grad")
