@@ -482,6 +482,8 @@ class Plan:
     def use_tc(self, Cin: int, Cout: int, k: int, stride: int, H: int, W: int) -> bool:
         if not self.tc or stride != 1 or k not in (1, 3) or Cin % 64 or Cout % 64:
             return False
+        if not self.v2 and ((H & (H - 1)) or (W & (W - 1))):
+            return False   # the legacy v1 kernel (PDAE_TC_V1=1, A/B aid) only tiles power-of-two images
         tw = 1
         while tw * 2 <= 128 and W % (tw * 2) == 0:
             tw *= 2

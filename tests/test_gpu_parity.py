@@ -133,7 +133,8 @@ def test_attention_tensor_core(C, heads, new_order):
             y = m(x.cuda())
         check(y, ref, precision, f"attention C={C} heads={heads} new={new_order}")
     plan = [v for k, v in m._plans().items() if k[1] == "bf16"][0][0]
-    assert "gemm_tc2" in [op[0] for op in plan.ops], "tensor-core attention path not taken"
+    if plan.v2:   # (the legacy v1 kernel, PDAE_TC_V1=1, has no batched-GEMM mode: CUDA-core attention there)
+        assert any(op[0].startswith("gemm_tc2") for op in plan.ops), "tensor-core attention path not taken"
 
 
 @pytest.mark.parametrize("size,batch", [(24, 3), (48, 1), (40, 2)])
