@@ -494,8 +494,10 @@ class Plan:
 
     def conv(self, x: Buf, weight: torch.Tensor, bias: Optional[torch.Tensor], out: Buf, *, B, H, W, Cin, Cout, k=3,
              stride=1, pad=None, residual: Optional[Buf] = None, in_nchw=False, out_nchw=False, a_silu=False,
-             wkey=None, want_stats=False, bn_override=0, skip=None) -> Optional[Buf]:
+             wkey=None, want_stats=False, bn_override=0, skip=None, w_transform=None) -> Optional[Buf]:
         """weight: nn-style [Cout, Cin, k, k] / [Cout, Cin, 1] / [Cout, Cin] parameter.
+        w_transform (tensor-core path only): maps the detached parameter to the [Cout, Cin, k, k] tensor actually convolved
+        with (e.g. the transposed, flipped weights of a dgrad) -- the packed copy still tracks the PARAMETER's version.
         Returns the per-channel (sum, sum^2) buffer [B][Cout][2] if the tensor-core epilogue produced one."""
         pad = k // 2 if pad is None else pad
         bias_b = self.param(bias)
@@ -503,12 +505,13 @@ class Plan:
         if x.dtype == torch.bfloat16 and self.use_tc(Cin, Cout, k, stride, H, W) and not (in_nchw or out_nchw or a_silu):
             x3 = bool(x.split3)
             fl = 2.0 * B * H * W * Cout * Cin * k * k     # algorithmic (the x3 mode issues 3x the MMAs for it)
+            wsrc = (lambda: w_transform(weight.detach())) if w_transform is not None else (lambda: weight.detach())
             if x3:   # activation blocks [a_hi | a_lo | a_hi] x weight blocks [W_hi | W_hi | W_lo]
-                wp = self.pack((wkey, "tc_x3"), [weight], lambda: split3_weights(weight.detach().reshape(Cout, Cin, k * k)))
+                wp = self.pack((wkey, "tc_x3"), [weight], lambda Cin=Cin: split3_weights(wsrc().reshape(Cout, Cin, k * k)))
                 Cin = 3 * Cin
             else:
                 wp = self.pack((wkey, "tc"), [weight],
-                               lambda: weight.detach().reshape(Cout, Cin, k * k).permute(2, 0, 1).to(torch.bfloat16))
+                               lambda: wsrc().reshape(Cout, Cin, k * k).permute(2, 0, 1).to(torch.bfloat16))
             if not self.v2:
                 assert out.dtype == torch.float32
                 self.call("conv_tc", x, wp, bias_b, residual, out, B, H, W, Cin, Cout, k, flops=fl)
@@ -523,7 +526,8 @@ class Plan:
                 else:
                     assert sk_in.dtype == torch.bfloat16 and bool(sk_in.split3) == x3
                 if x3:
-                    w2 = self.pack((id(sw), "tc_skip_x3"), [sw], lambda: split3_weights(sw.detach().reshape(Cout, Cin2, 1))[0])
+                    w2 = self.pack((id(sw), "tc_skip_x3"), [sw],
+                                   lambda Cin2=Cin2: split3_weights(sw.detach().reshape(Cout, Cin2, 1))[0])   # (bind the logical Cin2: it is tripled below, and this runs again on every weight refresh)
                     Cin2 = 3 * Cin2
                 else:
                     w2 = self.pack((id(sw), "tc_skip"), [sw], lambda: sw.detach().reshape(Cout, Cin2).to(torch.bfloat16))

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
@@ -48,6 +49,12 @@ def draw_dropout_masks(plan: Plan) -> None:
         mask.tensor.bernoulli_(1.0 - p)
 
 
+def bwd_plan(dev) -> Plan:
+    """Backward plans are fp32 CUDA-core plans; with PDAE_TRAIN_TC_DGRAD=1 (experimental, off by default) they are
+    split-operand tensor-core plans so that eligible data gradients run on `conv_tc2` (see Backward.conv)."""
+    return Plan(dev, "bf16x3" if os.environ.get("PDAE_TRAIN_TC_DGRAD", "0") == "1" else "fp32")
+
+
 class Backward:
     """Emission helpers for the backward plan (fp32)."""
 
@@ -55,6 +62,7 @@ class Backward:
         self.P = BP
         self.sink = sink
         self._fixed: Dict[int, Buf] = {}
+        self.tc_dgrad = bool(getattr(BP, "x3", False))
 
     def fx(self, b):
         if b is None:
@@ -87,6 +95,15 @@ class Backward:
                 self.sink.add(bias, db, Cout, lambda t: t)
         if not need_dx:
             return None
+        if self.tc_dgrad and stride == 1 and k in (1, 3) and pad == k // 2 and not in_nchw and P.use_tc(Cout, Cin, k, 1, H, W):
+            # dgrad of a stride-1 "same" conv = conv of dy with the transposed, spatially flipped weights: on the tensor
+            # cores in the split-operand (fp32-grade) mode -- dy is split [hi | lo | hi], W' packed [W'_hi | W'_hi | W'_lo]
+            dy3, _ = P.gn_apply(dy, Cout, None, 0, None, silu=False, resample=RESAMPLE_NONE, B=B, H=H, W=W,
+                                act_dtype=torch.bfloat16)
+            dx = P.new((B, H, W, Cin), torch.float32, "dx")
+            P.conv(dy3, weight, None, dx, B=B, H=H, W=W, Cin=Cout, Cout=Cin, k=k, wkey=(id(weight), "dgrad"),
+                   w_transform=lambda w, Cout=Cout, Cin=Cin, k=k: w.reshape(Cout, Cin, k, k).flip(2, 3).transpose(0, 1).contiguous())
+            return dx
         wt = P.pack((id(weight), "tco"), [weight], lambda: weight.detach().reshape(Cout, Cin, kk).permute(2, 0, 1).float())
         dx = P.new((B, H, W, Cin), torch.float32, "dx")
         P.call("conv2d_dgrad_simt", dy, wt, dx, B, H, W, Cin, Cout, k, stride, pad, 0, _STREAM)
@@ -260,7 +277,7 @@ class ShiftUNetTrainer:
         self.fwd = P
 
         # ---------------- backward plan ----------------
-        BP = Plan(dev, "fp32")
+        BP = bwd_plan(dev)
         self.sink = GradSink()
         bw = Backward(BP, self.sink)
         self.d_grad = BP.new((B, net.input_channel, H, W), torch.float32, "d_shift_nchw")
@@ -385,7 +402,7 @@ class UNetTrainer:
         P.finalize()
         self.fwd = P
 
-        BP = Plan(dev, "fp32")
+        BP = bwd_plan(dev)
         self.sink = GradSink()
         bw = Backward(BP, self.sink)
         self.d_out = BP.new((B, net.output_channel, H, W), torch.float32, "d_eps_nchw")
@@ -523,7 +540,7 @@ class EncoderTrainer:
         P.finalize()
         self.fwd = P
 
-        BP = Plan(dev, "fp32")
+        BP = bwd_plan(dev)
         self.sink = GradSink()
         bw = Backward(BP, self.sink)
         L = enc.latent_dim
@@ -652,7 +669,7 @@ class MLPTrainer:
         P.finalize()
         self.fwd = P
 
-        BP = Plan(dev, "fp32")
+        BP = bwd_plan(dev)
         self.sink = GradSink()
         bw = Backward(BP, self.sink)
         self.d_out = BP.new((B, D), torch.float32, "d_eps")
