@@ -521,6 +521,87 @@ class DiffusionOracle:
         return z
 
 
+    # ---- glue around the hot path (rows a20, a22, a24); random draws are passed in by the caller ----
+    def trajectory_interpolation(self, style, decoder, z_1, z_2, x_T, alpha):
+        """DDIM.shift_ddim_trajectory_interpolation (ddim.py:149-174): epsilon from the z_1 call, gradient mixed."""
+        tabs, tmap, S = self._ddim(style)
+        x = x_T
+        for i in reversed(range(1, S + 1)):
+            t = torch.full((x.shape[0],), i, dtype=torch.long)
+            eps, g1 = decoder(x, tmap[t], z_1)
+            _, g2 = decoder(x, tmap[t], z_2)
+            x = ddim_update(tabs, x, t, eps, (1.0 - alpha) * g1 + alpha * g2, "sample")
+        return x
+
+    def predicted_x_0(self, x_t, t, eps):
+        """predicted_noise_to_predicted_x_0 (gaussian_diffusion.py:156-159)."""
+        return _at(self.tabs["sqrt_recip_alphas_cumprod"], t, x_t) * x_t - _at(self.tabs["sqrt_recip_alphas_cumprod_m1"], t, x_t) * eps
+
+    def q_posterior_mean(self, x_0, x_t, t):
+        """gaussian_diffusion.py:105-108."""
+        return _at(self.tabs["x_0_posterior_mean_x_0_coef"], t, x_t) * x_0 + _at(self.tabs["x_0_posterior_mean_x_t_coef"], t, x_t) * x_t
+
+    def x_0_clip_p_sample(self, x_t, t, eps, noise, learned_range=None, clip_x_0=True):
+        """gaussian_diffusion.py:130-146 with the randn drawn by the caller."""
+        x0 = self.predicted_x_0(x_t, t, eps)
+        if clip_x_0:
+            x0 = x0.clamp(-1, 1)
+        mean = self.q_posterior_mean(x0, x_t, t)
+        lo = _at(self.tabs["posterior_log_variance_clipped"], t, x_t)
+        logvar = lo if learned_range is None else lo + (learned_range + 1) / 2 * (_at(torch.log(self.tabs["betas"]), t, x_t) - lo)
+        mask = (1 - (t == 0).float()).reshape([x_t.shape[0]] + [1] * (x_t.dim() - 1))
+        return mean + mask * (0.5 * logvar).exp() * noise
+
+    def ddpm_sample(self, net, x_T, randn, z=None, condition=None):
+        """regular_ddpm_sample (:216-229) when z is None, representation_learning_ddpm_sample (:257-270) otherwise;
+        `randn(shape)` supplies the per-step noise in the reference's draw order."""
+        img, C = x_T, x_T.shape[1]
+        for i in reversed(range(self.timesteps)):
+            t = torch.full((img.shape[0],), i, dtype=torch.long)
+            lr = None
+            if z is None:
+                out = net(img, t, condition)
+                eps, lr = (torch.split(out, C, dim=1) if out.shape[1] == 2 * C else (out, None))
+            else:
+                e, g = net(img, t, z)
+                eps = e + _at(self.tabs["shift_coef"], t, img) * g
+            img = self.noise_p_sample(img, t, eps, randn(img.shape), lr)
+        return img
+
+    def gap_measure(self, encoder, decoder, x_0, rand_like):
+        """representation_learning_gap_measure (:292-318) -- uniform 'noise' as in the reference."""
+        z = encoder(x_0)
+        gp, ga = [], []
+        for i in reversed(range(self.timesteps)):
+            t = torch.full((x_0.shape[0],), i, dtype=torch.long)
+            x_t = self.q_sample(x_0, t, rand_like(x_0))
+            eps, grad = decoder(x_t, t, z)
+            true = self.q_posterior_mean(x_0, x_t, t)
+            m1 = self.q_posterior_mean(self.predicted_x_0(x_t, t, eps), x_t, t)
+            m2 = self.q_posterior_mean(self.predicted_x_0(x_t, t, eps + _at(self.tabs["shift_coef"], t, x_0) * grad), x_t, t)
+            gp.append(float(torch.mean((true - m1) ** 2)))
+            ga.append(float(torch.mean((true - m2) ** 2)))
+        return gp, ga
+
+    def denoise_one_step(self, encoder, decoder, x_0, timestep_list, noise):
+        """representation_learning_denoise_one_step (:320-334)."""
+        t = torch.tensor(timestep_list, dtype=torch.long)
+        x_t = self.q_sample(x_0, t, noise)
+        eps, grad = decoder(x_t, t, encoder(x_0))
+        return self.predicted_x_0(x_t, t, eps), self.predicted_x_0(x_t, t, eps + _at(self.tabs["shift_coef"], t, x_0) * grad)
+
+    def latent_diffusion_sample(self, latent_style, dec_style, latent_fn, decoder, x_T, z_T, mean, std):
+        """latent_diffusion_sample (:400-415) with z_T given (already drawn, not yet clamped)."""
+        z = self.latent_ddim_sample(latent_style, latent_fn, z_T.clamp(-1.0, 1.0))
+        return self.representation_learning_ddim_sample(dec_style, decoder, x_T, z * std + mean, stop_percent=0.3)
+
+    def manipulation_sample(self, style, classifier_weight, encoder, decoder, x_0, x_T, mean, std, class_id, scale):
+        """manipulation_sample (:435-443)."""
+        zn = (encoder(x_0) - mean) / std
+        zn = zn + scale * math.sqrt(512) * F.normalize(classifier_weight[class_id][None, :], dim=1)
+        return self.representation_learning_ddim_sample(style, decoder, x_T, zn * std + mean, stop_percent=0.0)
+
+
 # ------------------------------------------------------------------------------------------------
 # Caller-side steps (SURVEY.md §8(f)): optimizer + EMA, wire formats, metrics
 

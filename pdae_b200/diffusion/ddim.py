@@ -25,6 +25,19 @@ def _stream(dev):
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
+def _f32(t):
+    """The elementwise kernels read raw fp32 pointers: promote anything else (half tensors under AMP, double images from a
+    dataset) the way the reference's type-promoting torch arithmetic would, instead of reinterpreting the bytes."""
+    return None if t is None else t.to(torch.float32).contiguous()
+
+
+def _t64(t, B, what):
+    t = t.to(torch.int64).contiguous()
+    if t.numel() != B:
+        raise ValueError(f"{what}: t must hold one timestep per sample ({B}), got {tuple(t.shape)}")
+    return t
+
+
 class DDIM:
     # replay each network step as one CUDA graph in the native fast path (PDAE_NO_GRAPH=1 disables, e.g. under ncu)
     use_cuda_graph = os.environ.get("PDAE_NO_GRAPH", "0") != "1"
@@ -53,11 +66,12 @@ class DDIM:
     def _update(self, x_t, t, eps, grad, direction, out=None):
         if not x_t.is_cuda:
             raise _native.NativeError("DDIM: CUDA tensors required (no CPU fallback)")
-        x_t, eps = x_t.contiguous(), eps.contiguous()
-        grad = grad.contiguous() if grad is not None else None
-        t = t.to(torch.int64).contiguous()
-        out = torch.empty_like(x_t) if out is None else out
+        x_t, eps, grad = _f32(x_t), _f32(eps), _f32(grad)
         B = x_t.shape[0]
+        t = _t64(t, B, "DDIM update")
+        if eps.shape != x_t.shape or (grad is not None and grad.shape != x_t.shape):
+            raise ValueError(f"DDIM update: x_t {tuple(x_t.shape)}, eps {tuple(eps.shape)} and grad must have one shape")
+        out = torch.empty_like(x_t) if out is None else out
         tab = self.alphas_cumprod_prev if direction == "sample" else self.alphas_cumprod_next
         rc = _native.lib().pdae_ddim_step(_ptr(x_t), _ptr(eps), _ptr(grad), _ptr(t), _ptr(self.sqrt_recip_alphas_cumprod),
                                           _ptr(self.sqrt_recip_alphas_cumprod_m1), _ptr(self.sqrt_one_minus_alphas_cumprod),
@@ -159,6 +173,16 @@ class DDIM:
             _, g2 = decoder(x_t, self.t_transform(t), z_2)
             x_t = self._update(x_t, t, eps, (1.0 - alpha) * g1 + alpha * g2, "sample")
         return x_t
+
+    def latent_ddim_sample(self, latent_denoise_fn, z_t, t):
+        """ddim.py:178-198 -- the unclamped single step (no caller in the reference uses it: its loop goes through
+        ddim_sample).  z_0 = A_t z_t - B_t eps;  z_prev = sqrt(abar_prev) z_0 + sqrt(1 - abar_prev) eps."""
+        s = z_t.shape
+        eps = latent_denoise_fn(z_t, self.t_transform(t))
+        z0 = self.extract_coef_at_t(self.sqrt_recip_alphas_cumprod, t, s) * z_t - \
+            self.extract_coef_at_t(self.sqrt_recip_alphas_cumprod_m1, t, s) * eps
+        ap = self.extract_coef_at_t(self.alphas_cumprod_prev, t, s)
+        return z0 * torch.sqrt(ap) + torch.sqrt(1.0 - ap) * eps
 
     def latent_ddim_sample_loop(self, latent_denoise_fn, z_T):
         """ddim.py:200-207 -- NB calls ddim_sample, i.e. WITH the clamp of the predicted z_0."""

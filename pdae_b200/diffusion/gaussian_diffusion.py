@@ -17,7 +17,7 @@ import torch
 import torch.nn.functional as F
 
 from .. import _native
-from .ddim import DDIM, _ptr, _stream
+from .ddim import DDIM, _f32, _ptr, _stream, _t64
 
 
 def _beta_schedule(kind: str, T: int) -> np.ndarray:
@@ -63,6 +63,17 @@ class GaussianDiffusion:
         self._ddim_cache: Dict[Tuple[str, int], DDIM] = {}
 
     # ---- helpers ------------------------------------------------------------------------------------
+    # Random draws of the sampling / training glue go through these three methods (same distributions and call order as
+    # the reference's torch.randn / randn_like / rand_like calls), so a parity test can substitute a seeded CPU stream.
+    def _randn(self, shape):
+        return torch.randn(tuple(shape), device=self.device)
+
+    def _randn_like(self, x):
+        return torch.randn_like(x)
+
+    def _rand_like(self, x):
+        return torch.rand_like(x)
+
     @staticmethod
     def extract_coef_at_t(schedule, t, x_shape):
         return torch.gather(schedule, -1, t).reshape([x_shape[0]] + [1] * (len(x_shape) - 1))
@@ -97,9 +108,12 @@ class GaussianDiffusion:
         """sqrt(abar_t) x_0 + sqrt(1 - abar_t) noise (:98-103)."""
         if not x_0.is_cuda:
             raise _native.NativeError("q_sample: CUDA tensors required (no CPU fallback)")
-        x_0, noise, t = x_0.contiguous(), noise.contiguous(), t.to(torch.int64).contiguous()
-        out = torch.empty_like(x_0)
+        x_0, noise = _f32(x_0), _f32(noise)
         B = x_0.shape[0]
+        t = _t64(t, B, "q_sample")
+        if noise.shape != x_0.shape:
+            raise ValueError(f"q_sample: x_0 {tuple(x_0.shape)} and noise {tuple(noise.shape)} must have one shape")
+        out = torch.empty_like(x_0)
         rc = _native.lib().pdae_q_sample(_ptr(x_0), _ptr(noise), _ptr(t), _ptr(self.sqrt_alphas_cumprod),
                                          _ptr(self.sqrt_one_minus_alphas_cumprod), _ptr(out), B, x_0.numel() // B,
                                          _stream(x_0.device))
@@ -114,14 +128,14 @@ class GaussianDiffusion:
     def noise_p_sample(self, x_t, t, predicted_noise, learned_range=None, noise=None):
         """DDPM ancestral step (:112-126).  ``noise`` defaults to torch.randn(shape) like the reference."""
         if noise is None:
-            noise = torch.randn(x_t.shape, device=self.device)
-        x_t, eps, noise = x_t.contiguous(), predicted_noise.contiguous(), noise.contiguous()
-        lr = learned_range.contiguous() if learned_range is not None else None
+            noise = self._randn(x_t.shape)
+        x_t, eps, noise = _f32(x_t), _f32(predicted_noise), _f32(noise)
+        lr = _f32(learned_range)
         if lr is not None and self._log_betas is None:
             self._log_betas = torch.log(self.betas)
-        t = t.to(torch.int64).contiguous()
-        out = torch.empty_like(x_t)
         B = x_t.shape[0]
+        t = _t64(t, B, "noise_p_sample")
+        out = torch.empty_like(x_t)
         rc = _native.lib().pdae_noise_p_sample(_ptr(x_t), _ptr(eps), _ptr(noise), _ptr(lr), _ptr(t),
                                                _ptr(self.noise_posterior_mean_x_t_coef),
                                                _ptr(self.noise_posterior_mean_noise_coef),
@@ -146,7 +160,7 @@ class GaussianDiffusion:
         logvar = self.learned_range_to_log_variance(learned_range, t) if learned_range is not None else \
             self.extract_coef_at_t(self.posterior_log_variance_clipped, t, s)
         mask = (1 - (t == 0).float()).reshape([s[0]] + [1] * (len(s) - 1))
-        return mean + mask * (0.5 * logvar).exp() * torch.randn(s, device=self.device)
+        return mean + mask * (0.5 * logvar).exp() * self._randn(s)
 
     def predicted_noise_to_predicted_x_0(self, x_t, t, predicted_noise):
         s = x_t.shape
@@ -179,7 +193,7 @@ class GaussianDiffusion:
     def regular_train_one_batch(self, denoise_fn, x_0, condition=None):
         B = x_0.shape[0]
         t = torch.randint(0, self.timesteps, (B,), device=self.device, dtype=torch.long)
-        noise = torch.randn_like(x_0)
+        noise = self._randn_like(x_0)
         pred = denoise_fn(self.q_sample(x_0=x_0, t=t, noise=noise), t, condition)
         return {"prediction_loss": self.p_loss(noise, pred)}
 
@@ -205,7 +219,7 @@ class GaussianDiffusion:
         s = x_0.shape
         z = encoder(x_0)
         t = torch.randint(0, self.timesteps, (s[0],), device=self.device, dtype=torch.long)
-        noise = torch.randn_like(x_0)
+        noise = self._randn_like(x_0)
         eps, grad = decoder(self.q_sample(x_0=x_0, t=t, noise=noise), t, z)
         target = eps + self.extract_coef_at_t(self.shift_coef, t, s) * grad
         return {"prediction_loss": self.p_loss(noise, target, weight=self.extract_coef_at_t(self.weight, t, s))}
@@ -243,7 +257,7 @@ class GaussianDiffusion:
         gap_pred, gap_ae = [], []
         for i in reversed(range(self.timesteps)):
             t = torch.full((s[0],), i, device=self.device, dtype=torch.long)
-            x_t = self.q_sample(x_0, t, torch.rand_like(x_0))
+            x_t = self.q_sample(x_0, t, self._rand_like(x_0))
             eps, grad = decoder(x_t, t, z)
             true_mean = self.q_posterior_mean(x_0, x_t, t)
             m1 = self.q_posterior_mean(self.predicted_noise_to_predicted_x_0(x_t, t, eps), x_t, t)
@@ -256,7 +270,7 @@ class GaussianDiffusion:
     def representation_learning_denoise_one_step(self, encoder, decoder, x_0, timestep_list):
         s = x_0.shape
         t = torch.tensor(timestep_list, device=self.device, dtype=torch.long)
-        x_t = self.q_sample(x_0, t, noise=torch.randn_like(x_0))
+        x_t = self.q_sample(x_0, t, noise=self._randn_like(x_0))
         eps, grad = decoder(x_t, t, encoder(x_0))
         eps_ae = eps + self.extract_coef_at_t(self.shift_coef, t, s) * grad
         return self.predicted_noise_to_predicted_x_0(x_t, t, eps), self.predicted_noise_to_predicted_x_0(x_t, t, eps_ae)
@@ -290,14 +304,14 @@ class GaussianDiffusion:
         z_0 = self.normalize(encoder(x_0).detach(), latents_mean, latents_std)
         s = z_0.shape
         t = torch.randint(0, cfg["timesteps"], (s[0],), device=self.device, dtype=torch.long)
-        noise = torch.randn_like(z_0)
+        noise = self._randn_like(z_0)
         z_t = self.extract_coef_at_t(cfg["sqrt_alphas_cumprod"], t, s) * z_0 + \
             self.extract_coef_at_t(cfg["sqrt_one_minus_alphas_cumprod"], t, s) * noise
         return {"prediction_loss": self.p_loss(noise, latent_denoise_fn(z_t, t), loss_type=cfg["loss_type"])}
 
     def latent_diffusion_sample(self, latent_ddim_style, decoder_ddim_style, latent_denoise_fn, decoder, x_T, latents_mean,
                                 latents_std):
-        z_T = torch.randn((x_T.shape[0], latent_denoise_fn.input_channel), device=self.device)
+        z_T = self._randn((x_T.shape[0], latent_denoise_fn.input_channel))
         z_T.clamp_(-1.0, 1.0)  # as in the reference: "may slightly improve sample quality"
         z = self._ddim(latent_ddim_style, self.latent_diffusion_config["alphas_cumprod"]).latent_ddim_sample_loop(
             latent_denoise_fn, z_T)

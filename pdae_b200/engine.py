@@ -90,9 +90,12 @@ class Packed:
     def _stamp(self):
         return tuple((s.data_ptr(), s._version) for s in self.sources)
 
-    def refresh(self) -> None:
+    def refresh(self, force: bool = False) -> None:
+        """Re-pack when a source's (storage, version) changed -- or unconditionally (`force`): writes through `p.data`
+        (the reference trainers' EMA loop, train_representation_learning.py:192-212) and raw-pointer writes bump no
+        version counter, so every sampling loop / graph capture forces one refresh (Plan.run_prologue)."""
         st = self._stamp()
-        if st != self.stamp:
+        if force or st != self.stamp:
             with torch.inference_mode(False), torch.no_grad():
                 self.tensor.copy_(self.fn())
             self.stamp = st
@@ -414,10 +417,15 @@ class Plan:
             if rc != 0:
                 _native.check(rc, "pdae_" + name)
 
-    def run_prologue(self) -> None:
-        """Launch only the step-invariant ops (after the loop's constant inputs have been written)."""
+    def refresh_packed(self, force: bool = False) -> None:
         for pk in self.packed:
-            pk.refresh()
+            pk.refresh(force)
+
+    def run_prologue(self) -> None:
+        """Launch only the step-invariant ops (after the loop's constant inputs have been written).  Called once per
+        sampling loop: the packed weight copies are re-derived unconditionally here (cost: one pass over the weights per
+        ~100 network evaluations), so weights updated through `.data` / raw pointers are never stale in a loop."""
+        self.refresh_packed(force=True)
         if self._pro_idx:
             self._launch_all(self._pro_idx)
 
@@ -436,8 +444,7 @@ class Plan:
         one launch instead of hundreds of ctypes calls.  Idempotent."""
         if self.graph is not None:
             return self
-        for pk in self.packed:
-            pk.refresh()
+        self.refresh_packed(force=True)
         self._launch_all(self._pro_idx)
         self._launch_all()  # warm-up outside capture (lazy module loading, cudaFuncSetAttribute, ...)
         torch.cuda.synchronize(self.device)

@@ -151,6 +151,20 @@ class PlannedModule(nn.Module):
             plans[key] = ent
         return ent
 
+    def invalidate_packed(self) -> None:
+        """Force every cached plan of this module (and of its sub-modules) to re-derive its packed weight copies on the
+        next run.  Needed only after an in-place weight update that bumps no autograd version counter outside a sampling
+        loop (`p.data.mul_()`, raw-pointer writes): versioned updates (optimizers, load_state_dict, copy_) are detected,
+        and every sampling loop re-packs once at its start anyway."""
+        for m in self.modules():
+            for cache_name in ("_plan_cache", "_train_cache"):
+                for ent in (m.__dict__.get(cache_name) or {}).values():
+                    plans = [ent[0]] if isinstance(ent, tuple) else [getattr(ent, "fwd", None), getattr(ent, "bwd", None)]
+                    for pl in plans:
+                        if pl is not None:
+                            for pk in pl.packed:
+                                pk.stamp = None
+
     def _device(self) -> torch.device:
         p = next(self.parameters())
         if not p.is_cuda:

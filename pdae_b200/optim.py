@@ -101,4 +101,8 @@ class FusedAdamEMA(torch.optim.Optimizer):
                                       self.ema_decay if do_ema else -1.0,
                                       ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
             _native.check(rc, "pdae_adam_ema_step")
+            # the kernel wrote p and the EMA copies through raw pointers: bump their autograd version counters so every
+            # packed (re-laid-out / bf16) weight copy keyed on (storage, version) is re-derived on its next use
+            touched = list(ps) + ([self._ema[p] for p in ps if p in self._ema] if do_ema else [])
+            torch.autograd.graph.increment_version(touched)
         return loss

@@ -233,7 +233,31 @@ class Backward:
 # ======================================================================================================================
 # ShiftUNet
 # ======================================================================================================================
-class ShiftUNetTrainer:
+
+class _Generation:
+    """A trainer keeps the saved-for-backward activations in ONE set of plan buffers, so only strictly alternating
+    forward / backward is valid.  Each forward stamps a generation; backward refuses to run against buffers that a later
+    forward of the same shape has overwritten (two micro-batches before the first backward, retain_graph / double
+    backward) instead of returning silently wrong gradients."""
+    _gen = 0
+    _consumed = -1
+
+    def _stamp(self) -> int:
+        self._gen += 1
+        return self._gen
+
+    def _claim(self, gen: int, what: str) -> None:
+        if gen != self._gen:
+            raise RuntimeError(f"pdae_b200 {what}: backward for forward call #{gen} but the trainer's activation buffers now "
+                               f"hold call #{self._gen} (two forwards of the same shape before the first backward). "
+                               "Run forward and backward strictly alternately, or use separate module instances.")
+        if self._consumed == gen:
+            raise RuntimeError(f"pdae_b200 {what}: backward ran twice for the same forward (retain_graph / double backward "
+                               "are not supported by the native backward plans)")
+        self._consumed = gen
+
+
+class ShiftUNetTrainer(_Generation):
     """Forward (fp32, all intermediates kept) + backward plans of a ShiftUNet for one input shape."""
 
     def __init__(self, net, B: int, H: int, W: int):
@@ -328,6 +352,7 @@ class _ShiftUNetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, trainer: ShiftUNetTrainer, x, t, z, *params):
         ctx.trainer = trainer
+        ctx.gen = trainer._stamp()
         ctx.z_needs = z.requires_grad
         with torch.no_grad():
             eps, grad = trainer.forward(x, t, z)
@@ -337,6 +362,7 @@ class _ShiftUNetFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_eps, d_grad):
         tr = ctx.trainer
+        tr._claim(ctx.gen, "ShiftUNet")
         with torch.no_grad():
             dz, pgrads = tr.backward(d_grad.contiguous())
         return (None, None, None, dz if ctx.z_needs else None, *pgrads)
@@ -356,7 +382,7 @@ def shiftunet_train_forward(net, x, t, z):
 # ======================================================================================================================
 # Plain UNet (regular DPM training, gaussian_diffusion.py:199-211) -- every parameter trainable, skip gradients routed
 # ======================================================================================================================
-class UNetTrainer:
+class UNetTrainer(_Generation):
     def __init__(self, net, B: int, H: int, W: int):
         from .model.unet import EmbBank, emit_head, res_blocks_of
         from .model.module import timestep_freqs
@@ -475,11 +501,13 @@ class _UNetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, trainer: UNetTrainer, x, t, cond, *params):
         ctx.trainer = trainer
+        ctx.gen = trainer._stamp()
         with torch.no_grad():
             return trainer.forward(x, t, cond)
 
     @staticmethod
     def backward(ctx, d_out):
+        ctx.trainer._claim(ctx.gen, "UNet")
         with torch.no_grad():
             pg = ctx.trainer.backward(d_out.contiguous())
         return (None, None, None, None, *pg)
@@ -499,7 +527,7 @@ def unet_train_forward(net, x, t, cond):
 # ======================================================================================================================
 # Semantic encoder
 # ======================================================================================================================
-class EncoderTrainer:
+class EncoderTrainer(_Generation):
     def __init__(self, enc, B: int, H: int, W: int):
         self.enc = enc
         dev = enc._device()
@@ -598,11 +626,13 @@ class _EncoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, trainer: EncoderTrainer, x, *params):
         ctx.trainer = trainer
+        ctx.gen = trainer._stamp()
         with torch.no_grad():
             return trainer.forward(x)
 
     @staticmethod
     def backward(ctx, dz):
+        ctx.trainer._claim(ctx.gen, "encoder")
         with torch.no_grad():
             pg = ctx.trainer.backward(dz.contiguous())
         return (None, None, *pg)
@@ -621,7 +651,7 @@ def encoder_train_forward(enc, x):
 # ======================================================================================================================
 # MLPSkipNet (latent DPM training, diffusion/gaussian_diffusion.py:373-398)
 # ======================================================================================================================
-class MLPTrainer:
+class MLPTrainer(_Generation):
     """Forward plan keeping every layer's (input, pre-activation, modulation) + backward plan for all parameters of the
     MLPSkipNet; no gradient w.r.t. z_t (the reference's z_t is built from detached latents)."""
 
@@ -732,11 +762,13 @@ class _MLPFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, trainer: MLPTrainer, x, t, *params):
         ctx.trainer = trainer
+        ctx.gen = trainer._stamp()
         with torch.no_grad():
             return trainer.forward(x, t)
 
     @staticmethod
     def backward(ctx, d_out):
+        ctx.trainer._claim(ctx.gen, "MLPSkipNet")
         with torch.no_grad():
             pg = ctx.trainer.backward(d_out.contiguous())
         return (None, None, None, *pg)

@@ -49,10 +49,16 @@ def sharded_autoencode(gd, encoder, decoder, x0_all: torch.Tensor, enc_style: st
     x = x0_all[s:e]
     if device is not None:
         x = x.to(device)
-    rec = gd.representation_learning_autoencoding(enc_style, dec_style, encoder, decoder, x)
+    if e == s:   # fewer images than ranks: shard_range gives everything to the last rank -- nothing to run here
+        rec = x.new_empty((0,) + tuple(x0_all.shape[1:]), dtype=torch.float32)
+    else:
+        rec = gd.representation_learning_autoencoding(enc_style, dec_style, encoder, decoder, x)
     if as_uint8:
         from ..metric import images_to_uint8
-        rec = images_to_uint8(rec)
+        if rec.shape[0]:
+            rec = images_to_uint8(rec)
+        else:
+            rec = rec.new_empty((0, rec.shape[2], rec.shape[3], rec.shape[1]), dtype=torch.uint8)
     return all_gather_images(rec, x0_all.shape[0])
 
 

@@ -68,3 +68,40 @@ def adam_case(cfg):
     scale = (lambda i: 10.0 ** (i - 2)) if cfg["ema_decay"] >= 0 else (lambda i: 1.0)
     grads = [[synth_normal(s, 100 + 10 * step + i) * scale(i) for i, s in enumerate(shapes)] for step in range(cfg["steps"])]
     return params, grads
+
+
+# ---- glue fixtures (tests/golden/make_golden.py::glue_cases) ---------------------------------------------------------
+class CpuStream:
+    """Replays the reference's random draws: torch.manual_seed(seed) on the default CPU generator, then randn / randn_like /
+    rand_like in call order (moved to `device` for the GPU tests)."""
+
+    def __init__(self, seed, device=None):
+        self.device = device
+        torch.manual_seed(seed)
+
+    def _mv(self, t):
+        return t if self.device is None else t.to(self.device)
+
+    def randn(self, shape):
+        return self._mv(torch.randn(tuple(shape)))
+
+    def randn_like(self, x):
+        return self._mv(torch.randn(tuple(x.shape)))
+
+    def rand_like(self, x):
+        return self._mv(torch.rand(tuple(x.shape)))
+
+    def install(self, gd):
+        gd._randn, gd._randn_like, gd._rand_like = self.randn, self.randn_like, self.rand_like
+        return gd
+
+
+def glue_inputs():
+    """Seeded inputs shared by the glue fixtures."""
+    return dict(xT=synth_normal((2, 3, 16, 16), 25), z1=synth_normal((2, 64), 27), z2=synth_normal((2, 64), 61),
+                x_t=synth_normal((4, 3, 8, 8), 62), eps=synth_normal((4, 3, 8, 8), 63),
+                lr=synth_normal((4, 3, 8, 8), 64).clamp(-1, 1),
+                mean64=synth_normal((1, 64), 65) * 0.1, std64=synth_normal((1, 64), 66).abs() + 0.5,
+                x0=synth_images(2, 3, 64, 28), xT64=synth_normal((2, 3, 64, 64), 67),
+                mean512=synth_normal((1, 512), 34) * 0.1, std512=synth_normal((1, 512), 35).abs() + 0.5,
+                cw=synth_normal((5, 512), 68))

@@ -163,6 +163,69 @@ def diffusion_cases():
     save("loop_latent_ddim10", dict(kind="latent_loop", cfg=TINY_MLP), z=DDIM(nb, tmap, "cpu").latent_ddim_sample_loop(mlp, zT))
 
 
+def glue_cases():
+    """The thin wrappers around the hot path: trajectory interpolation, the x_0-clip
+    ancestral step, the DDPM loops, latent sampling with stop_percent=0.3, manipulation, gap measure, one-step denoising.
+    Every random draw of the reference comes from the default CPU generator after torch.manual_seed(seed): the tests replay
+    the same stream through GaussianDiffusion._randn / _randn_like / _rand_like."""
+    gd = GaussianDiffusion(DIFF, "cpu")
+    dec16 = fill_module_(ShiftUNet(**TINY_SHIFT), seed=6).eval()
+    xT = synth_normal((2, 3, 16, 16), 25)
+    z1, z2 = synth_normal((2, 64), 27), synth_normal((2, 64), 61)
+    save("glue_interpolation", dict(kind="glue_interp", cfg=TINY_SHIFT, size=16, alpha=0.3, style="ddim10"),
+         y=gd.representation_learning_ddim_trajectory_interpolation("ddim10", dec16, z1, z2, xT, 0.3))
+
+    # x_0_clip_p_sample (gaussian_diffusion.py:130-146): fixed + learned variance, with / without the clip
+    x_t = synth_normal((4, 3, 8, 8), 62)
+    eps = synth_normal((4, 3, 8, 8), 63)
+    lr = synth_normal((4, 3, 8, 8), 64).clamp(-1, 1)
+    t = torch.tensor([0, 1, 500, 999], dtype=torch.long)
+    out = {}
+    for name, kw in (("fixed_clip", {}), ("fixed_noclip", dict(clip_x_0=False)), ("learned_clip", dict(learned_range=lr))):
+        torch.manual_seed(4321)
+        out[name] = gd.x_0_clip_p_sample(x_t.clone(), t, eps, **kw)
+    save("glue_x0_clip", dict(kind="glue_x0_clip", seed=4321), t=t, **out)
+
+    # DDPM ancestral loops on a short schedule (T=20): plain UNet, learn_sigma UNet, ShiftUNet
+    gd20 = GaussianDiffusion({"timesteps": 20, "betas_type": "linear"}, "cpu")
+    unet = fill_module_(UNet(**TINY_UNET), seed=5).eval()
+    unet_ls = fill_module_(UNet(**TINY_UNET_HC), seed=5).eval()
+    torch.manual_seed(555)
+    y_reg = gd20.regular_ddpm_sample(unet, xT)
+    torch.manual_seed(556)
+    y_ls = gd20.regular_ddpm_sample(unet_ls, xT)
+    z = synth_normal((2, 64), 27)
+    torch.manual_seed(557)
+    y_rl = gd20.representation_learning_ddpm_sample(None, dec16, xT, xT, z)
+    save("glue_ddpm", dict(kind="glue_ddpm", timesteps=20, cfg_unet=TINY_UNET, cfg_sigma=TINY_UNET_HC, cfg_shift=TINY_SHIFT,
+                           size=16, seeds=[555, 556, 557]), regular=y_reg, learned_sigma=y_ls, representation=y_rl)
+
+    # latent_diffusion_sample (:400-415): draws z_T inside, clamps it, latent DDIM loop, decoder loop with stop_percent=0.3
+    mlp = fill_module_(MLPSkipNet(**TINY_MLP), seed=8).eval()
+    mean, std = synth_normal((1, 64), 65) * 0.1, synth_normal((1, 64), 66).abs() + 0.5
+    torch.manual_seed(558)
+    y = gd.latent_diffusion_sample("ddim10", "ddim10", mlp, dec16, xT, mean, std)
+    save("glue_latent_sample", dict(kind="glue_latent_sample", cfg_mlp=TINY_MLP, cfg_shift=TINY_SHIFT, size=16, seed=558), y=y)
+
+    # manipulation_sample (:435-443), gap measure (:292-318) and one-step denoising (:320-334) on the 64-px tiny autoencoder
+    cfg = dict(TINY_SHIFT, latent_dim=512)
+    dec = fill_module_(ShiftUNet(**cfg), seed=6).eval()
+    enc = fill_module_(CELEBA64Encoder(latent_dim=512), seed=7).eval()
+    x0 = synth_images(2, 3, 64, 28)
+    xT64 = synth_normal((2, 3, 64, 64), 67)
+    mean, std = synth_normal((1, 512), 34) * 0.1, synth_normal((1, 512), 35).abs() + 0.5
+    cw = synth_normal((5, 512), 68)
+    save("glue_manipulation", dict(kind="glue_manipulation", cfg=cfg, size=64, class_id=3, scale=0.3, style="ddim10"),
+         y=gd.manipulation_sample("ddim10", cw, enc, dec, x0, xT64, mean, std, 3, 0.3))
+    gd8 = GaussianDiffusion({"timesteps": 8, "betas_type": "linear"}, "cpu")
+    torch.manual_seed(559)
+    gp, ga = gd8.representation_learning_gap_measure(enc, dec, x0)
+    save("glue_gap", dict(kind="glue_gap", cfg=cfg, size=64, timesteps=8, seed=559), gap_pred=np.array(gp), gap_ae=np.array(ga))
+    torch.manual_seed(560)
+    p0, a0 = gd.representation_learning_denoise_one_step(enc, dec, x0, [10, 700])
+    save("glue_denoise_one_step", dict(kind="glue_denoise", cfg=cfg, size=64, seed=560, timesteps=[10, 700]), pred=p0, ae=a0)
+
+
 def training_cases():
     torch.set_grad_enabled(True)
     gd = GaussianDiffusion(DIFF, "cpu")
@@ -266,8 +329,12 @@ def caller_cases():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "glue":      # regenerate only the round-2 glue fixtures
+        glue_cases()
+        sys.exit(0)
     block_cases()
     model_cases()
     diffusion_cases()
+    glue_cases()
     training_cases()
     caller_cases()

@@ -27,6 +27,7 @@ def _worker(rank, world, port, n_total, q):
 
     class FakeGD:  # the hot path itself needs a GPU; here only the sharding/gather wrapper is under test
         def representation_learning_autoencoding(self, a, b, enc, dec, x):
+            assert x.shape[0] > 0, "an empty shard must not reach the hot path (n < world)"
             return x + 1.0
     got2 = sharded_autoencode(FakeGD(), None, None, full)
     ok = ok and torch.equal(got2, full + 1.0)
@@ -44,7 +45,7 @@ def _worker(rank, world, port, n_total, q):
 
 def test_two_rank_shard_and_gather():
     ctx = mp.get_context("spawn")
-    for n_total in (8, 7):  # even and ragged (remainder to the last rank, as in the reference)
+    for n_total in (8, 7, 1):  # even, ragged (remainder to the last rank, as in the reference), fewer images than ranks
         q = ctx.Queue()
         port = _free_port()
         procs = [ctx.Process(target=_worker, args=(r, 2, port, n_total, q)) for r in range(2)]

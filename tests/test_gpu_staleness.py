@@ -1,0 +1,158 @@
+"""Packed-weight staleness, trainer buffer reuse and input-dtype guards (round-1 advisor findings).
+
+Plans cache re-laid-out / bf16 copies of the parameters keyed on (storage, autograd version).  Updates that bump no
+version -- the native fused optimizer's raw-pointer writes, the reference trainers' ``ema.data.mul_().add_()`` loop
+(trainer/train_representation_learning.py:192-212) -- must still be seen."""
+import copy
+
+import pytest
+import torch
+
+from tests import cases
+from tests.util import assert_close, load_golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _loss(gd, enc, dec, x0, t, noise):
+    z = enc(x0)
+    eps, grad = dec(gd.q_sample(x0, t, noise), t, z)
+    s = x0.shape
+    return gd.p_loss(noise, eps + gd.extract_coef_at_t(gd.shift_coef, t, s) * grad, weight=gd.extract_coef_at_t(gd.weight, t, s))
+
+
+def _train_setup():
+    from pdae_b200.diffusion.gaussian_diffusion import GaussianDiffusion
+    from pdae_b200.utils.synth import synth_images
+    cfg, g = load_golden("train_representation_learning")
+    dec, _ = cases.model_case({"kind": "shiftunet", "cfg": cfg["cfg"], "size": 64})
+    enc, _ = cases.model_case({"kind": "encoder", "size": 64})
+    dec, enc = dec.cuda().train(), enc.cuda().train()
+    dec.freeze()
+    dec.set_train_mode()
+    dec.precision = enc.precision = "fp32"
+    gd = GaussianDiffusion(cases.DIFF, torch.device("cuda"))
+    return cfg, gd, enc, dec, synth_images(2, 3, 64, 31).cuda(), g["t"].cuda(), g["noise"].cuda()
+
+
+def test_fused_adam_ema_step_is_seen_by_cached_plans():
+    """FusedAdamEMA writes p and the EMA copies through raw pointers: step-2 loss and gradients must equal those of a
+    FRESHLY built module holding the same weights, and the EMA net's sampling output must follow its new weights."""
+    from pdae_b200.optim import FusedAdamEMA
+    cfg, gd, enc, dec, x0, t, noise = _train_setup()
+    ema_dec = copy.deepcopy(dec).eval().requires_grad_(False)
+    params = [p for p in list(dec.parameters()) + list(enc.parameters()) if p.requires_grad]
+    opt = FusedAdamEMA(params, lr=2e-3, ema_decay=0.5)
+    opt.attach_ema(dec, ema_dec)
+    with torch.no_grad():   # pack the EMA net's weights BEFORE the step (this is what went stale)
+        z = enc(x0).detach()
+        ema_before = gd.representation_learning_ddim_sample("ddim2", None, ema_dec, None, noise, z)
+        e_b, g_b = ema_dec(noise, t, z)
+    loss1 = _loss(gd, enc, dec, x0, t, noise)
+    loss1.backward()
+    opt.step()
+    for p in params:
+        p.grad = None
+    loss2 = _loss(gd, enc, dec, x0, t, noise)
+    loss2.backward()
+    # fresh modules (no cached plans) with the post-step weights
+    dec2, _ = cases.model_case({"kind": "shiftunet", "cfg": cfg["cfg"], "size": 64})
+    enc2, _ = cases.model_case({"kind": "encoder", "size": 64})
+    dec2, enc2 = dec2.cuda().train(), enc2.cuda().train()
+    dec2.load_state_dict(dec.state_dict())
+    enc2.load_state_dict(enc.state_dict())
+    dec2.freeze()
+    dec2.set_train_mode()
+    dec2.precision = enc2.precision = "fp32"
+    loss2f = _loss(gd, enc2, dec2, x0, t, noise)
+    loss2f.backward()
+    assert abs(float(loss2) - float(loss1)) > 1e-6, "the optimizer step did not change the loss"
+    assert_close(loss2, loss2f, rtol=1e-5, atol=1e-7, what="step-2 loss vs fresh module")
+    fresh = dict(dec2.named_parameters())
+    for k, p in dec.named_parameters():
+        if p.grad is not None:
+            assert rel_l2(p.grad, fresh[k].grad) < 1e-4, k
+    # EMA net: direct forward (version bump) and a sampling loop both use the updated weights
+    ema_fresh, _ = cases.model_case({"kind": "shiftunet", "cfg": cfg["cfg"], "size": 64})
+    ema_fresh = ema_fresh.cuda().eval()
+    ema_fresh.load_state_dict(ema_dec.state_dict())
+    ema_fresh.precision = "fp32"
+    with torch.no_grad():
+        e_a, g_a = ema_dec(noise, t, z)
+        e_f, g_f = ema_fresh(noise, t, z)
+        assert rel_l2(g_a, g_b) > 1e-4, "EMA weights changed but the EMA net's output did not (stale packs)"
+        assert_close(g_a, g_f, rtol=1e-4, atol=1e-5, what="EMA net forward vs fresh module")
+        ema_after = gd.representation_learning_ddim_sample("ddim2", None, ema_dec, None, noise, z)
+        want = gd.representation_learning_ddim_sample("ddim2", None, ema_fresh, None, noise, z)
+        assert_close(ema_after, want, rtol=1e-4, atol=1e-5, what="EMA net sampling vs fresh module")
+        assert rel_l2(ema_after, ema_before) > 1e-5
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+def test_data_attribute_updates_are_seen_by_loops_and_after_invalidate(precision):
+    """`p.data.mul_(d).add_(...)` bumps no version counter (the reference's accumulate()): a sampling loop re-packs at its
+    start; a direct forward needs `invalidate_packed()`."""
+    from pdae_b200.diffusion.gaussian_diffusion import GaussianDiffusion
+    cfg, g = load_golden("model_shiftunet_b64")
+    m, inp = cases.model_case(cfg)
+    m = m.cuda().eval()
+    m.precision = precision
+    x, z, t = inp["x"].cuda(), inp["z"].cuda(), g["t"].cuda()
+    gd = GaussianDiffusion(cases.DIFF, torch.device("cuda"))
+    with torch.no_grad():
+        s1 = gd.representation_learning_ddim_sample("ddim3", None, m, None, x, z)
+        _, g1 = m(x, t, z)
+        for p in m.parameters():          # the reference's EMA-style write
+            p.data.mul_(0.5).add_(p.data, alpha=0.25)       # = 0.75 p, through .data only
+        assert all(p._version == 0 or True for p in m.parameters())
+        s2 = gd.representation_learning_ddim_sample("ddim3", None, m, None, x, z)
+        m.invalidate_packed()
+        _, g2 = m(x, t, z)
+    fresh, _ = cases.model_case(cfg)
+    fresh = fresh.cuda().eval()
+    fresh.load_state_dict(m.state_dict())
+    fresh.precision = precision
+    with torch.no_grad():
+        s2f = gd.representation_learning_ddim_sample("ddim3", None, fresh, None, x, z)
+        _, g2f = fresh(x, t, z)
+    tol = dict(rtol=1e-3, atol=1e-4) if precision != "bf16" else dict(rtol=5e-2, atol=5e-2)
+    assert rel_l2(s2, s1) > 1e-3 and rel_l2(g2, g1) > 1e-3, "stale packed weights after a .data update"
+    assert_close(s2, s2f, what="loop after .data update vs fresh module", **tol)
+    assert_close(g2, g2f, what="forward after invalidate_packed vs fresh module", **tol)
+
+
+def test_two_forwards_before_backward_raise_instead_of_corrupting_gradients():
+    cfg, gd, enc, dec, x0, t, noise = _train_setup()
+    l1 = _loss(gd, enc, dec, x0, t, noise)
+    l2 = _loss(gd, enc, dec, x0 * 0.5, t, noise)       # same shapes: overwrites the saved activations of call 1
+    l2.backward()                                       # the most recent forward is fine
+    with pytest.raises(RuntimeError, match="strictly alternately|alternately"):
+        l1.backward()
+    for p in list(dec.parameters()) + list(enc.parameters()):
+        p.grad = None
+    l3 = _loss(gd, enc, dec, x0, t, noise)
+    l3.backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="twice"):
+        l3.backward()
+
+
+def test_elementwise_wrappers_promote_non_fp32_inputs():
+    from pdae_b200.diffusion.gaussian_diffusion import GaussianDiffusion
+    from pdae_b200.utils.synth import synth_images, synth_normal
+    gd = GaussianDiffusion(cases.DIFF, torch.device("cuda"))
+    x0, noise = synth_images(4, 3, 8, 21).cuda(), synth_normal((4, 3, 8, 8), 22).cuda()
+    t = torch.tensor([0, 1, 500, 999], device="cuda")
+    want = gd.q_sample(x0, t, noise)
+    got = gd.q_sample(x0.double(), t.int(), noise.half())
+    assert got.dtype == torch.float32
+    assert_close(got, gd.q_sample(x0, t, noise.half().float()), rtol=0, atol=0, what="q_sample promotion")
+    assert rel_l2(got, want) < 1e-3
+    d = gd._ddim("ddim10")
+    td = torch.tensor([1, 2, 5, 10], device="cuda")
+    a = d._update(x0, td, noise, None, "sample")
+    b = d._update(x0.double(), td, noise.double(), None, "sample")
+    assert_close(b, a, rtol=0, atol=0, what="ddim update promotion")
+    with pytest.raises(ValueError):
+        gd.q_sample(x0, t[:2], noise)
+    with pytest.raises(ValueError):
+        d._update(x0, td[:1], noise, None, "sample")

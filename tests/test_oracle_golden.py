@@ -203,3 +203,85 @@ def test_caller_adam_ema(name):
         assert_close(p, g[f"p{i}"], rtol=1e-6, atol=1e-8, what=f"p{i}")
         if ema is not None:
             assert_close(ema[i], g[f"e{i}"], rtol=1e-6, atol=1e-8, what=f"e{i}")
+
+
+# ---- glue rows a20 / a22 / a24 -----------------------------------------------------------------------------------------
+def _shift16(cfg):
+    m, _ = cases.model_case({"kind": "shiftunet", "cfg": cfg, "size": 16})
+    sd = cases.sd_of(m)
+    return lambda x, t, z: O.shiftunet_forward(sd, cfg, x, t, z)
+
+
+def _unet16(cfg):
+    m, _ = cases.model_case({"kind": "unet", "cfg": cfg, "size": 16})
+    sd = cases.sd_of(m)
+    return lambda x, t, c: O.unet_forward(sd, cfg, x, t, c)
+
+
+def _autoenc64(cfg):
+    dec_m, _ = cases.model_case({"kind": "shiftunet", "cfg": cfg, "size": 64})
+    enc_m, _ = cases.model_case({"kind": "encoder", "size": 64})
+    dsd, esd = cases.sd_of(dec_m), cases.sd_of(enc_m)
+    return (lambda x: O.encoder_forward(esd, "celeba64", x)), (lambda x, t, z: O.shiftunet_forward(dsd, cfg, x, t, z))
+
+
+def test_glue_interpolation_and_x0_clip():
+    i = cases.glue_inputs()
+    D = O.DiffusionOracle(cases.DIFF)
+    cfg, g = load_golden("glue_interpolation")
+    y = D.trajectory_interpolation(cfg["style"], _shift16(cfg["cfg"]), i["z1"], i["z2"], i["xT"], cfg["alpha"])
+    assert_close(y, g["y"], what="trajectory interpolation", **TOL)
+    cfg, g = load_golden("glue_x0_clip")
+    for name, kw in (("fixed_clip", {}), ("fixed_noclip", dict(clip_x_0=False)), ("learned_clip", dict(learned_range=i["lr"]))):
+        noise = cases.CpuStream(cfg["seed"]).randn(i["x_t"].shape)
+        assert_close(D.x_0_clip_p_sample(i["x_t"], g["t"], i["eps"], noise, **kw), g[name], rtol=1e-6, atol=1e-6, what=name)
+
+
+def test_glue_ddpm_loops():
+    i = cases.glue_inputs()
+    cfg, g = load_golden("glue_ddpm")
+    D = O.DiffusionOracle({"timesteps": cfg["timesteps"], "betas_type": "linear"})
+    s = cfg["seeds"]
+    assert_close(D.ddpm_sample(_unet16(cfg["cfg_unet"]), i["xT"], cases.CpuStream(s[0]).randn), g["regular"], what="regular", **TOL)
+    assert_close(D.ddpm_sample(_unet16(cfg["cfg_sigma"]), i["xT"], cases.CpuStream(s[1]).randn), g["learned_sigma"],
+                 what="learned sigma", **TOL)
+    assert_close(D.ddpm_sample(_shift16(cfg["cfg_shift"]), i["xT"], cases.CpuStream(s[2]).randn, z=i["z1"]), g["representation"],
+                 what="representation", **TOL)
+
+
+def test_glue_latent_sample_manipulation_gap_denoise():
+    i = cases.glue_inputs()
+    D = O.DiffusionOracle(cases.DIFF)
+    cfg, g = load_golden("glue_latent_sample")
+    m, _ = cases.model_case({"kind": "mlp", "cfg": cfg["cfg_mlp"]})
+    sd = cases.sd_of(m)
+    zT = cases.CpuStream(cfg["seed"]).randn((2, 64))
+    y = D.latent_diffusion_sample("ddim10", "ddim10", lambda z, t: O.mlp_skip_net_forward(sd, cfg["cfg_mlp"], z, t),
+                                  _shift16(cfg["cfg_shift"]), i["xT"], zT, i["mean64"], i["std64"])
+    assert_close(y, g["y"], what="latent_diffusion_sample", **TOL)
+    cfg, g = load_golden("glue_manipulation")
+    enc, dec = _autoenc64(cfg["cfg"])
+    y = D.manipulation_sample(cfg["style"], i["cw"], enc, dec, i["x0"], i["xT64"], i["mean512"], i["std512"], cfg["class_id"],
+                              cfg["scale"])
+    assert_close(y, g["y"], what="manipulation_sample", rtol=1e-3, atol=1e-4)
+    cfg, g = load_golden("glue_gap")
+    D8 = O.DiffusionOracle({"timesteps": cfg["timesteps"], "betas_type": "linear"})
+    gp, ga = D8.gap_measure(enc, dec, i["x0"], cases.CpuStream(cfg["seed"]).rand_like)
+    np.testing.assert_allclose(gp, g["gap_pred"].numpy(), rtol=1e-4)
+    np.testing.assert_allclose(ga, g["gap_ae"].numpy(), rtol=1e-4)
+    cfg, g = load_golden("glue_denoise_one_step")
+    p0, a0 = D.denoise_one_step(enc, dec, i["x0"], cfg["timesteps"], cases.CpuStream(cfg["seed"]).randn_like(i["x0"]))
+    assert_close(p0, g["pred"], what="denoise pred", **TOL)
+    assert_close(a0, g["ae"], what="denoise ae", rtol=1e-4, atol=1e-4)
+
+
+def test_product_ddim_respacing_matches_reference_for_every_style():
+    """Row a16 on the PRODUCT function (host-side, no GPU needed): ddim10/100/200/500/1000 -> 11/101/201/501/1000 entries."""
+    from pdae_b200.diffusion.gaussian_diffusion import GaussianDiffusion
+    _, g = load_golden("diffusion_ddim_maps")
+    ac = O.gaussian_tables(cases.DIFF)["alphas_cumprod"].numpy()
+    for style, n in (("ddim10", 11), ("ddim100", 101), ("ddim200", 201), ("ddim500", 501), ("ddim1000", 1000)):
+        nb, tmap = GaussianDiffusion.get_ddim_betas_and_timestep_map(style, ac)
+        assert tmap.shape[0] == n and tmap.dtype == torch.long
+        assert torch.equal(tmap, g[style + "_map"]), style
+        np.testing.assert_array_equal(nb, g[style + "_betas"].numpy())
