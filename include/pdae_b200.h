@@ -125,6 +125,11 @@ int pdae_embedding_add(float* emb, const float* table, const int64_t* idx, int B
 int pdae_ddim_step(const float* x, const float* eps, const float* grad, const int64_t* t, const float* tab_A,
                    const float* tab_Bm, const float* tab_s1m, const float* tab_ab, float* out, int B,
                    int64_t per_sample, pdae_stream_t stream);
+/* Loop bookkeeping of the DDIM loops (ddim.py:57-64,81-88,110-120,140-147: `for i in ...: t = full(i)` + t_transform,
+ * ddim.py:39-41) on the device, so a whole step (select -> network -> update) is one CUDA-graph replay:
+ * i = *counter; t_loc[b] = i; t_net[b] = timestep_map[i]; *counter = i + delta.                         */
+int pdae_ddim_select_t(int64_t* counter, int delta, const int64_t* timestep_map, int map_len, int64_t* t_loc,
+                       int64_t* t_net, int B, pdae_stream_t stream);
 /* gaussian_diffusion.py:98-103: out = c1[t]*x0 + c2[t]*noise.                                         */
 int pdae_q_sample(const float* x0, const float* noise, const int64_t* t, const float* tab_c1, const float* tab_c2,
                   float* out, int B, int64_t per_sample, pdae_stream_t stream);

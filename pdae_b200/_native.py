@@ -67,6 +67,7 @@ _SIGS = {
     "pdae_timestep_embedding": (c_int, [_P, c_int, c_int, _P, _P, _P]),
     "pdae_embedding_add": (c_int, [_P, _P, _P, c_int, c_int, _P]),
     "pdae_ddim_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int64, _P]),
+    "pdae_ddim_select_t": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, _P]),
     "pdae_q_sample": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int64, _P]),
     "pdae_noise_p_sample": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int64, _P]),
     "pdae_mlp_mod_ln_act": (c_int, [_P, _P, _P, _P, c_float, c_int, _P, c_int, c_int, c_int, _P]),

@@ -559,6 +559,22 @@ __global__ void ddim_step_kernel(const float* __restrict__ x, const float* __res
   }
 }
 
+// One step of a sampling loop's bookkeeping, on the device so that the whole step is ONE CUDA-graph replay: read the loop
+// index i from `counter`, broadcast it (t_loc, the index into the respaced DDIM tables) and the original-schedule timestep
+// map[i] (t_net, the network's time input; ddim.py:39-41 t_transform), then advance the counter by `delta`.
+__global__ void ddim_select_t_kernel(long long* __restrict__ counter, int delta, const int64_t* __restrict__ map, int map_len,
+                                     int64_t* __restrict__ t_loc, int64_t* __restrict__ t_net, int B) {
+  const long long i = *counter;
+  const long long ic = i < 0 ? 0 : (i >= map_len ? map_len - 1 : i);
+  const int64_t m = map[ic];
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    t_loc[b] = (int64_t)ic;
+    t_net[b] = m;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *counter = i + delta;
+}
+
 __global__ void q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
                                 const int64_t* __restrict__ t, const float* __restrict__ c1,
                                 const float* __restrict__ c2, float* __restrict__ out, long long per_sample,
@@ -899,6 +915,14 @@ extern "C" int pdae_ddim_step(const float* x, const float* eps, const float* gra
   ddim_step_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(x, eps, grad, t, tab_A, tab_Bm, tab_s1m, tab_ab, out,
                                                                     per_sample, total);
   PDAE_LAUNCH_CHECK("ddim_step_kernel");
+  return PDAE_OK;
+}
+
+extern "C" int pdae_ddim_select_t(int64_t* counter, int delta, const int64_t* timestep_map, int map_len, int64_t* t_loc,
+                                  int64_t* t_net, int B, pdae_stream_t stream) {
+  PDAE_REQUIRE(counter && timestep_map && t_loc && t_net && map_len > 0 && B > 0, "ddim_select_t: bad args");
+  ddim_select_t_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((long long*)counter, delta, timestep_map, map_len, t_loc, t_net, B);
+  PDAE_LAUNCH_CHECK("ddim_select_t_kernel");
   return PDAE_OK;
 }
 

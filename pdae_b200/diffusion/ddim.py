@@ -38,6 +38,68 @@ def _t64(t, B, what):
     return t
 
 
+class _StepRunner:
+    """One network plan + the loop bookkeeping + the fused update of a DDIM loop direction, replayed as ONE CUDA graph per
+    step.  The graph is cached on the plan, keyed by (DDIM object, direction, shift) -- those fix the table pointers the
+    update kernel reads.  `seek(i)` sets the device-side step counter; `step()` is a single graph launch (or, with
+    PDAE_NO_GRAPH=1, the same launch sequence issued eagerly)."""
+
+    def __init__(self, ddim: "DDIM", plan, x_in, t_in, eps, grad, direction: str, C: int):
+        self.d, self.plan, self.x_in, self.t_in, self.eps, self.grad, self.direction = ddim, plan, x_in, t_in, eps, grad, direction
+        dev = ddim.device
+        B = x_in.tensor.shape[0]
+        self.B = B
+        self.delta = -1 if direction == "sample" else 1
+        self.in_graph_update = eps.tensor.shape[1] == C      # learn_sigma heads: the update runs after the replay
+        self.C = C
+        cache = plan.__dict__.setdefault("_step_cache", {})
+        key = (id(ddim), direction, grad is not None)
+        ent = cache.get(key)
+        if ent is None:
+            with torch.inference_mode(False):   # never inference tensors: the cache outlives the caller's autograd mode
+                ent = {"counter": torch.zeros(1, dtype=torch.int64, device=dev),
+                       "t_loc": torch.zeros(B, dtype=torch.int64, device=dev), "graph": None, "ddim": ddim}
+            cache[key] = ent
+        self.ent = ent
+
+    def _launch_step(self):
+        d, L = self.d, _native.lib()
+        st = _stream(d.device)
+        rc = L.pdae_ddim_select_t(_ptr(self.ent["counter"]), self.delta, _ptr(d.timestep_map), int(d.timestep_map.shape[0]),
+                                  _ptr(self.ent["t_loc"]), _ptr(self.t_in.tensor), self.B, st)
+        _native.check(rc, "pdae_ddim_select_t")
+        self.plan._launch_all()
+        if self.in_graph_update:
+            x = self.x_in.tensor
+            d._update(x, self.ent["t_loc"], self.eps.tensor, self.grad.tensor if self.grad is not None else None,
+                      self.direction, out=x)
+
+    def begin(self, use_graph: bool):
+        self.plan.run_prologue()          # forced weight re-pack + step-invariant ops (label_emb(z), emb_z_layers)
+        if use_graph and self.ent["graph"] is None:
+            self.seek(1 if self.direction == "sample" else 0)
+            self._launch_step()           # warm-up outside capture (lazy module loading, cudaFuncSetAttribute, ...)
+            torch.cuda.synchronize(self.d.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._launch_step()
+            self.ent["graph"] = g
+        self.use_graph = use_graph
+
+    def seek(self, i: int):
+        self.ent["counter"].fill_(int(i))
+
+    def step(self):
+        if self.use_graph:
+            self.ent["graph"].replay()
+        else:
+            self._launch_step()
+        if not self.in_graph_update:
+            x = self.x_in.tensor
+            e = self.eps.tensor[:, :self.C].contiguous()
+            self.d._update(x, self.ent["t_loc"], e, self.grad.tensor if self.grad is not None else None, self.direction, out=x)
+
+
 class DDIM:
     # replay each network step as one CUDA graph in the native fast path (PDAE_NO_GRAPH=1 disables, e.g. under ncu)
     use_cuda_graph = os.environ.get("PDAE_NO_GRAPH", "0") != "1"
@@ -115,41 +177,40 @@ class DDIM:
                 else:
                     img = self._update(img, t, net(img, self.t_transform(t), cond), None, direction)
             return img
-        # fast path: drive the network's static plan buffers in place
+        # fast path: drive the network's static plan buffers in place; a WHOLE step -- loop-index broadcast + timestep
+        # map lookup, every network launch, the fused DDIM update writing x_t back into the network's input buffer -- is one
+        # CUDA graph (device-side step counter), so a step costs one graph launch and no other host work
         H, W = x.shape[2], x.shape[3]
-        tail = None   # (plan, x_in, t_in, eps) of the epsilon-only plan used once the shift is switched off
+        C = x.shape[1]
+        tail = None   # StepRunner of the epsilon-only plan used once the shift is switched off
         if isinstance(net, ShiftUNet):
             plan, (x_in, t_in, z_in, eps, grad) = net.plan_for(B, H, W)
             z_in.tensor.copy_(cond)
+            main = _StepRunner(self, plan, x_in, t_in, eps, grad if shift else None, direction, C)
             if shift and direction == "sample" and stop_step > 0:
                 # ddim.py:119: steps with (i-1) < stop_step ignore the shift -> replay only the frozen epsilon half there
                 p2, (x2, t2, _, eps2, _) = net.plan_for(B, H, W, with_shift=False)
-                tail = (p2, x2, t2, eps2)
+                tail = _StepRunner(self, p2, x2, t2, eps2, None, direction, C)
         else:
             plan, (x_in, t_in, c_in, eps) = net._get_plan(("unet", B, H, W), lambda P: net._build(P, B, H, W))
-            grad = None
             if c_in is not None:
                 c_in.tensor.copy_(cond)
-        if self.use_cuda_graph:
-            plan.capture_graph()
-            if tail is not None:
-                tail[0].capture_graph()
-        plan.run_prologue()   # step-invariant ops (label_emb(z), emb_z_layers): once per loop, not once per step
+            main = _StepRunner(self, plan, x_in, t_in, eps, None, direction, C)
+        main.begin(self.use_cuda_graph)   # re-packs weights (forced: `.data` / raw-pointer updates bump no version), prologue
+        if tail is not None:
+            tail.begin(self.use_cuda_graph)
         x_in.tensor.copy_(x)
-        t_loc = torch.empty(B, device=self.device, dtype=torch.int64)
-        C = x.shape[1]
-        for i in self._steps(direction):
+        cur = main
+        steps = list(self._steps(direction))
+        cur.seek(steps[0])
+        for i in steps:
             use_shift = shift and (direction == "encode" or (i - 1) >= stop_step)
-            if tail is not None and not use_shift and plan is not tail[0]:
-                tail[1].tensor.copy_(x_in.tensor)
-                plan, x_in, t_in, eps = tail
-            t_loc.fill_(i)
-            torch.index_select(self.timestep_map, 0, t_loc, out=t_in.tensor)
-            plan.run(prologue=False)
-            eps_t = eps.tensor
-            e = eps_t if eps_t.shape[1] == C else eps_t[:, :C].contiguous()
-            self._update(x_in.tensor, t_loc, e, grad.tensor if use_shift else None, direction, out=x_in.tensor)
-        return x_in.tensor.clone()
+            if tail is not None and not use_shift and cur is not tail:
+                tail.x_in.tensor.copy_(cur.x_in.tensor)
+                cur = tail
+                cur.seek(i)
+            cur.step()
+        return cur.x_in.tensor.clone()
 
     def ddim_sample_loop(self, denoise_fn, x_T, condition=None):
         return self._loop(denoise_fn, x_T, condition, "sample", shift=False)

@@ -56,3 +56,21 @@ def synth_images(batch: int, channels: int, size: int, seed: int) -> torch.Tenso
 def synth_normal(shape: Tuple[int, ...], seed: int) -> torch.Tensor:
     rng = np.random.default_rng([seed, 2])
     return torch.from_numpy(rng.standard_normal(shape, dtype=np.float32))
+
+
+# ---- the weight mode SURVEY.md section 8(d) prescribes ------------------------------------------------------------------
+def build_survey_init(factory, seed: int = 0) -> torch.nn.Module:
+    """``factory()`` under ``torch.manual_seed(seed)`` -- i.e. the reference's own default initialisation (nn.Conv2d /
+    nn.Linear kaiming-uniform, GroupNorm 1/0) -- and then EVERY all-zero floating parameter re-drawn N(0, 0.02^2)
+    (the zero-initialised ResBlock / attention / head convs and all the zero biases), from a numpy PCG64
+    stream keyed by (seed, crc32(parameter name)).  Deterministic for a given torch version; the oracle and the product
+    share the resulting state_dict."""
+    with torch.random.fork_rng(devices=[]):
+        torch.manual_seed(seed)
+        m = factory()
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if torch.is_floating_point(p) and p.numel() and not bool(p.any()):
+                rng = np.random.default_rng([seed, zlib.crc32(name.encode()), 20])
+                p.copy_(torch.from_numpy(rng.standard_normal(tuple(p.shape), dtype=np.float32) * np.float32(0.02)))
+    return m
