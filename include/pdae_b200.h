@@ -197,6 +197,24 @@ int pdae_gemm_batched_simt(const float* A, int64_t lda, int64_t a_bs, int64_t a_
                            int64_t b_bs, int64_t b_hs, int transB, float* C, int64_t ldc, int64_t c_bs, int64_t c_hs, int M,
                            int N, int K, int batch, int heads, float alpha, pdae_stream_t stream);
 
+/* v3: the fused ResBlock convolution (model/module.py:278-297, 361-384).  out = conv3x3(SiLU(a*cat(src1, src2) + b)) + bias
+ * [+ residual] [+ cat(skp1, skp2) * w_skip^T]: the GroupNorm / AdaGN / z-modulation coefficients (a, b) ([B][2][C1+C2] fp32
+ * from pdae_gn_coef_ch) and the SiLU are applied while the tensor-core operand is built (one swizzled 18 x 10-pixel halo tile
+ * per 64-channel block, all nine taps address it through row-shifted UMMA descriptors), so the activated tensor is never
+ * written to HBM; the concatenated skip input (unet.py:199) is never materialised either.  src_dtype PDAE_BF16: bf16 NHWC
+ * sources, weights bf16 [9][Cout][Cin] (w_skip [Cout][S1+S2]).  src_dtype PDAE_F32 = split-operand mode: fp32 NHWC sources
+ * are split hi/lo in the prologue, weights are (hi, lo) pairs [9][2][Cout][Cin] (w_skip [2][Cout][S1+S2]) and every
+ * product is a_hi*W_hi + a_lo*W_hi + a_hi*W_lo (fp32-grade).  H % 16 == 0, W % 8 == 0, every channel count % 64 == 0
+ * (pdae_conv_tc3_supported).  Residual / ch_stats / out_dtype as for v2; the fused skip conv's bias must be folded into `bias`. */
+typedef struct pdae_conv_tc3_plan pdae_conv_tc3_plan;
+int pdae_conv_tc3_supported(int H, int W, int Cin, int Cout);
+int pdae_conv_tc3_create(pdae_conv_tc3_plan** plan, const void* src1, int C1, const void* src2, int C2, int src_dtype,
+                         const float* ab, int silu, const void* w, const float* bias, const void* skp1, int S1,
+                         const void* skp2, int S2, const void* w_skip, const void* residual, void* out, int out_dtype,
+                         float* ch_stats, int B, int H, int W, int Cout, int bn_override);
+int pdae_conv_tc3_run(const pdae_conv_tc3_plan* plan, pdae_stream_t stream);
+void pdae_conv_tc3_destroy(pdae_conv_tc3_plan* plan);
+
 /* v2: persistent CTAs, double-buffered TMEM accumulators (epilogue overlaps the next tile's main loop), TMA-store
  * epilogue.  out_dtype PDAE_F32|PDAE_BF16; ch_stats (optional) fp32 [B][Cout][2] accumulates per-channel (sum, sum^2)
  * of the stored values (zero it first); a residual is read in the OUTPUT's dtype.  cout_valid > 0 selects the image-head variant:

@@ -1,0 +1,743 @@
+// conv_tc3 -- 3x3 convolution with the GroupNorm-apply / AdaGN / SiLU prologue FUSED into the operand path (sm_100a).
+//
+// Reference op chain (model/module.py:278-297, 361-384):   h = conv3x3(SiLU(GN(x)))   and
+// out = conv3x3(SiLU((1+zs)*(GN(h)*(1+s)+sh)+zsh)) [+ skip_1x1(x_raw)] + residual.  The GroupNorm / AdaGN / z-modulation
+// algebra is folded by gn_coef_ch into per-(image, channel) coefficients (a, b); this kernel applies
+// SiLU(a*x + b) while it builds the tensor-core A operand, so the activated tensor never exists in HBM.
+//
+//   warp 0      : TMA producer of the weight (B) tiles                       [tap][Cout][Cin] bf16, SWIZZLE_128B
+//   warp 1      : tcgen05.mma issuer, accumulators double-buffered in TMEM (2 x BN columns)
+//   warps 2-9   : two epilogue groups (one per TMEM accumulator): tcgen05.ld -> +bias (+residual via TMA) -> swizzled
+//                 staging -> per-channel GroupNorm sums (for the NEXT GroupNorm) -> TMA store        (as conv_tc2)
+//   warps 10-17 : TRANSFORM group.  Per 64-channel k-block it reads the raw (pre-normalisation) 18 x 10 pixel HALO of
+//                 the CTA's 16 x 8 output tile straight from global memory, applies SiLU(a*x+b), zero-fills the conv
+//                 padding, and writes ONE 128B-swizzled halo tile (180 rows x 128 B) into shared memory.
+// All nine taps of the k-block address that single tile: tap (dy, dx) is the UMMA descriptor started (dy*10 + dx) rows
+// into it with a stride-byte-offset of 10 rows (1280 B) between its 8-pixel row groups -- the 128B swizzle is a function
+// of the absolute shared-memory address (scripts/desc_shift_probe.py), so a row-shifted window of a tile written with
+// address-based swizzling is a valid K-major operand.  Shared-memory operand writes per k-block drop from 9 x 16 KB
+// (one TMA box per tap, conv_tc2) to 23 KB, and the separate gn_apply pass over HBM disappears.
+//
+// X3 = split-operand mode (fp32-grade products): the source is fp32; the transform writes TWO halo tiles
+// hi = bf16(v), lo = bf16(v - hi); weights come as (W_hi, W_lo) tile pairs; per tap the issuer accumulates
+// a_hi*W_hi + a_lo*W_hi + a_hi*W_lo.  The hi tile is written and read once (conv_tc2's [hi|lo|hi] layout duplicated it).
+//
+// The 1x1 skip convolution of a channel-changing ResBlock (model/module.py:268-276) rides along as extra k-blocks whose
+// transform is the identity and whose single tap is the centre window.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace pdae {
+
+constexpr int T3_BM = 128, T3_BK = 64;
+constexpr int T3_TW = 8, T3_TH = 16;                  // output tile (pixels): 8 wide x 16 tall, one image
+constexpr int T3_P = T3_TW + 2;                       // halo pitch (pixels per halo row)
+constexpr int T3_HROWS = T3_TH + 2;
+constexpr int T3_HALO = T3_P * T3_HROWS;              // 180 halo pixels = 180 shared-memory rows of 128 B
+constexpr int T3_HALO_BYTES = 23 * 1024;              // 180 * 128 = 23040 B, padded to a 1024-B multiple (swizzle atom alignment)
+constexpr int T3_STG_BYTES = 128 * 128;
+constexpr int T3_MAX_SA = 3, T3_MAX_SB = 8;
+constexpr int T3_XF_WARPS = 8;
+constexpr int T3_THREADS = 64 + 256 + 32 * T3_XF_WARPS;   // 576
+constexpr int T3_XF_PASSES = (T3_HALO + 31) / 32;     // 6 passes of 32 pixel slots (8 threads x 16 B per pixel)
+
+struct ConvTc3Args {
+  const void* src1; const void* src2;   // pre-activation conv input (virtual channel concat C1 | C2), NHWC, bf16 (X3=0) / fp32 (X3=1)
+  int C1, C2;
+  const float* ab;                      // [B][2][C1+C2]: a | b of SiLU(a*x+b)
+  const void* skp1; const void* skp2;   // raw input of the fused 1x1 skip conv (S1 | S2 channels), same dtype as src
+  int S1, S2;
+  const float* bias;
+  float* ch_stats;                      // [B][Cout][2] (sum, sum^2) accumulators of the OUTPUT or nullptr
+  int B, H, W, Cout;
+  int tiles_x, tiles_y, tiles_m, tiles_total;
+  int kblocks, kblocks2;
+  int sa, sb;                           // pipeline depths: halo stages / weight-tile stages
+  int has_res, out_bf16, silu;
+};
+
+// ---- small PTX helpers (same protocol as conv_tc2.cu) -------------------------------------------------------------------
+namespace t3 {
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mb_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mb_try(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
+__device__ __noinline__ void mb_wait_slow(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mb_try(bar, parity))
+    if (clock64() - t0 > 4000000000LL) __trap();  // a protocol bug must trap, never hang the GPU
+}
+__device__ __forceinline__ void mb_wait(uint32_t bar, uint32_t parity) {
+  if (mb_try(bar, parity)) return;
+  if (mb_try(bar, parity)) return;
+  mb_wait_slow(bar, parity);
+}
+__device__ __forceinline__ void tma_ld4(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_ld3(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_st4(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(m), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+// K-major SWIZZLE_128B operand descriptor; sbo = bytes between consecutive 8-row groups
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(a), "l"(b), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_to(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void epi_bar(int g) { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+// byte offset of (row, 16-byte chunk) inside a SWIZZLE_128B tile whose base is 1024-B aligned
+__device__ __forceinline__ uint32_t swz(int row, int chunk16) { return (uint32_t)(row * 128 + ((chunk16 ^ (row & 7)) << 4)); }
+
+// SiLU of the fused prologue.  bf16 mode: one MUFU (tanh.approx), the result is rounded to bf16 anyway.  Split mode: ex2 + rcp
+// approximations (rel. error ~1e-7), well inside the 2^-17 the hi/lo pair resolves.
+template <bool X3>
+__device__ __forceinline__ float act(float x, int silu) {
+  if (!silu) return x;
+  if (X3) return __fdividef(x, 1.0f + __expf(-x));
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+}  // namespace t3
+
+template <int BN, bool X3>
+__global__ void __launch_bounds__(T3_THREADS, 1)
+conv_tc3_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2,
+                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, ConvTc3Args p) {
+  using namespace t3;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_a_full[T3_MAX_SA], bar_a_empty[T3_MAX_SA];
+  __shared__ __align__(8) uint64_t bar_b_full[T3_MAX_SB], bar_b_empty[T3_MAX_SB];
+  __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2], bar_res[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float st_acc[2][2][BN];   // [epilogue group][sum | sum^2][channel] of the group's current (image, n-tile)
+
+  constexpr int B_BYTES = BN * T3_BK * 2;
+  constexpr int A_STAGE = (X3 ? 2 : 1) * T3_HALO_BYTES;
+  constexpr int TMEM_COLS = 2 * BN;
+  constexpr int NMAT = X3 ? 2 : 1;   // weight tiles per (tap, k-block): W | (W_hi, W_lo)
+  const uint32_t smem0 = (s_u32(smem_raw) + 1023u) & ~1023u;
+  const int SA = p.sa, SB = p.sb;
+  const uint32_t a_base = smem0;
+  const uint32_t b_base = a_base + (uint32_t)(SA * A_STAGE);
+  const uint32_t stg_out = b_base + (uint32_t)(SB * B_BYTES);
+  const uint32_t stg_res = stg_out + 2u * T3_STG_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_it = p.kblocks + p.kblocks2;
+  const int per_cta = (p.tiles_total + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int tile_begin = (int)blockIdx.x * per_cta;
+  const int tile_end = min(p.tiles_total, tile_begin + per_cta);
+  const int tiles_img = p.tiles_x * p.tiles_y;
+
+  for (int j = threadIdx.x; j < BN; j += T3_THREADS) {
+    st_acc[0][0][j] = 0.f; st_acc[0][1][j] = 0.f;
+    st_acc[1][0][j] = 0.f; st_acc[1][1][j] = 0.f;
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SA; ++s) {
+      mb_init(s_u32(&bar_a_full[s]), T3_XF_WARPS);   // one elected arrive per transform warp
+      mb_init(s_u32(&bar_a_empty[s]), 1);
+    }
+    for (int s = 0; s < SB; ++s) {
+      mb_init(s_u32(&bar_b_full[s]), 1);
+      mb_init(s_u32(&bar_b_empty[s]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mb_init(s_u32(&bar_acc_full[i]), 1);
+      mb_init(s_u32(&bar_acc_empty[i]), 1);
+      mb_init(s_u32(&bar_res[i]), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
+  }
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_slot)), "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= weight-tile TMA producer =================
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int n0 = (tile / p.tiles_m) * BN;
+        for (int it = 0; it < total_it; ++it) {
+          const bool skipk = it >= p.kblocks;
+          const int ntap = skipk ? 1 : 9;
+          for (int tap = 0; tap < ntap; ++tap) {
+#pragma unroll
+            for (int m = 0; m < NMAT; ++m) {
+              mb_wait(s_u32(&bar_b_empty[s]), ph ^ 1u);
+              const uint32_t full = s_u32(&bar_b_full[s]);
+              mb_expect_tx(full, (uint32_t)B_BYTES);
+              if (!skipk) tma_ld3(b_base + (uint32_t)(s * B_BYTES), &tmB, full, it * T3_BK, n0, tap * NMAT + m);
+              else tma_ld3(b_base + (uint32_t)(s * B_BYTES), &tmB2, full, (it - p.kblocks) * T3_BK, n0, m);
+              if (++s == SB) { s = 0; ph ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================= MMA issuer =================
+      constexpr uint32_t IDESC =
+          (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(T3_BM >> 4) << 24);
+      constexpr uint32_t A_SBO = (uint32_t)T3_P * 128u;   // 8-pixel row groups of the halo are one halo row (10 px) apart
+      int sa = 0, sb = 0, tl = 0;
+      uint32_t pha = 0, phb = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile, ++tl) {
+        const int ab = tl & 1;
+        mb_wait(s_u32(&bar_acc_empty[ab]), (uint32_t)(((tl >> 1) & 1) ^ 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_d = tmem_base + (uint32_t)(ab * BN);
+        for (int it = 0; it < total_it; ++it) {
+          mb_wait(s_u32(&bar_a_full[sa]), pha);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const bool skipk = it >= p.kblocks;
+          const int ntap = skipk ? 1 : 9;
+          const uint32_t a_hi = a_base + (uint32_t)(sa * A_STAGE);
+          for (int tp = 0; tp < ntap; ++tp) {
+            const int tap = skipk ? 4 : tp;
+            const uint32_t off = (uint32_t)((tap / 3) * T3_P + (tap % 3)) * 128u;
+            const uint64_t ad_hi = sw128_desc(a_hi + off, A_SBO);
+            mb_wait(s_u32(&bar_b_full[sb]), phb);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t bd = sw128_desc(b_base + (uint32_t)(sb * B_BYTES), 1024u);
+#pragma unroll
+            for (int k = 0; k < T3_BK / 16; ++k)
+              umma(tmem_d, ad_hi + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), IDESC, (uint32_t)((it | tp | k) != 0));
+            if (X3) {
+              const uint64_t ad_lo = sw128_desc(a_hi + (uint32_t)T3_HALO_BYTES + off, A_SBO);
+#pragma unroll
+              for (int k = 0; k < T3_BK / 16; ++k) umma(tmem_d, ad_lo + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), IDESC, 1u);
+            }
+            umma_commit_to(s_u32(&bar_b_empty[sb]));
+            if (++sb == SB) { sb = 0; phb ^= 1u; }
+            if (X3) {   // a_hi * W_lo
+              mb_wait(s_u32(&bar_b_full[sb]), phb);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              const uint64_t bd2 = sw128_desc(b_base + (uint32_t)(sb * B_BYTES), 1024u);
+#pragma unroll
+              for (int k = 0; k < T3_BK / 16; ++k) umma(tmem_d, ad_hi + (uint64_t)(2 * k), bd2 + (uint64_t)(2 * k), IDESC, 1u);
+              umma_commit_to(s_u32(&bar_b_empty[sb]));
+              if (++sb == SB) { sb = 0; phb ^= 1u; }
+            }
+          }
+          umma_commit_to(s_u32(&bar_a_empty[sa]));
+          if (++sa == SA) { sa = 0; pha ^= 1u; }
+        }
+        umma_commit_to(s_u32(&bar_acc_full[ab]));
+      }
+    }
+  } else if (warp >= 10) {
+    // ================= transform group: raw halo -> SiLU(a*x+b) -> swizzled operand tile(s) =================
+    using TSrc = typename std::conditional<X3, float, __nv_bfloat16>::type;
+    const int tt = (int)threadIdx.x - 320;   // 0..255
+    const int slot = tt >> 3, ch8 = tt & 7;  // pixel slot (32 per pass), 8-channel chunk (16 B of bf16 operand)
+    const int C = p.C1 + p.C2;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      int mt = tile % p.tiles_m;
+      const int tx = mt % p.tiles_x;
+      mt /= p.tiles_x;
+      const int ty = mt % p.tiles_y;
+      const int b0 = mt / p.tiles_y;
+      const int x0 = tx * T3_TW - 1, y0 = ty * T3_TH - 1;   // image coordinates of halo pixel (0, 0)
+      for (int it = 0; it < total_it; ++it) {
+        const bool skipk = it >= p.kblocks;
+        const TSrc* src;
+        int cs, c0;
+        if (!skipk) {
+          const int kc = it * T3_BK;
+          if (kc < p.C1) { src = (const TSrc*)p.src1; cs = p.C1; c0 = kc; }
+          else { src = (const TSrc*)p.src2; cs = p.C2; c0 = kc - p.C1; }
+        } else {
+          const int kc = (it - p.kblocks) * T3_BK;
+          if (kc < p.S1) { src = (const TSrc*)p.skp1; cs = p.S1; c0 = kc; }
+          else { src = (const TSrc*)p.skp2; cs = p.S2; c0 = kc - p.S1; }
+        }
+        src += (long long)b0 * p.H * p.W * cs + c0 + ch8 * 8;
+        float ca[8], cb[8];
+        if (!skipk) {
+          const float* ap = p.ab + ((long long)b0 * 2) * C + it * T3_BK + ch8 * 8;
+          const float4 a0 = __ldg(reinterpret_cast<const float4*>(ap)), a1 = __ldg(reinterpret_cast<const float4*>(ap + 4));
+          const float4 q0 = __ldg(reinterpret_cast<const float4*>(ap + C)), q1 = __ldg(reinterpret_cast<const float4*>(ap + C + 4));
+          ca[0] = a0.x; ca[1] = a0.y; ca[2] = a0.z; ca[3] = a0.w; ca[4] = a1.x; ca[5] = a1.y; ca[6] = a1.z; ca[7] = a1.w;
+          cb[0] = q0.x; cb[1] = q0.y; cb[2] = q0.z; cb[3] = q0.w; cb[4] = q1.x; cb[5] = q1.y; cb[6] = q1.z; cb[7] = q1.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { ca[j] = 1.f; cb[j] = 0.f; }
+        }
+        const int silu = skipk ? 0 : p.silu;
+        // ---- issue every global load of this k-block first (latency overlaps the wait for the stage) ----
+        uint4 raw[T3_XF_PASSES][X3 ? 2 : 1];
+        uint32_t vmask = 0;
+#pragma unroll
+        for (int j = 0; j < T3_XF_PASSES; ++j) {
+          const int hp = j * 32 + slot;
+          const int hy = hp / T3_P, hx = hp - hy * T3_P;
+          const int gy = y0 + hy, gx = x0 + hx;
+          bool ok = hp < T3_HALO && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+          if (skipk) ok = ok && hy >= 1 && hy <= T3_TH && hx >= 1 && hx <= T3_TW;   // the 1x1 conv reads the centre window only
+          if (ok) {
+            vmask |= 1u << j;
+            const uint4* g = reinterpret_cast<const uint4*>(src + ((long long)gy * p.W + gx) * cs);
+            raw[j][0] = __ldg(g);
+            if (X3) raw[j][1] = __ldg(g + 1);
+          }
+        }
+        mb_wait(s_u32(&bar_a_empty[s]), ph ^ 1u);
+        const uint32_t hi_base = a_base + (uint32_t)(s * A_STAGE);
+#pragma unroll
+        for (int j = 0; j < T3_XF_PASSES; ++j) {
+          const int hp = j * 32 + slot;
+          if (hp < T3_HALO) {
+            float v[8];
+            if (vmask & (1u << j)) {
+              if (X3) {
+                const float* f0 = reinterpret_cast<const float*>(&raw[j][0]);
+                const float* f1 = reinterpret_cast<const float*>(&raw[j][X3 ? 1 : 0]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { v[e] = f0[e]; v[4 + e] = f1[e]; }
+              } else {
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(&raw[j][0]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  v[2 * e] = __uint_as_float(w[e] << 16);
+                  v[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+                }
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = act<X3>(fmaf(ca[e], v[e], cb[e]), silu);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = 0.f;   // conv zero padding (applied AFTER the activation, as F.conv2d pads)
+            }
+            const uint32_t dst = hi_base + swz(hp, ch8);
+            uint32_t h[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+            if (X3) {
+              uint32_t l[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float r0 = v[2 * e] - __uint_as_float(h[e] << 16);
+                const float r1 = v[2 * e + 1] - __uint_as_float(h[e] & 0xffff0000u);
+                l[e] = pack_bf16(r0, r1);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + (uint32_t)T3_HALO_BYTES), "r"(l[0]), "r"(l[1]),
+                           "r"(l[2]), "r"(l[3])
+                           : "memory");
+            }
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mb_arrive(s_u32(&bar_a_full[s]));
+        if (++s == SA) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // ================= epilogue: two groups of 128 threads; group g drains accumulator buffer g (as conv_tc2) =================
+    const int eg = (warp - 2) >> 2;
+    const int et = (int)threadIdx.x - 64 - eg * 128;
+    const bool elected = et == 0;
+    const int q = warp & 3;                    // TMEM lane quadrant of this warp
+    const int r = q * 32 + lane;               // accumulator row = pixel index in the tile (row-major 16 x 8)
+    int rc = 0;
+    const uint32_t obuf = stg_out + (uint32_t)eg * T3_STG_BYTES, rbuf = stg_res + (uint32_t)eg * T3_STG_BYTES;
+    const uint32_t rbar = s_u32(&bar_res[eg]);
+    const int CW = p.out_bf16 ? 64 : 32;       // accumulator columns per staging tile (128-byte rows)
+    const int nch = BN / CW;
+    for (int tile = tile_begin + eg, tl = eg; tile < tile_end; tile += 2, tl += 2) {
+      const int nt = tile / p.tiles_m;
+      int mt = tile - nt * p.tiles_m;
+      const int tx = mt % p.tiles_x;
+      mt /= p.tiles_x;
+      const int ty = mt % p.tiles_y;
+      const int b0 = mt / p.tiles_y;
+      const int x0 = tx * T3_TW, y0 = ty * T3_TH, n0 = nt * BN;
+      const int ab = tl & 1;
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(ab * BN) + ((uint32_t)(q * 32) << 16);
+      if (p.has_res && elected) {              // residual chunk 0 (issued before the accumulator is needed)
+        mb_expect_tx(rbar, T3_STG_BYTES);
+        tma_ld4(rbuf, &tmR, rbar, n0, x0, y0, b0);
+      }
+      mb_wait(s_u32(&bar_acc_full[ab]), (uint32_t)((tl >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int c = 0; c < nch; ++c) {
+        float val[64];
+        {
+          uint32_t v[32];
+          tmem_ld32(tmem_acc + (uint32_t)(c * CW), v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(v[j]);
+          if (p.out_bf16) {
+            tmem_ld32(tmem_acc + (uint32_t)(c * CW + 32), v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) val[32 + j] = __uint_as_float(v[j]);
+          }
+        }
+        if (p.bias) {
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c * CW);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (j * 4 < CW) {
+              const float4 bv = __ldg(bp + j);
+              val[4 * j + 0] += bv.x; val[4 * j + 1] += bv.y; val[4 * j + 2] += bv.z; val[4 * j + 3] += bv.w;
+            }
+          }
+        }
+        if (p.has_res) {
+          mb_wait(rbar, (uint32_t)(rc & 1));
+          if (p.out_bf16) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint32_t w[4];
+              asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
+                           : "r"(rbuf + swz(r, j)));
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                val[8 * j + 2 * h] += __uint_as_float(w[h] << 16);
+                val[8 * j + 2 * h + 1] += __uint_as_float(w[h] & 0xffff0000u);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 rv;
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(rv.x), "=f"(rv.y), "=f"(rv.z), "=f"(rv.w)
+                           : "r"(rbuf + swz(r, j)));
+              val[4 * j + 0] += rv.x; val[4 * j + 1] += rv.y; val[4 * j + 2] += rv.z; val[4 * j + 3] += rv.w;
+            }
+          }
+          ++rc;
+        }
+        if (elected) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous TMA store has read the staging buffer
+        epi_bar(eg);
+        if (p.has_res && elected && c + 1 < nch) {
+          mb_expect_tx(rbar, T3_STG_BYTES);
+          tma_ld4(rbuf, &tmR, rbar, n0 + (c + 1) * CW, x0, y0, b0);
+        }
+        if (p.out_bf16) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint32_t w[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) w[h] = pack_bf16(val[8 * j + 2 * h], val[8 * j + 2 * h + 1]);
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(obuf + swz(r, j)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                         : "memory");
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(obuf + swz(r, j)), "f"(val[4 * j]), "f"(val[4 * j + 1]),
+                         "f"(val[4 * j + 2]), "f"(val[4 * j + 3])
+                         : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        epi_bar(eg);
+        if (elected) {
+          tma_st4(&tmO, obuf, n0 + c * CW, x0, y0, b0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (p.ch_stats) {
+          // per-channel partial sums over this tile's rows, read back from the staged (rounded) values:
+          // thread -> column (et % CW), rows [(et / CW) * CW, +CW); accumulated in shared memory across the CTA's tiles of an image
+          const int col = et % CW, r0 = (et / CW) * CW;
+          const uint32_t cbyte = p.out_bf16 ? (uint32_t)((col & 7) * 2) : (uint32_t)((col & 3) * 4);
+          const int cchunk = p.out_bf16 ? (col >> 3) : (col >> 2);
+          float s = 0.f, qq = 0.f;
+#pragma unroll 8
+          for (int rr = r0; rr < r0 + CW; ++rr) {
+            float x;
+            if (p.out_bf16) {
+              unsigned short h;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(obuf + swz(rr, cchunk) + cbyte));
+              x = __uint_as_float(((uint32_t)h) << 16);
+            } else {
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(obuf + swz(rr, cchunk) + cbyte));
+            }
+            s += x;
+            qq = fmaf(x, x, qq);
+          }
+          atomicAdd(&st_acc[eg][0][c * CW + col], s);
+          atomicAdd(&st_acc[eg][1][c * CW + col], qq);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      epi_bar(eg);
+      if (elected) mb_arrive(s_u32(&bar_acc_empty[ab]));
+      if (p.ch_stats) {
+        bool flush = tile + 2 >= tile_end;     // this group's next tile is tile + 2
+        if (!flush) {
+          const int nt2 = (tile + 2) / p.tiles_m;
+          const int b2 = ((tile + 2) - nt2 * p.tiles_m) / tiles_img;
+          flush = nt2 != nt || b2 != b0;
+        }
+        if (flush) {   // (the epi_bar above ordered every thread's shared-memory atomics before these reads)
+          for (int j = et; j < BN; j += 128) {
+            float* dst = p.ch_stats + ((long long)b0 * p.Cout + n0 + j) * 2;
+            atomicAdd(dst, st_acc[eg][0][j]);
+            atomicAdd(dst + 1, st_acc[eg][1][j]);
+            st_acc[eg][0][j] = 0.f;
+            st_acc[eg][1][j] = 0.f;
+          }
+          epi_bar(eg);
+        }
+      }
+    }
+    if (elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn3 encode_fn3() {
+  static EncodeTiledFn3 fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  fn = (EncodeTiledFn3)sym;
+  return fn;
+}
+
+template <int BN, bool X3>
+static cudaError_t launch_tc3(const CUtensorMap& b, const CUtensorMap& b2, const CUtensorMap& o, const CUtensorMap& r,
+                              const ConvTc3Args& args, int grid, size_t smem, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<BN, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  conv_tc3_kernel<BN, X3><<<grid, T3_THREADS, smem, s>>>(b, b2, o, r, args);
+  return cudaPeekAtLastError();
+}
+
+}  // namespace pdae
+
+using namespace pdae;
+
+struct pdae_conv_tc3_plan {
+  CUtensorMap tmB, tmB2, tmO, tmR;
+  ConvTc3Args args;
+  int BN, x3, grid;
+  size_t smem;
+};
+
+static int g_num_sms3 = 0;
+
+extern "C" int pdae_conv_tc3_supported(int H, int W, int Cin, int Cout) {
+  return (H % T3_TH == 0 && W % T3_TW == 0 && Cin % T3_BK == 0 && Cout % 64 == 0) ? 1 : 0;
+}
+
+extern "C" int pdae_conv_tc3_create(pdae_conv_tc3_plan** plan_out, const void* src1, int C1, const void* src2, int C2,
+                                    int src_dtype, const float* ab, int silu, const void* w, const float* bias,
+                                    const void* skp1, int S1, const void* skp2, int S2, const void* w_skip,
+                                    const void* residual, void* out, int out_dtype, float* ch_stats, int B, int H, int W,
+                                    int Cout, int bn_override) {
+  PDAE_REQUIRE(plan_out && src1 && ab && w && out, "conv_tc3_create: null pointer");
+  PDAE_REQUIRE(src_dtype == PDAE_BF16 || src_dtype == PDAE_F32, "conv_tc3_create: bad source dtype");
+  PDAE_REQUIRE(out_dtype == PDAE_BF16 || out_dtype == PDAE_F32, "conv_tc3_create: bad out dtype");
+  const bool x3 = src_dtype == PDAE_F32;
+  const int Cin = C1 + C2, Cs = S1 + S2;
+  PDAE_REQUIRE(C1 > 0 && C1 % T3_BK == 0 && C2 % T3_BK == 0 && (C2 == 0 || src2), "conv_tc3_create: bad C1=%d C2=%d", C1, C2);
+  PDAE_REQUIRE(S1 % T3_BK == 0 && S2 % T3_BK == 0 && (Cs == 0 || (skp1 && w_skip && S1 > 0)) && (S2 == 0 || skp2),
+               "conv_tc3_create: bad fused-skip operands S1=%d S2=%d", S1, S2);
+  PDAE_REQUIRE(!(Cs > 0 && residual), "conv_tc3_create: a block has an identity residual OR a skip conv, not both");
+  PDAE_REQUIRE(pdae_conv_tc3_supported(H, W, Cin, Cout), "conv_tc3_create: unsupported shape H=%d W=%d Cin=%d Cout=%d", H, W, Cin, Cout);
+  PDAE_REQUIRE(!(((uintptr_t)src1 | (uintptr_t)src2 | (uintptr_t)skp1 | (uintptr_t)skp2 | (uintptr_t)w | (uintptr_t)w_skip |
+                  (uintptr_t)out | (uintptr_t)residual | (uintptr_t)bias | (uintptr_t)ab) & 15),
+               "conv_tc3_create: pointers must be 16-byte aligned");
+  EncodeTiledFn3 enc = encode_fn3();
+  PDAE_REQUIRE(enc != nullptr, "conv_tc3_create: cuTensorMapEncodeTiled unavailable (no driver)");
+  if (g_num_sms3 == 0) {
+    int dev = 0;
+    PDAE_CUDA(cudaGetDevice(&dev));
+    PDAE_CUDA(cudaDeviceGetAttribute(&g_num_sms3, cudaDevAttrMultiProcessorCount, dev));
+  }
+  pdae_conv_tc3_plan* pl = new pdae_conv_tc3_plan();
+  ConvTc3Args& a = pl->args;
+  a.src1 = src1; a.src2 = src2; a.C1 = C1; a.C2 = C2; a.ab = ab;
+  a.skp1 = skp1; a.skp2 = skp2; a.S1 = S1; a.S2 = S2;
+  a.bias = bias; a.ch_stats = ch_stats;
+  a.B = B; a.H = H; a.W = W; a.Cout = Cout;
+  a.tiles_x = W / T3_TW; a.tiles_y = H / T3_TH; a.tiles_m = a.tiles_x * a.tiles_y * B;
+  a.kblocks = Cin / T3_BK; a.kblocks2 = Cs / T3_BK;
+  a.has_res = residual != nullptr; a.out_bf16 = out_dtype == PDAE_BF16; a.silu = silu;
+  pl->x3 = x3 ? 1 : 0;
+  int BN;
+  const int bn_max = x3 ? 128 : 256;   // split mode: two halo tiles per stage leave room for 128-wide weight tiles only
+  if ((bn_override == 64 || bn_override == 128 || bn_override == 256) && bn_override <= bn_max && Cout % bn_override == 0) BN = bn_override;
+  else if (!x3 && Cout % 256 == 0 && (long long)a.tiles_m * (Cout / 256) >= g_num_sms3) BN = 256;
+  else BN = (Cout % 128 == 0) ? 128 : 64;
+  pl->BN = BN;
+  a.tiles_total = a.tiles_m * (Cout / BN);
+  pl->grid = a.tiles_total < g_num_sms3 ? a.tiles_total : g_num_sms3;
+  const int a_stage = (x3 ? 2 : 1) * T3_HALO_BYTES, b_bytes = BN * T3_BK * 2;
+  const int staging = (a.has_res ? 4 : 2) * T3_STG_BYTES;
+  const int budget = 220 * 1024 - 1024 - staging;
+  int sa = 2;
+  int sb = (budget - sa * a_stage) / b_bytes;
+  if (sb > T3_MAX_SB) sb = T3_MAX_SB;
+  if (sb >= 6 && budget - 3 * a_stage - 4 * b_bytes >= 0) { sa = 3; sb = (budget - sa * a_stage) / b_bytes; if (sb > T3_MAX_SB) sb = T3_MAX_SB; }
+  if (sb < 2) {
+    delete pl;
+    PDAE_REQUIRE(false, "conv_tc3_create: shared-memory budget too small (BN=%d x3=%d)", BN, (int)x3);
+  }
+  a.sa = sa; a.sb = sb;
+  pl->smem = (size_t)sa * a_stage + (size_t)sb * b_bytes + staging + 1024;
+
+  auto fail = [&](const char* what, int code) {
+    delete pl;
+    set_error("conv_tc3_create: cuTensorMapEncodeTiled(%s) failed with %d", what, code);
+    return PDAE_EINVAL;
+  };
+  const int nmat = x3 ? 2 : 1;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)(9 * nmat)};
+    cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
+    cuuint32_t box[3] = {(cuuint32_t)T3_BK, (cuuint32_t)BN, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&pl->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("W", (int)r);
+  }
+  pl->tmB2 = pl->tmB;
+  if (Cs > 0) {
+    cuuint64_t dims[3] = {(cuuint64_t)Cs, (cuuint64_t)Cout, (cuuint64_t)nmat};
+    cuuint64_t strides[2] = {(cuuint64_t)Cs * 2, (cuuint64_t)Cout * Cs * 2};
+    cuuint32_t box[3] = {(cuuint32_t)T3_BK, (cuuint32_t)BN, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&pl->tmB2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_skip), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("W_skip", (int)r);
+  }
+  {
+    const int esz = a.out_bf16 ? 2 : 4;
+    cuuint32_t estr4[4] = {1, 1, 1, 1};
+    cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)Cout * esz, (cuuint64_t)W * Cout * esz, (cuuint64_t)H * W * Cout * esz};
+    cuuint32_t box[4] = {(cuuint32_t)(a.out_bf16 ? 64 : 32), (cuuint32_t)T3_TW, (cuuint32_t)T3_TH, 1};
+    const CUtensorMapDataType dt = a.out_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    CUresult r = enc(&pl->tmO, dt, 4, out, dims, strides, box, estr4, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("O", (int)r);
+    pl->tmR = pl->tmO;
+    if (a.has_res) {
+      r = enc(&pl->tmR, dt, 4, const_cast<void*>(residual), dims, strides, box, estr4, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail("R", (int)r);
+    }
+  }
+  *plan_out = pl;
+  return PDAE_OK;
+}
+
+extern "C" int pdae_conv_tc3_run(const pdae_conv_tc3_plan* pl, pdae_stream_t stream) {
+  PDAE_REQUIRE(pl, "conv_tc3_run: null plan");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e;
+  if (pl->x3) {
+    if (pl->BN == 64) e = launch_tc3<64, true>(pl->tmB, pl->tmB2, pl->tmO, pl->tmR, pl->args, pl->grid, pl->smem, s);
+    else e = launch_tc3<128, true>(pl->tmB, pl->tmB2, pl->tmO, pl->tmR, pl->args, pl->grid, pl->smem, s);
+  } else {
+    switch (pl->BN) {
+      case 64: e = launch_tc3<64, false>(pl->tmB, pl->tmB2, pl->tmO, pl->tmR, pl->args, pl->grid, pl->smem, s); break;
+      case 128: e = launch_tc3<128, false>(pl->tmB, pl->tmB2, pl->tmO, pl->tmR, pl->args, pl->grid, pl->smem, s); break;
+      default: e = launch_tc3<256, false>(pl->tmB, pl->tmB2, pl->tmO, pl->tmR, pl->args, pl->grid, pl->smem, s); break;
+    }
+  }
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    set_error("launch of conv_tc3_kernel<%d,%d> failed: %s", pl->BN, pl->x3, cudaGetErrorString(e));
+    return PDAE_ECUDA;
+  }
+  return PDAE_OK;
+}
+
+extern "C" void pdae_conv_tc3_destroy(pdae_conv_tc3_plan* pl) { delete pl; }

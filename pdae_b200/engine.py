@@ -134,6 +134,9 @@ class Plan:
         # residual stream (block outputs / skip tensors) kept in bf16 instead of fp32: halves the HBM bytes of the
         # bandwidth-bound top-level layers.  "bf16" precision + v2 kernel only.
         self.stream_bf16 = self.tc and self.v2 and not self.x3 and os.environ.get("PDAE_STREAM_BF16", "1") == "1"
+        # conv_tc3: GroupNorm-apply / AdaGN / SiLU (and the bf16x3 hi/lo split) fused into the conv's operand path -- the
+        # activated tensor never exists in HBM.  PDAE_TC3=0 restores the separate gn_apply + conv_tc2 pair (A/B aid).
+        self.fuse_prologue = self.tc and self.v2 and os.environ.get("PDAE_TC3", "0") == "1"   # (default flips to on once validated on the GPU)
         self.fuse_coef = os.environ.get("PDAE_FUSE_COEF", "0") == "1"   # GN coefficients inside gn_apply: measured 0.15 ms/step SLOWER under graph replay (profiles/README.md) -> off
         self.L = _native.lib()
         self.ops: List[Tuple[str, list]] = []
@@ -148,6 +151,7 @@ class Plan:
         self._compiled = None
         self._tc_handles: List[ctypes.c_void_p] = []
         self._tc2_handles: List[ctypes.c_void_p] = []
+        self._tc3_handles: List[ctypes.c_void_p] = []
         self.n_launch = 0
         self.keep_all = False
         self.dropout_masks: list = []   # (block, mask buffer, p): filled by the trainer before every training forward
@@ -299,6 +303,9 @@ class Plan:
             if fn == "conv_tc2_skip":
                 compiled.append(self._compile_tc2_skip(args))
                 continue
+            if fn == "conv_tc3":
+                compiled.append(self._compile_tc3(args))
+                continue
             cargs = []
             sidx = -1
             for k, a in enumerate(args):
@@ -362,6 +369,17 @@ class Plan:
         self._tc2_handles.append(h)
         return (self.L.pdae_conv_tc2_run, [h, None], 1, "conv_tc2")
 
+    def _compile_tc3(self, args):
+        (s1, C1, s2, C2, sdt, ab, silu, w, bias, k1, S1, k2, S2, wsk, resid, out, odt, stats, B, H, W, Cout, bn) = args
+        h = ctypes.c_void_p()
+        rc = self.L.pdae_conv_tc3_create(ctypes.byref(h), self._resolve(s1), C1, self._resolve(s2), C2, sdt, self._resolve(ab), silu,
+                                         self._resolve(w), self._resolve(bias), self._resolve(k1), S1, self._resolve(k2), S2,
+                                         self._resolve(wsk), self._resolve(resid), self._resolve(out), odt, self._resolve(stats),
+                                         B, H, W, Cout, bn)
+        _native.check(rc, "pdae_conv_tc3_create")
+        self._tc3_handles.append(h)
+        return (self.L.pdae_conv_tc3_run, [h, None], 1, "conv_tc3")
+
     def _compile_gemm_softmax(self, args):
         a, a_ld, a_bs, b, b_ld, b_bs, out, o_ld, o_bs, batch, M, N, K, alpha = args
         h = ctypes.c_void_p()
@@ -401,6 +419,8 @@ class Plan:
                 self.L.pdae_conv_tc_destroy(h)
             for h in self._tc2_handles:
                 self.L.pdae_conv_tc2_destroy(h)
+            for h in self._tc3_handles:
+                self.L.pdae_conv_tc3_destroy(h)
         except Exception:
             pass
 
@@ -552,6 +572,74 @@ class Plan:
         self.call("conv2d_simt", x, _DT[x.dtype], int(in_nchw), wp, bias_b, residual, out, int(out_nchw), B, H, W, Cin, Cout,
                   k, stride, pad, int(a_silu), _STREAM, flops=2.0 * B * Ho * Wo * Cout * Cin * k * k)
         return None
+
+    # ---- fused-prologue conv (conv_tc3) --------------------------------------------------------------------------------
+    def can_fuse_prologue(self, srcs: Sequence[Tuple[Optional[Buf], int]], Cout: int, H: int, W: int) -> bool:
+        """3x3 stride-1 conv whose input is SiLU(a*x+b) of (a virtual concat of) NHWC tensors already in this mode's
+        stream dtype: 16 x 8 output tiles of one image, 64-channel k-blocks that do not straddle the concat seam."""
+        if not self.fuse_prologue or H % 16 or W % 8 or Cout % 64:
+            return False
+        want = torch.float32 if self.x3 else torch.bfloat16
+        for b, C in srcs:
+            if b is None:
+                continue
+            if C <= 0 or C % 64 or b.dtype != want or b.split3:
+                return False
+        return True
+
+    def coef_buffer(self, ab) -> Buf:
+        """Materialise deferred GroupNorm coefficients ([B][2][C] fp32: a | b) with one gn_coef_ch launch."""
+        if not isinstance(ab, CoefSpec):
+            return ab
+        c = ab
+        buf = self.new((c.B, 2, c.C1 + c.C2), torch.float32, "gn_ab")
+        self.call("gn_coef_ch", c.stats1, c.C1, c.stats2, c.C2, c.gamma, c.beta, c.B, c.HW, ctypes.c_float(1e-5),
+                  c.emb, c.emb_ld, c.embz, c.embz_ld, buf, _STREAM)
+        return buf
+
+    def conv_fused(self, s1: Buf, C1: int, s2: Optional[Buf], C2: int, ab, weight: torch.Tensor, bias: Optional[torch.Tensor],
+                   out: Buf, *, B, H, W, Cout, silu=True, residual: Optional[Buf] = None, skip=None, want_stats=False,
+                   bn_override=0) -> Optional["BufView"]:
+        """out = conv3x3(SiLU(a*cat(s1, s2)+b)) + bias (+ residual | + 1x1 skip conv of cat(skip sources)) on conv_tc3.
+        skip = (k1, S1, k2, S2, skip_weight, skip_bias): raw (un-normalised) sources of the ResBlock's skip_connection."""
+        Cin = C1 + C2
+        x3 = self.x3
+        ab = self.coef_buffer(ab)
+        if x3:
+            def pack3(Cin=Cin):
+                w = weight.detach().reshape(Cout, Cin, 9).float()
+                hi = w.to(torch.bfloat16)
+                lo = (w - hi.float()).to(torch.bfloat16)
+                return torch.stack([hi, lo], 0).permute(3, 0, 1, 2).contiguous()          # [9][2][Cout][Cin]
+            wp = self.pack((id(weight), "tc3_x3"), [weight], pack3)
+        else:
+            wp = self.pack((id(weight), "tc"), [weight],
+                           lambda: weight.detach().reshape(Cout, Cin, 9).permute(2, 0, 1).to(torch.bfloat16))
+        fl = 2.0 * B * H * W * Cout * Cin * 9
+        k1 = k2 = wsk = None
+        S1 = S2 = 0
+        if skip is not None:
+            assert residual is None
+            k1, S1, k2, S2, sw, sb = skip
+            Cs = S1 + S2
+            if x3:
+                def packs(Cs=Cs):
+                    w = sw.detach().reshape(Cout, Cs).float()
+                    hi = w.to(torch.bfloat16)
+                    return torch.stack([hi, (w - hi.float()).to(torch.bfloat16)], 0).contiguous()   # [2][Cout][Cs]
+                wsk = self.pack((id(sw), "tc3_skip_x3"), [sw], packs)
+            else:
+                wsk = self.pack((id(sw), "tc_skip"), [sw], lambda: sw.detach().reshape(Cout, Cs).to(torch.bfloat16))
+            bias_b = self.pack((id(bias), id(sb), "bias_sum"), [bias, sb], lambda: (bias.detach() + sb.detach()).float())
+            self.params.append((sb, sb.data_ptr()))
+            self.params.append((bias, bias.data_ptr()))
+            fl += 2.0 * B * H * W * Cout * Cs
+        else:
+            bias_b = self.param(bias)
+        stats = self.new_stats(B, Cout) if want_stats else None
+        self.call("conv_tc3", s1, C1, s2, C2, PDAE_F32 if x3 else PDAE_BF16, ab, int(silu), wp, bias_b, k1, S1, k2, S2, wsk,
+                  residual, out, _DT[out.dtype], stats, B, H, W, Cout, bn_override or self.bn_override, flops=fl)
+        return stats
 
     def linear(self, x: Buf, weight: torch.Tensor, bias: Optional[torch.Tensor], out: Buf, *, B, Cin, Cout, a_silu=False,
                wkey=None) -> None:

@@ -269,6 +269,45 @@ class _ResBase(PlannedModule):
 
         ab1 = P.gn_coef(x.b1, x.C1, x.b2, x.C2, gn1.weight, gn1.bias, B=B, HW=H * W, stats1=x.s1, stats2=x.s2)
         sums1 = P.last_sums
+        eb, eoff, eld = emb
+        zb = zoff = zld = None
+        if self.has_z:
+            zb, zoff, zld = embz
+        # ---- fused-prologue path (conv_tc3): GN-apply / AdaGN / SiLU (and the hi/lo split) happen inside the convs' operand
+        # path; the activated tensors act1 / act2 and the concatenated raw input never exist in HBM ----
+        srcs = [(x.b1, x.C1), (x.b2, x.C2)]
+        fuse2 = tape is None and not drop and P.can_fuse_prologue([(None, Co)], Co, H2, W2) and \
+            (ident or (self.skip_connection.kernel_size[0] == 1 and P.can_fuse_prologue(srcs, Co, H2, W2)))
+        fuse1 = fuse2 and not self.updown and P.can_fuse_prologue(srcs, Co, H, W)
+        if fuse2 and (fuse1 or self.updown) and (not ident or self.updown or x.b2 is None):
+            sdt = torch.float32 if P.x3 else torch.bfloat16          # this mode's stream dtype == conv_tc3's source dtype
+            raw = None
+            if fuse1:
+                h = P.new((B, H2, W2, Co), sdt, "res_h")
+                hs = P.conv_fused(x.b1, x.C1, x.b2, x.C2, ab1, conv1.weight, conv1.bias, h, B=B, H=H2, W=W2, Cout=Co,
+                                  want_stats=True)
+            else:
+                # up / down-sampling block: the resample (of both the activated h and the raw x, module.py:282-288) stays a
+                # gn_apply pass; its conv1 runs on conv_tc2, conv2 below on conv_tc3
+                act1, raw = P.gn_apply(x.b1, x.C1, x.b2, x.C2, ab1, silu=True, resample=rs, B=B, H=H, W=W,
+                                       act_dtype=torch.bfloat16, raw_dtype=sdt)
+                h = P.new((B, H2, W2, Co), sdt, "res_h")
+                hs = P.conv(act1, conv1.weight, conv1.bias, h, B=B, H=H2, W=W2, Cin=C, Cout=Co, k=3, want_stats=True)
+            ab2 = P.gn_coef(h, Co, None, 0, gn2.weight, gn2.bias, B=B, HW=H2 * W2, emb=eb.at(eoff), emb_ld=eld,
+                            embz=zb.at(zoff) if zb is not None else None, embz_ld=zld or 0, stats1=hs)
+            out = P.new((B, H2, W2, Co), sdt, "res_out")
+            if ident:
+                resid = raw if raw is not None else x.b1
+                assert resid.dtype == sdt
+                os_ = P.conv_fused(h, Co, None, 0, ab2, conv2.weight, conv2.bias, out, B=B, H=H2, W=W2, Cout=Co, residual=resid,
+                                   want_stats=True)
+            else:
+                sk = self.skip_connection
+                k1, S1, k2, S2 = (raw, C, None, 0) if raw is not None else (x.b1, x.C1, x.b2, x.C2)
+                os_ = P.conv_fused(h, Co, None, 0, ab2, conv2.weight, conv2.bias, out, B=B, H=H2, W=W2, Cout=Co,
+                                   skip=(k1, S1, k2, S2, sk.weight, sk.bias), want_stats=True)
+            return Src(out, Co, B, H2, W2, s1=os_)
+
         tc1 = P.use_tc(C, Co, 3, 1, H2, W2)
         tc2 = P.use_tc(Co, Co, 3, 1, H2, W2)
         tcs = (not ident) and P.use_tc(C, Co, self.skip_connection.kernel_size[0], 1, H2, W2)
