@@ -249,6 +249,13 @@ int pdae_conv_tc2_run(const pdae_conv_tc2_plan* plan, pdae_stream_t stream);
 /* P = softmax(alpha * S) per row, fp32 in -> bf16 out.  vT[b*heads+h][c][t] = V part of qkv (bf16 [B][T][3C]).        */
 int pdae_softmax_bf16(const float* S, void* P_bf16, int64_t rows, int cols, float alpha, pdae_stream_t stream);
 int pdae_transpose_v(const void* qkv_bf16, void* vT_bf16, int B, int T, int C, int heads, int legacy, pdae_stream_t stream);
+/* Split-operand ("bf16x3") attention: re-lay the fp32 qkv rows as bf16 blocks Q3 = [q_hi|q_lo|q_hi], K3 = [k_hi|k_hi|k_lo]
+ * ([B*heads][T][3*ch]) and VT3 = [vT_hi|vT_hi|vT_lo] ([B*heads][ch][3*T]) so that QK^T and PV (model/module.py:452-456,
+ * 483-487) run as batched tcgen05 GEMMs with fp32-grade products; pdae_softmax_split3 turns the fp32 scores into
+ * P3 = [p_hi|p_lo|p_hi] with p = softmax(alpha * S) evaluated in fp32.                                                  */
+int pdae_qkv_split3(const float* qkv, void* Q3, void* K3, void* VT3, int B, int T, int C, int heads, int legacy,
+                    pdae_stream_t stream);
+int pdae_softmax_split3(const float* S, void* P3_bf16, int64_t rows, int cols, float alpha, pdae_stream_t stream);
 void pdae_conv_tc2_destroy(pdae_conv_tc2_plan* plan);
 
 /* Stem: nn.Conv2d(input_channel, base, 3, padding=1) on the NCHW fp32 image (unet.py:62-64, shift_unet.py:64-66), written

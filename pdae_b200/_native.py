@@ -108,6 +108,8 @@ _SIGS = {
     "pdae_conv_tc3_destroy": (None, [_P]),
     "pdae_softmax_bf16": (c_int, [_P, _P, c_int64, c_int, c_float, _P]),
     "pdae_transpose_v": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "pdae_qkv_split3": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "pdae_softmax_split3": (c_int, [_P, _P, c_int64, c_int, c_float, _P]),
     "pdae_conv_tc2_destroy": (None, [_P]),
     "pdae_mlp_mod_ln_act_bwd": (c_int, [_P, _P, _P, _P, c_float, c_int, _P, c_int, _P, _P, _P, _P, c_int, c_int, _P]),
     "pdae_mul_mask_cols": (c_int, [_P, c_int, _P, c_float, c_int, c_int, _P]),

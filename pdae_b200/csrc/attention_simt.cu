@@ -165,6 +165,85 @@ __global__ void __launch_bounds__(256) transpose_v_kernel(const __nv_bfloat16* _
   }
 }
 
+// ---- split-operand ("bf16x3") attention on the tensor cores -----------------------------------------------------------
+// The fp32 qkv rows are re-laid-out as bf16 operand blocks so that the two attention GEMMs run on conv_tc2's batched-GEMM
+// mode with fp32-grade products:  S = [q_hi|q_lo|q_hi] * [k_hi|k_hi|k_lo]^T  and  A = [p_hi|p_lo|p_hi] * [vT_hi|vT_hi|vT_lo]^T.
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// Q3 / K3: [B*heads][T][3*ch] ; one thread per (z, t, c)
+__global__ void __launch_bounds__(256) qk_split3_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ Q3,
+                                                        __nv_bfloat16* __restrict__ K3, int T, int C3, int ch, int heads,
+                                                        long long koff, long long hs, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % ch);
+  const long long zt = i / ch;
+  const int t = (int)(zt % T);
+  const int z = (int)(zt / T), b = z / heads, h = z % heads;
+  const float* row = qkv + ((long long)b * T + t) * C3 + h * hs;
+  __nv_bfloat16 qh, ql, kh, kl;
+  split_bf16(row[c], qh, ql);
+  split_bf16(row[koff + c], kh, kl);
+  __nv_bfloat16* q = Q3 + zt * 3 * ch;
+  __nv_bfloat16* k = K3 + zt * 3 * ch;
+  q[c] = qh; q[ch + c] = ql; q[2 * ch + c] = qh;
+  k[c] = kh; k[ch + c] = kh; k[2 * ch + c] = kl;
+}
+
+// VT3: [B*heads][ch][3*T] = [vT_hi | vT_hi | vT_lo]  (32 x 32 shared-memory transpose)
+__global__ void __launch_bounds__(256) v_split3_transpose_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ VT3,
+                                                                 int T, int C3, int ch, int heads, long long voff, long long hs) {
+  __shared__ float tile[32][33];
+  const int z = blockIdx.z, b = z / heads, h = z % heads;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const float* src = qkv + (long long)b * T * C3 + voff + h * hs;
+#pragma unroll
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + tx;
+    tile[i][tx] = (t < T && c < ch) ? src[(long long)t * C3 + c] : 0.f;
+  }
+  __syncthreads();
+  __nv_bfloat16* dst = VT3 + (long long)z * ch * 3 * T;
+#pragma unroll
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + tx;
+    if (c < ch && t < T) {
+      __nv_bfloat16 hi, lo;
+      split_bf16(tile[tx][i], hi, lo);
+      __nv_bfloat16* r = dst + (long long)c * 3 * T;
+      r[t] = hi; r[T + t] = hi; r[2 * T + t] = lo;
+    }
+  }
+}
+
+// P3[row] = [p_hi | p_lo | p_hi],  p = softmax(alpha * S[row])  -- one warp per row, fp32 arithmetic (module.py:452-455)
+__global__ void __launch_bounds__(256) softmax_split3_kernel(const float* __restrict__ S, __nv_bfloat16* __restrict__ P3,
+                                                             long long rows, int cols, float alpha) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* s = S + row * cols;
+  float mx = -3.0e38f;
+  for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, s[c] * alpha);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int c = lane; c < cols; c += 32) sum += expf(s[c] * alpha - mx);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.0f / sum;
+  __nv_bfloat16* p = P3 + row * 3 * cols;
+  for (int c = lane; c < cols; c += 32) {
+    __nv_bfloat16 hi, lo;
+    split_bf16(expf(s[c] * alpha - mx) * inv, hi, lo);
+    p[c] = hi; p[cols + c] = lo; p[2 * cols + c] = hi;
+  }
+}
+
 }  // namespace pdae
 
 using namespace pdae;
@@ -173,6 +252,31 @@ extern "C" int pdae_softmax_bf16(const float* S, void* P_bf16, int64_t rows, int
   PDAE_REQUIRE(S && P_bf16 && cols % 4 == 0, "softmax_bf16: bad args");
   softmax_rows_bf16_kernel<<<cdiv(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(S, (__nv_bfloat16*)P_bf16, rows, cols, alpha);
   PDAE_LAUNCH_CHECK("softmax_rows_bf16_kernel");
+  return PDAE_OK;
+}
+
+
+// fp32 qkv [B][T][3C] (channel order per `legacy`, model/module.py:440-447 / 469-477) -> the split-operand GEMM inputs
+extern "C" int pdae_qkv_split3(const float* qkv, void* Q3, void* K3, void* VT3, int B, int T, int C, int heads, int legacy,
+                               pdae_stream_t stream) {
+  PDAE_REQUIRE(qkv && Q3 && K3 && VT3 && heads > 0 && C % heads == 0, "qkv_split3: bad args");
+  const int ch = C / heads;
+  const long long hs = legacy ? 3LL * ch : ch, ko = legacy ? ch : C, vo = legacy ? 2LL * ch : 2LL * C;
+  PDAE_REQUIRE((long long)B * heads <= 65535, "qkv_split3: B*heads too large");
+  const long long total = (long long)B * heads * T * ch;
+  cudaStream_t s = (cudaStream_t)stream;
+  qk_split3_kernel<<<cdiv(total, 256), 256, 0, s>>>(qkv, (__nv_bfloat16*)Q3, (__nv_bfloat16*)K3, T, 3 * C, ch, heads, ko, hs, total);
+  PDAE_LAUNCH_CHECK("qk_split3_kernel");
+  dim3 grid(cdiv(T, 32), cdiv(ch, 32), B * heads);
+  v_split3_transpose_kernel<<<grid, 256, 0, s>>>(qkv, (__nv_bfloat16*)VT3, T, 3 * C, ch, heads, vo, hs);
+  PDAE_LAUNCH_CHECK("v_split3_transpose_kernel");
+  return PDAE_OK;
+}
+
+extern "C" int pdae_softmax_split3(const float* S, void* P3_bf16, int64_t rows, int cols, float alpha, pdae_stream_t stream) {
+  PDAE_REQUIRE(S && P3_bf16 && rows > 0 && cols > 0, "softmax_split3: bad args");
+  softmax_split3_kernel<<<cdiv(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(S, (__nv_bfloat16*)P3_bf16, rows, cols, alpha);
+  PDAE_LAUNCH_CHECK("softmax_split3_kernel");
   return PDAE_OK;
 }
 

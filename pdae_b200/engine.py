@@ -399,7 +399,7 @@ class Plan:
         return (self.L.pdae_conv_tc2_run, [h, None], 1, "gemm_tc2")
 
     def gemm_tc(self, a, a_ld, a_bs, b, b_ld, b_bs, out, out_ld, out_bs, *, batch, M, N, K, out_dtype,
-                softmax_alpha: Optional[float] = None) -> None:
+                softmax_alpha: Optional[float] = None, flops: Optional[float] = None) -> None:
         """Batched out_i = A_i (MxK) * B_i (NxK)^T on the persistent tcgen05 kernel; a/b/out are Buf or BufView.
         softmax_alpha: store softmax_rows(alpha * out_i) (bf16) instead -- needs N in {64,128,256} (row inside one tile)."""
         if softmax_alpha is not None:
@@ -408,10 +408,15 @@ class Plan:
                       ctypes.c_float(softmax_alpha), flops=2.0 * batch * M * N * K)
             return
         self.call("gemm_tc2", a, a_ld, a_bs, b, b_ld, b_bs, out, _DT[out_dtype], out_ld, out_bs, batch, M, N, K,
-                  flops=2.0 * batch * M * N * K)
+                  flops=2.0 * batch * M * N * K if flops is None else flops)
 
     def can_gemm_tc(self, M: int, N: int, K: int) -> bool:
         return self.tc and self.v2 and not self.x3 and M % 128 == 0 and N % 64 == 0 and K % 64 == 0
+
+    def can_gemm_x3(self, M: int, N: int, K: int) -> bool:
+        """Batched GEMM in the split-operand mode: K is the LOGICAL depth (the operand blocks hold 3*K)."""
+        return self.x3 and self.v2 and M % 128 == 0 and N % 64 == 0 and K % 64 == 0 and \
+            os.environ.get("PDAE_X3_ATTN_TC", "1") == "1"
 
     def __del__(self):
         try:

@@ -495,6 +495,28 @@ class AttentionBlock(PlannedModule):
             for h in range(heads):
                 P.gemm_tc(Pm.at(h * T * T), T, heads * T * T, vT.at(h * ch * T), T, heads * ch * T,
                           att.at(h * ch), C, T * C, batch=B, M=T, N=ch, K=T, out_dtype=torch.bfloat16)
+        elif tcq and tape is None and P.can_gemm_x3(T, T, ch) and P.can_gemm_x3(T, ch, T):
+            # ---- split-operand tensor-core attention (fp32-grade): fp32 qkv -> [hi|lo|hi] x [hi|hi|lo] operand blocks ->
+            # S = Q K^T (fp32) -> fp32 softmax, split -> A = P V (fp32); every product is three bf16 tcgen05 MMAs ----
+            qkv = P.new((B, T, 3 * C), torch.float32, "qkv")
+            P.conv(xn, self.qkv.weight, self.qkv.bias, qkv, B=B, H=H, W=W, Cin=C, Cout=3 * C, k=1)
+            Z = B * heads
+            Q3 = P.new((Z, T, 3 * ch), torch.bfloat16, "q3")
+            K3 = P.new((Z, T, 3 * ch), torch.bfloat16, "k3")
+            VT3 = P.new((Z, ch, 3 * T), torch.bfloat16, "vT3")
+            P.call("qkv_split3", qkv, Q3, K3, VT3, B, T, C, heads, int(legacy), _STREAM)
+            S = P.new((Z, T, T), torch.float32, "att_scores")
+            P.gemm_tc(Q3, 3 * ch, T * 3 * ch, K3, 3 * ch, T * 3 * ch, S, T, T * T, batch=Z, M=T, N=T, K=3 * ch,
+                      out_dtype=torch.float32, flops=2.0 * Z * T * T * ch)
+            P3 = P.new((Z, T, 3 * T), torch.bfloat16, "att_probs3")
+            P.call("softmax_split3", S, P3, ctypes.c_int64(Z * T), T, ctypes.c_float(1.0 / math.sqrt(ch)), _STREAM)
+            att = P.new((B, T, C), torch.float32, "att")
+            for h in range(heads):
+                P.gemm_tc(P3.at(h * T * 3 * T), 3 * T, heads * T * 3 * T, VT3.at(h * ch * 3 * T), 3 * T, heads * ch * 3 * T,
+                          att.at(h * ch), C, T * C, batch=B, M=T, N=ch, K=3 * T, out_dtype=torch.float32,
+                          flops=2.0 * B * T * ch * T)
+            att, _ = P.gn_apply(att, C, None, 0, None, silu=False, resample=RESAMPLE_NONE, B=B, H=H, W=W,
+                                act_dtype=torch.bfloat16)
         else:
             qkv = P.new((B, T, 3 * C), torch.float32, "qkv")
             P.conv(xn, self.qkv.weight, self.qkv.bias, qkv, B=B, H=H, W=W, Cin=C, Cout=3 * C, k=1)

@@ -138,11 +138,14 @@ def test_attention_tensor_core(C, heads, new_order):
     sd = {"blk." + k: v for k, v in cases.sd_of(m).items()}
     ref = O.attention_block(sd, "blk", x, heads, new_order)
     m = m.cuda()
-    for precision in ("fp32", "bf16"):
+    for precision in ("fp32", "bf16", "bf16x3"):
         m.precision = precision
         with torch.no_grad():
             y = m(x.cuda())
         check(y, ref, precision, f"attention C={C} heads={heads} new={new_order}")
+    plan3 = [v for k, v in m._plans().items() if k[1] == "bf16x3"][0][0]
+    # split-operand mode: QK^T and PV as batched tcgen05 GEMMs on [hi|lo|hi] x [hi|hi|lo] operand blocks (fp32-grade)
+    assert any(op[0] == "qkv_split3" for op in plan3.ops) and not any(op[0] == "attention_simt" for op in plan3.ops)
     plan = [v for k, v in m._plans().items() if k[1] == "bf16"][0][0]
     if plan.v2:   # (the legacy v1 kernel, PDAE_TC_V1=1, has no batched-GEMM mode: CUDA-core attention there)
         assert any(op[0].startswith("gemm_tc2") for op in plan.ops), "tensor-core attention path not taken"
