@@ -94,3 +94,80 @@ def allreduce_grads_(params, bucket_bytes: int = 32 << 20) -> float:
             g.copy_(flat[off: off + g.numel()].view_as(g))
             off += g.numel()
     return 1.0 / dist.get_world_size()
+
+
+class OverlappedGradAllReduce:
+    """DDP-equivalent gradient exchange that OVERLAPS with the backward pass (trainer/train_representation_learning.py:29,39
+    wraps encoder and decoder in DistributedDataParallel).  Parameters are grouped in the order their gradients become
+    ready: the hand-written ShiftUNet backward delivers every decoder gradient at once, then dz flows into the encoder's
+    backward -- so the decoder bucket's SUM all-reduce is launched (async, on the process group's own stream) from a
+    post-accumulate-grad hook the moment the decoder gradients land and runs while the encoder backward computes.
+    `finish()` waits, scatters the reduced values back into `.grad` and returns 1/world for the optimizer to fold in
+    (`FusedAdamEMA.step(grad_scale=...)`) -- the mean is never a separate pass."""
+
+    def __init__(self, groups, bucket_bytes: int = 64 << 20):
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.buckets = []          # [params, flat buffer or None, pending count]
+        for params in groups:
+            cur, size = [], 0
+            for p in params:
+                if not p.requires_grad:
+                    continue
+                nb = p.numel() * p.element_size()
+                if cur and size + nb > bucket_bytes:
+                    self.buckets.append({"params": cur})
+                    cur, size = [], 0
+                cur.append(p)
+                size += nb
+            if cur:
+                self.buckets.append({"params": cur})
+        self._of = {}
+        self.handles = []
+        for bi, bk in enumerate(self.buckets):
+            bk["left"] = len(bk["params"])
+            bk["flat"] = None
+            for p in bk["params"]:
+                self._of[p] = bi
+                self.handles.append(p.register_post_accumulate_grad_hook(self._hook))
+        self.pending = []
+
+    def _hook(self, p):
+        bk = self.buckets[self._of[p]]
+        bk["left"] -= 1
+        if bk["left"] == 0:
+            self._launch(bk)
+
+    def _launch(self, bk):
+        if self.world == 1:
+            return
+        grads = [p.grad for p in bk["params"]]
+        n = sum(g.numel() for g in grads)
+        if bk["flat"] is None or bk["flat"].numel() != n or bk["flat"].device != grads[0].device:
+            bk["flat"] = torch.empty(n, dtype=grads[0].dtype, device=grads[0].device)
+        off = 0
+        for g in grads:
+            bk["flat"][off: off + g.numel()].copy_(g.reshape(-1))
+            off += g.numel()
+        self.pending.append((dist.all_reduce(bk["flat"], op=dist.ReduceOp.SUM, async_op=True), bk))
+
+    def finish(self) -> float:
+        """Call after loss.backward(): waits for every collective and writes the sums back into `.grad`."""
+        for work, bk in self.pending:
+            work.wait()
+            off = 0
+            for p in bk["params"]:
+                n = p.grad.numel()
+                p.grad.copy_(bk["flat"][off: off + n].view_as(p.grad))
+                off += n
+        self.pending = []
+        for bk in self.buckets:
+            if bk["left"] != 0 and self.world > 1 and any(p.grad is not None for p in bk["params"]):
+                raise RuntimeError("OverlappedGradAllReduce: a bucket received gradients for only some of its parameters; "
+                                   "group parameters that are trained together")
+            bk["left"] = len(bk["params"])
+        return 1.0 / self.world
+
+    def remove(self):
+        for h in self.handles:
+            h.remove()
+        self.handles = []

@@ -70,14 +70,14 @@ def test_ddpm_loops():
     cfg, g = load_golden("glue_ddpm")
     d = _gd({"timesteps": cfg["timesteps"], "betas_type": "linear"})
     s = cfg["seeds"]
+    # (modules are built BEFORE seeding: nn.Conv2d's default init draws from the same CPU generator)
+    unet, unet_ls, dec = _net("unet", cfg["cfg_unet"], 16), _net("unet", cfg["cfg_sigma"], 16), _net("shiftunet", cfg["cfg_shift"], 16)
     with torch.no_grad():
         cases.CpuStream(s[0], DEV).install(d)
-        assert_close(d.regular_ddpm_sample(_net("unet", cfg["cfg_unet"], 16), i["xT"]), g["regular"], what="regular ddpm", **LOOP)
+        assert_close(d.regular_ddpm_sample(unet, i["xT"]), g["regular"], what="regular ddpm", **LOOP)
         cases.CpuStream(s[1], DEV).install(d)
-        assert_close(d.regular_ddpm_sample(_net("unet", cfg["cfg_sigma"], 16), i["xT"]), g["learned_sigma"],
-                     what="ddpm with learned sigma", **LOOP)
+        assert_close(d.regular_ddpm_sample(unet_ls, i["xT"]), g["learned_sigma"], what="ddpm with learned sigma", **LOOP)
         cases.CpuStream(s[2], DEV).install(d)
-        dec = _net("shiftunet", cfg["cfg_shift"], 16)
         assert_close(d.representation_learning_ddpm_sample(None, dec, i["xT"], i["xT"], i["z1"]), g["representation"],
                      what="representation ddpm", **LOOP)
 
@@ -86,10 +86,10 @@ def test_ddpm_loops():
 def test_latent_diffusion_sample_with_stop_percent(precision):
     i = _cu(cases.glue_inputs())
     cfg, g = load_golden("glue_latent_sample")
-    d = cases.CpuStream(cfg["seed"], DEV).install(_gd())
     mlp, _ = cases.model_case({"kind": "mlp", "cfg": cfg["cfg_mlp"]})
     mlp = mlp.cuda().eval()
     dec = _net("shiftunet", cfg["cfg_shift"], 16, precision)
+    d = cases.CpuStream(cfg["seed"], DEV).install(_gd())     # seed AFTER building the modules (their default init draws too)
     with torch.no_grad():
         y = d.latent_diffusion_sample("ddim10", "ddim10", mlp, dec, i["xT"], i["mean64"], i["std64"])
     assert_close(y, g["y"], what="latent_diffusion_sample (stop_percent 0.3 tail on the epsilon-only plan)", **LOOP)

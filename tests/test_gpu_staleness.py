@@ -69,9 +69,12 @@ def test_fused_adam_ema_step_is_seen_by_cached_plans():
     assert abs(float(loss2) - float(loss1)) > 1e-6, "the optimizer step did not change the loss"
     assert_close(loss2, loss2f, rtol=1e-5, atol=1e-7, what="step-2 loss vs fresh module")
     fresh = dict(dec2.named_parameters())
+    gmax = max(float(p.grad.abs().max()) for p in dec.parameters() if p.grad is not None)
     for k, p in dec.named_parameters():
         if p.grad is not None:
-            assert rel_l2(p.grad, fresh[k].grad) < 1e-4, k
+            # conv biases feeding a GroupNorm have analytically ~zero gradients (rounding noise): absolute floor
+            err = float((p.grad - fresh[k].grad).abs().max())
+            assert rel_l2(p.grad, fresh[k].grad) < 1e-4 or err < 1e-6 * gmax, (k, err, gmax)
     # EMA net: direct forward (version bump) and a sampling loop both use the updated weights
     ema_fresh, _ = cases.model_case({"kind": "shiftunet", "cfg": cfg["cfg"], "size": 64})
     ema_fresh = ema_fresh.cuda().eval()
