@@ -425,9 +425,9 @@ def main():
                 autoencode(x_dev)
                 ms_m = timed(lambda: autoencode(x_dev), 1)
                 pl_m, _ = dec.plan_for(B, size, size)
-                r_m, _k = (None, None) if args.no_profile else kernel_view(pl_m)
+                r_m, k_m = (None, None) if args.no_profile else kernel_view(pl_m)
                 modes[m] = {"value": round(world * B / (ms_m / 1e3), 4), "unit": "images/s", "ms_per_step": round(ms_m, 3),
-                            "steps": 1, "warmup": 1, "roofline": r_m,
+                            "steps": 1, "warmup": 1, "roofline": r_m, "kernels_per_decoder_step": k_m,
                             "parity": "see cpu_baseline.parity.modes (N=1 line)"}
             except Exception as e:   # never lose the headline to a secondary measurement
                 modes[m] = {"error": repr(e)[:300]}

@@ -136,7 +136,7 @@ class Plan:
         self.stream_bf16 = self.tc and self.v2 and not self.x3 and os.environ.get("PDAE_STREAM_BF16", "1") == "1"
         # conv_tc3: GroupNorm-apply / AdaGN / SiLU (and the bf16x3 hi/lo split) fused into the conv's operand path -- the
         # activated tensor never exists in HBM.  PDAE_TC3=0 restores the separate gn_apply + conv_tc2 pair (A/B aid).
-        self.fuse_prologue = self.tc and self.v2 and os.environ.get("PDAE_TC3", "0") == "1"   # (default flips to on once validated on the GPU)
+        self.fuse_prologue = self.tc and self.v2 and os.environ.get("PDAE_TC3", "1") == "1"
         self.fuse_coef = os.environ.get("PDAE_FUSE_COEF", "0") == "1"   # GN coefficients inside gn_apply: measured 0.15 ms/step SLOWER under graph replay (profiles/README.md) -> off
         self.L = _native.lib()
         self.ops: List[Tuple[str, list]] = []
