@@ -37,7 +37,7 @@ constexpr int T3_HROWS = T3_TH + 2;
 constexpr int T3_HALO = T3_P * T3_HROWS;              // 180 halo pixels = 180 shared-memory rows of 128 B
 constexpr int T3_HALO_BYTES = 23 * 1024;              // 180 * 128 = 23040 B, padded to a 1024-B multiple (swizzle atom alignment)
 constexpr int T3_STG_BYTES = 128 * 128;
-constexpr int T3_MAX_SA = 3, T3_MAX_SB = 8;
+constexpr int T3_MAX_SA = 3, T3_MAX_SB = 12;
 constexpr int T3_XF_WARPS = 8;
 constexpr int T3_THREADS = 64 + 256 + 32 * T3_XF_WARPS;   // 576
 constexpr int T3_XF_PASSES = (T3_HALO + 31) / 32;     // 6 passes of 32 pixel slots (8 threads x 16 B per pixel)
@@ -49,6 +49,7 @@ struct ConvTc3Args {
   const void* skp1; const void* skp2;   // raw input of the fused 1x1 skip conv (S1 | S2 channels), same dtype as src
   int S1, S2;
   const float* bias;
+  const float* res_f32;                 // X3 only: fp32 NHWC residual read straight from global memory by the epilogue
   float* ch_stats;                      // [B][Cout][2] (sum, sum^2) accumulators of the OUTPUT or nullptr
   int B, H, W, Cout;
   int tiles_x, tiles_y, tiles_m, tiles_total;
@@ -295,113 +296,146 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__
     }
   } else if (warp >= 10) {
     // ================= transform group: raw halo -> SiLU(a*x+b) -> swizzled operand tile(s) =================
+    // Software-pipelined over (tile, k-block) work items with NO extra registers: right after pass j of the current
+    // k-block has been transformed and stored, the same registers receive the global load of pass j of the NEXT k-block,
+    // so every load has a whole k-block period to land.
     using TSrc = typename std::conditional<X3, float, __nv_bfloat16>::type;
     const int tt = (int)threadIdx.x - 320;   // 0..255
     const int slot = tt >> 3, ch8 = tt & 7;  // pixel slot (32 per pass), 8-channel chunk (16 B of bf16 operand)
     const int C = p.C1 + p.C2;
-    int s = 0;
-    uint32_t ph = 0;
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
+    struct Item {
+      const TSrc* src;   // image base + channel offset of this thread's 8 channels
+      int cs;            // channels per pixel of the source tensor
+      int x0, y0;        // image coordinates of halo pixel (0, 0)
+      int b0, it;
+      bool skipk;
+    };
+    auto setup = [&](int tile, int it) -> Item {
+      Item w;
       int mt = tile % p.tiles_m;
       const int tx = mt % p.tiles_x;
       mt /= p.tiles_x;
       const int ty = mt % p.tiles_y;
-      const int b0 = mt / p.tiles_y;
-      const int x0 = tx * T3_TW - 1, y0 = ty * T3_TH - 1;   // image coordinates of halo pixel (0, 0)
-      for (int it = 0; it < total_it; ++it) {
-        const bool skipk = it >= p.kblocks;
-        const TSrc* src;
-        int cs, c0;
-        if (!skipk) {
-          const int kc = it * T3_BK;
-          if (kc < p.C1) { src = (const TSrc*)p.src1; cs = p.C1; c0 = kc; }
-          else { src = (const TSrc*)p.src2; cs = p.C2; c0 = kc - p.C1; }
-        } else {
-          const int kc = (it - p.kblocks) * T3_BK;
-          if (kc < p.S1) { src = (const TSrc*)p.skp1; cs = p.S1; c0 = kc; }
-          else { src = (const TSrc*)p.skp2; cs = p.S2; c0 = kc - p.S1; }
-        }
-        src += (long long)b0 * p.H * p.W * cs + c0 + ch8 * 8;
-        float ca[8], cb[8];
-        if (!skipk) {
-          const float* ap = p.ab + ((long long)b0 * 2) * C + it * T3_BK + ch8 * 8;
-          const float4 a0 = __ldg(reinterpret_cast<const float4*>(ap)), a1 = __ldg(reinterpret_cast<const float4*>(ap + 4));
-          const float4 q0 = __ldg(reinterpret_cast<const float4*>(ap + C)), q1 = __ldg(reinterpret_cast<const float4*>(ap + C + 4));
-          ca[0] = a0.x; ca[1] = a0.y; ca[2] = a0.z; ca[3] = a0.w; ca[4] = a1.x; ca[5] = a1.y; ca[6] = a1.z; ca[7] = a1.w;
-          cb[0] = q0.x; cb[1] = q0.y; cb[2] = q0.z; cb[3] = q0.w; cb[4] = q1.x; cb[5] = q1.y; cb[6] = q1.z; cb[7] = q1.w;
-        } else {
+      w.b0 = mt / p.tiles_y;
+      w.x0 = tx * T3_TW - 1;
+      w.y0 = ty * T3_TH - 1;
+      w.it = it;
+      w.skipk = it >= p.kblocks;
+      const TSrc* src;
+      int c0;
+      if (!w.skipk) {
+        const int kc = it * T3_BK;
+        if (kc < p.C1) { src = (const TSrc*)p.src1; w.cs = p.C1; c0 = kc; }
+        else { src = (const TSrc*)p.src2; w.cs = p.C2; c0 = kc - p.C1; }
+      } else {
+        const int kc = (it - p.kblocks) * T3_BK;
+        if (kc < p.S1) { src = (const TSrc*)p.skp1; w.cs = p.S1; c0 = kc; }
+        else { src = (const TSrc*)p.skp2; w.cs = p.S2; c0 = kc - p.S1; }
+      }
+      w.src = src + (long long)w.b0 * p.H * p.W * w.cs + c0 + ch8 * 8;
+      return w;
+    };
+    uint4 raw[T3_XF_PASSES][X3 ? 2 : 1];
+    // issue the global load of pass j of work item w into raw[j]; returns whether the pixel is a real (non-padding) one
+    auto issue = [&](const Item& w, int j) -> bool {
+      const int hp = j * 32 + slot;
+      const int hy = hp / T3_P, hx = hp - hy * T3_P;
+      const int gy = w.y0 + hy, gx = w.x0 + hx;
+      bool ok = hp < T3_HALO && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+      if (w.skipk) ok = ok && hy >= 1 && hy <= T3_TH && hx >= 1 && hx <= T3_TW;   // the 1x1 conv reads the centre window only
+      if (ok) {
+        const uint4* g = reinterpret_cast<const uint4*>(w.src + ((long long)gy * p.W + gx) * w.cs);
+        raw[j][0] = __ldg(g);
+        if (X3) raw[j][X3 ? 1 : 0] = __ldg(g + 1);
+      }
+      return ok;
+    };
+    int s = 0;
+    uint32_t ph = 0;
+    int tile = tile_begin, it = 0;
+    bool have = tile < tile_end;
+    Item cur;
+    uint32_t vmask = 0;
+    if (have) {
+      cur = setup(tile, it);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { ca[j] = 1.f; cb[j] = 0.f; }
-        }
-        const int silu = skipk ? 0 : p.silu;
-        // ---- issue every global load of this k-block first (latency overlaps the wait for the stage) ----
-        uint4 raw[T3_XF_PASSES][X3 ? 2 : 1];
-        uint32_t vmask = 0;
+      for (int j = 0; j < T3_XF_PASSES; ++j) vmask |= issue(cur, j) ? (1u << j) : 0u;
+    }
+    while (have) {
+      int ntile = tile, nit = it + 1;
+      if (nit == total_it) { nit = 0; ++ntile; }
+      const bool hn = ntile < tile_end;
+      Item nxt = cur;
+      if (hn) nxt = setup(ntile, nit);
+      float ca[8], cb[8];
+      if (!cur.skipk) {
+        const float* ap = p.ab + ((long long)cur.b0 * 2) * C + cur.it * T3_BK + ch8 * 8;
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(ap)), a1 = __ldg(reinterpret_cast<const float4*>(ap + 4));
+        const float4 q0 = __ldg(reinterpret_cast<const float4*>(ap + C)), q1 = __ldg(reinterpret_cast<const float4*>(ap + C + 4));
+        ca[0] = a0.x; ca[1] = a0.y; ca[2] = a0.z; ca[3] = a0.w; ca[4] = a1.x; ca[5] = a1.y; ca[6] = a1.z; ca[7] = a1.w;
+        cb[0] = q0.x; cb[1] = q0.y; cb[2] = q0.z; cb[3] = q0.w; cb[4] = q1.x; cb[5] = q1.y; cb[6] = q1.z; cb[7] = q1.w;
+      } else {
 #pragma unroll
-        for (int j = 0; j < T3_XF_PASSES; ++j) {
-          const int hp = j * 32 + slot;
-          const int hy = hp / T3_P, hx = hp - hy * T3_P;
-          const int gy = y0 + hy, gx = x0 + hx;
-          bool ok = hp < T3_HALO && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
-          if (skipk) ok = ok && hy >= 1 && hy <= T3_TH && hx >= 1 && hx <= T3_TW;   // the 1x1 conv reads the centre window only
-          if (ok) {
-            vmask |= 1u << j;
-            const uint4* g = reinterpret_cast<const uint4*>(src + ((long long)gy * p.W + gx) * cs);
-            raw[j][0] = __ldg(g);
-            if (X3) raw[j][1] = __ldg(g + 1);
-          }
-        }
-        mb_wait(s_u32(&bar_a_empty[s]), ph ^ 1u);
-        const uint32_t hi_base = a_base + (uint32_t)(s * A_STAGE);
+        for (int j = 0; j < 8; ++j) { ca[j] = 1.f; cb[j] = 0.f; }
+      }
+      const int silu = cur.skipk ? 0 : p.silu;
+      mb_wait(s_u32(&bar_a_empty[s]), ph ^ 1u);
+      const uint32_t hi_base = a_base + (uint32_t)(s * A_STAGE);
+      uint32_t vmask_n = 0;
 #pragma unroll
-        for (int j = 0; j < T3_XF_PASSES; ++j) {
-          const int hp = j * 32 + slot;
-          if (hp < T3_HALO) {
-            float v[8];
-            if (vmask & (1u << j)) {
-              if (X3) {
-                const float* f0 = reinterpret_cast<const float*>(&raw[j][0]);
-                const float* f1 = reinterpret_cast<const float*>(&raw[j][X3 ? 1 : 0]);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) { v[e] = f0[e]; v[4 + e] = f1[e]; }
-              } else {
-                const uint32_t* w = reinterpret_cast<const uint32_t*>(&raw[j][0]);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  v[2 * e] = __uint_as_float(w[e] << 16);
-                  v[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
-                }
-              }
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = act<X3>(fmaf(ca[e], v[e], cb[e]), silu);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = 0.f;   // conv zero padding (applied AFTER the activation, as F.conv2d pads)
-            }
-            const uint32_t dst = hi_base + swz(hp, ch8);
-            uint32_t h[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) h[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+      for (int j = 0; j < T3_XF_PASSES; ++j) {
+        const int hp = j * 32 + slot;
+        if (hp < T3_HALO) {
+          float v[8];
+          if (vmask & (1u << j)) {
             if (X3) {
-              uint32_t l[4];
+              const float* f0 = reinterpret_cast<const float*>(&raw[j][0]);
+              const float* f1 = reinterpret_cast<const float*>(&raw[j][X3 ? 1 : 0]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { v[e] = f0[e]; v[4 + e] = f1[e]; }
+            } else {
+              const uint32_t* w = reinterpret_cast<const uint32_t*>(&raw[j][0]);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float r0 = v[2 * e] - __uint_as_float(h[e] << 16);
-                const float r1 = v[2 * e + 1] - __uint_as_float(h[e] & 0xffff0000u);
-                l[e] = pack_bf16(r0, r1);
+                v[2 * e] = __uint_as_float(w[e] << 16);
+                v[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
               }
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + (uint32_t)T3_HALO_BYTES), "r"(l[0]), "r"(l[1]),
-                           "r"(l[2]), "r"(l[3])
-                           : "memory");
             }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = act<X3>(fmaf(ca[e], v[e], cb[e]), silu);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = 0.f;   // conv zero padding (applied AFTER the activation, as F.conv2d pads)
+          }
+          const uint32_t dst = hi_base + swz(hp, ch8);
+          uint32_t h[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+          if (X3) {
+            uint32_t l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float r0 = v[2 * e] - __uint_as_float(h[e] << 16);
+              const float r1 = v[2 * e + 1] - __uint_as_float(h[e] & 0xffff0000u);
+              l[e] = pack_bf16(r0, r1);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + (uint32_t)T3_HALO_BYTES), "r"(l[0]), "r"(l[1]),
+                         "r"(l[2]), "r"(l[3])
+                         : "memory");
           }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mb_arrive(s_u32(&bar_a_full[s]));
-        if (++s == SA) { s = 0; ph ^= 1u; }
+        if (hn) vmask_n |= issue(nxt, j) ? (1u << j) : 0u;   // pass j's registers are free again: prefetch the next k-block
       }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mb_arrive(s_u32(&bar_a_full[s]));
+      if (++s == SA) { s = 0; ph ^= 1u; }
+      cur = nxt;
+      vmask = vmask_n;
+      tile = ntile;
+      it = nit;
+      have = hn;
     }
   } else {
     // ================= epilogue: two groups of 128 threads; group g drains accumulator buffer g (as conv_tc2) =================
@@ -425,7 +459,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__
       const int x0 = tx * T3_TW, y0 = ty * T3_TH, n0 = nt * BN;
       const int ab = tl & 1;
       const uint32_t tmem_acc = tmem_base + (uint32_t)(ab * BN) + ((uint32_t)(q * 32) << 16);
-      if (p.has_res && elected) {              // residual chunk 0 (issued before the accumulator is needed)
+      if (!X3 && p.has_res && elected) {       // residual chunk 0 (issued before the accumulator is needed)
         mb_expect_tx(rbar, T3_STG_BYTES);
         tma_ld4(rbuf, &tmR, rbar, n0, x0, y0, b0);
       }
@@ -456,7 +490,18 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__
             }
           }
         }
-        if (p.has_res) {
+        if (X3 && p.has_res) {
+          // split mode: the fp32 residual row of this pixel (32 channels = one 128-B line) comes straight from global memory
+          // -- no shared-memory staging, which leaves room for a deeper weight pipeline
+          const float4* rp = reinterpret_cast<const float4*>(
+              p.res_f32 + (((long long)b0 * p.H + y0 + (r >> 3)) * p.W + x0 + (r & 7)) * p.Cout + n0 + c * CW);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 rv = __ldg(rp + j);
+            val[4 * j + 0] += rv.x; val[4 * j + 1] += rv.y; val[4 * j + 2] += rv.z; val[4 * j + 3] += rv.w;
+          }
+        }
+        if (!X3 && p.has_res) {
           mb_wait(rbar, (uint32_t)(rc & 1));
           if (p.out_bf16) {
 #pragma unroll
@@ -483,7 +528,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__
         }
         if (elected) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous TMA store has read the staging buffer
         epi_bar(eg);
-        if (p.has_res && elected && c + 1 < nch) {
+        if (!X3 && p.has_res && elected && c + 1 < nch) {
           mb_expect_tx(rbar, T3_STG_BYTES);
           tma_ld4(rbuf, &tmR, rbar, n0 + (c + 1) * CW, x0, y0, b0);
         }
@@ -621,6 +666,8 @@ extern "C" int pdae_conv_tc3_create(pdae_conv_tc3_plan** plan_out, const void* s
   PDAE_REQUIRE(plan_out && src1 && ab && w && out, "conv_tc3_create: null pointer");
   PDAE_REQUIRE(src_dtype == PDAE_BF16 || src_dtype == PDAE_F32, "conv_tc3_create: bad source dtype");
   PDAE_REQUIRE(out_dtype == PDAE_BF16 || out_dtype == PDAE_F32, "conv_tc3_create: bad out dtype");
+  PDAE_REQUIRE(!(src_dtype == PDAE_F32 && residual && out_dtype != PDAE_F32),
+               "conv_tc3_create: the split mode reads an fp32 residual (output must be fp32 too)");
   const bool x3 = src_dtype == PDAE_F32;
   const int Cin = C1 + C2, Cs = S1 + S2;
   PDAE_REQUIRE(C1 > 0 && C1 % T3_BK == 0 && C2 % T3_BK == 0 && (C2 == 0 || src2), "conv_tc3_create: bad C1=%d C2=%d", C1, C2);
@@ -642,7 +689,7 @@ extern "C" int pdae_conv_tc3_create(pdae_conv_tc3_plan** plan_out, const void* s
   ConvTc3Args& a = pl->args;
   a.src1 = src1; a.src2 = src2; a.C1 = C1; a.C2 = C2; a.ab = ab;
   a.skp1 = skp1; a.skp2 = skp2; a.S1 = S1; a.S2 = S2;
-  a.bias = bias; a.ch_stats = ch_stats;
+  a.bias = bias; a.ch_stats = ch_stats; a.res_f32 = x3 ? (const float*)residual : nullptr;
   a.B = B; a.H = H; a.W = W; a.Cout = Cout;
   a.tiles_x = W / T3_TW; a.tiles_y = H / T3_TH; a.tiles_m = a.tiles_x * a.tiles_y * B;
   a.kblocks = Cin / T3_BK; a.kblocks2 = Cs / T3_BK;
@@ -657,12 +704,14 @@ extern "C" int pdae_conv_tc3_create(pdae_conv_tc3_plan** plan_out, const void* s
   a.tiles_total = a.tiles_m * (Cout / BN);
   pl->grid = a.tiles_total < g_num_sms3 ? a.tiles_total : g_num_sms3;
   const int a_stage = (x3 ? 2 : 1) * T3_HALO_BYTES, b_bytes = BN * T3_BK * 2;
-  const int staging = (a.has_res ? 4 : 2) * T3_STG_BYTES;
+  const int staging = ((a.has_res && !x3) ? 4 : 2) * T3_STG_BYTES;   // split mode reads its residual from global memory
   const int budget = 220 * 1024 - 1024 - staging;
+  // the transform is software-pipelined, so two halo stages suffice; the weight tiles need depth (bytes in flight from L2)
   int sa = 2;
   int sb = (budget - sa * a_stage) / b_bytes;
   if (sb > T3_MAX_SB) sb = T3_MAX_SB;
-  if (sb >= 6 && budget - 3 * a_stage - 4 * b_bytes >= 0) { sa = 3; sb = (budget - sa * a_stage) / b_bytes; if (sb > T3_MAX_SB) sb = T3_MAX_SB; }
+  if (budget - sa * a_stage - sb * b_bytes >= a_stage) sa = 3;
+  { const char* e = getenv("PDAE_TC3_SB"); if (e && atoi(e) >= 2 && atoi(e) <= sb) sb = atoi(e); }   // tuning aid
   if (sb < 2) {
     delete pl;
     PDAE_REQUIRE(false, "conv_tc3_create: shared-memory budget too small (BN=%d x3=%d)", BN, (int)x3);

@@ -33,7 +33,11 @@ for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
     print(f"  {k:18s} {v['ms']:8.3f} ms  {100 * v['ms'] / tot:5.1f}%  n={v['launches']:4d}  {tf:8.1f} TFLOP/s")
 rows = []
 for i, (fn, args) in enumerate(plan.ops):
-    if fn.startswith("conv_tc"):
+    if fn == "conv_tc3":
+        (s1, C1, s2, C2, sdt, ab, silu, w, bias, k1, S1, k2, S2, wsk, resid, out, odt, stats, Bb, H, W, Cout, bn) = args
+        rows.append((plan.last_op_ms[i], f"conv_tc3 {H}x{W} {C1}+{C2}->{Cout} skip={S1 + S2} res={int(resid is not None)} obf16={odt}",
+                     plan.flops[i]))
+    elif fn.startswith("conv_tc"):
         ints = [a for a in args if isinstance(a, int)]
         if fn == "conv_tc2_skip":
             odt, Bb, H, W, Cin, Cout, k, bn = ints[-8:]
