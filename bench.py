@@ -25,6 +25,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"      # NCCL prints its version banner on STDOUT: keep stdout to the one JSON line
 
 import torch  # noqa: E402
 

@@ -173,36 +173,52 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
   lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
-// Q3 / K3: [B*heads][T][3*ch] ; one thread per (z, t, c)
+// Q3 / K3: [B*heads][T][3*ch] ; one thread per (z, t, 8 channels): 2 x 32 B loads, 6 x 16 B stores
+__device__ __forceinline__ void split8(const float* src, uint4& hi, uint4& lo) {
+  const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+    const float2 hf = __bfloat1622float2(hh);
+    __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+    h[e] = *reinterpret_cast<uint32_t*>(&hh);
+    l[e] = *reinterpret_cast<uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
 __global__ void __launch_bounds__(256) qk_split3_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ Q3,
                                                         __nv_bfloat16* __restrict__ K3, int T, int C3, int ch, int heads,
                                                         long long koff, long long hs, long long total) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over (z, t, ch / 8)
   if (i >= total) return;
-  const int c = (int)(i % ch);
-  const long long zt = i / ch;
+  const int c8 = ch >> 3;
+  const int c = (int)(i % c8) * 8;
+  const long long zt = i / c8;
   const int t = (int)(zt % T);
   const int z = (int)(zt / T), b = z / heads, h = z % heads;
   const float* row = qkv + ((long long)b * T + t) * C3 + h * hs;
-  __nv_bfloat16 qh, ql, kh, kl;
-  split_bf16(row[c], qh, ql);
-  split_bf16(row[koff + c], kh, kl);
-  __nv_bfloat16* q = Q3 + zt * 3 * ch;
-  __nv_bfloat16* k = K3 + zt * 3 * ch;
-  q[c] = qh; q[ch + c] = ql; q[2 * ch + c] = qh;
-  k[c] = kh; k[ch + c] = kh; k[2 * ch + c] = kl;
+  uint4 qh, ql, kh, kl;
+  split8(row + c, qh, ql);
+  split8(row + koff + c, kh, kl);
+  __nv_bfloat16* q = Q3 + zt * 3 * ch + c;
+  __nv_bfloat16* k = K3 + zt * 3 * ch + c;
+  *reinterpret_cast<uint4*>(q) = qh; *reinterpret_cast<uint4*>(q + ch) = ql; *reinterpret_cast<uint4*>(q + 2 * ch) = qh;
+  *reinterpret_cast<uint4*>(k) = kh; *reinterpret_cast<uint4*>(k + ch) = kh; *reinterpret_cast<uint4*>(k + 2 * ch) = kl;
 }
 
 // VT3: [B*heads][ch][3*T] = [vT_hi | vT_hi | vT_lo]  (32 x 32 shared-memory transpose)
 __global__ void __launch_bounds__(256) v_split3_transpose_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ VT3,
                                                                  int T, int C3, int ch, int heads, long long voff, long long hs) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[64][33];   // [t][c]
   const int z = blockIdx.z, b = z / heads, h = z % heads;
-  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int t0 = blockIdx.x * 64, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
   const float* src = qkv + (long long)b * T * C3 + voff + h * hs;
 #pragma unroll
-  for (int i = ty; i < 32; i += 8) {
+  for (int i = ty; i < 64; i += 8) {
     const int t = t0 + i, c = c0 + tx;
     tile[i][tx] = (t < T && c < ch) ? src[(long long)t * C3 + c] : 0.f;
   }
@@ -210,12 +226,16 @@ __global__ void __launch_bounds__(256) v_split3_transpose_kernel(const float* __
   __nv_bfloat16* dst = VT3 + (long long)z * ch * 3 * T;
 #pragma unroll
   for (int i = ty; i < 32; i += 8) {
-    const int c = c0 + i, t = t0 + tx;
+    const int c = c0 + i, t = t0 + 2 * tx;     // two consecutive tokens per thread: 4-byte stores, 128 B per warp
     if (c < ch && t < T) {
-      __nv_bfloat16 hi, lo;
-      split_bf16(tile[tx][i], hi, lo);
-      __nv_bfloat16* r = dst + (long long)c * 3 * T;
-      r[t] = hi; r[T + t] = hi; r[2 * T + t] = lo;
+      const float v0 = tile[2 * tx][i], v1 = tile[2 * tx + 1][i];
+      __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
+      const float2 hf = __bfloat1622float2(hh);
+      __nv_bfloat162 ll = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
+      __nv_bfloat16* r = dst + (long long)c * 3 * T + t;
+      *reinterpret_cast<__nv_bfloat162*>(r) = hh;
+      *reinterpret_cast<__nv_bfloat162*>(r + T) = hh;
+      *reinterpret_cast<__nv_bfloat162*>(r + 2 * T) = ll;
     }
   }
 }
@@ -263,11 +283,13 @@ extern "C" int pdae_qkv_split3(const float* qkv, void* Q3, void* K3, void* VT3, 
   const int ch = C / heads;
   const long long hs = legacy ? 3LL * ch : ch, ko = legacy ? ch : C, vo = legacy ? 2LL * ch : 2LL * C;
   PDAE_REQUIRE((long long)B * heads <= 65535, "qkv_split3: B*heads too large");
-  const long long total = (long long)B * heads * T * ch;
+  PDAE_REQUIRE(ch % 8 == 0 && C % 4 == 0, "qkv_split3: C/heads=%d must be a multiple of 8", ch);
+  const long long total = (long long)B * heads * T * (ch / 8);
   cudaStream_t s = (cudaStream_t)stream;
   qk_split3_kernel<<<cdiv(total, 256), 256, 0, s>>>(qkv, (__nv_bfloat16*)Q3, (__nv_bfloat16*)K3, T, 3 * C, ch, heads, ko, hs, total);
   PDAE_LAUNCH_CHECK("qk_split3_kernel");
-  dim3 grid(cdiv(T, 32), cdiv(ch, 32), B * heads);
+  PDAE_REQUIRE(T % 2 == 0, "qkv_split3: T must be even");
+  dim3 grid(cdiv(T, 64), cdiv(ch, 32), B * heads);
   v_split3_transpose_kernel<<<grid, 256, 0, s>>>(qkv, (__nv_bfloat16*)VT3, T, 3 * C, ch, heads, vo, hs);
   PDAE_LAUNCH_CHECK("v_split3_transpose_kernel");
   return PDAE_OK;

@@ -778,6 +778,13 @@ extern "C" int pdae_conv_tc3_create(pdae_conv_tc3_plan** plan_out, const void* s
   int sb = (budget - sa * a_stage) / b_bytes;
   if (sb > T3_MAX_SB) sb = T3_MAX_SB;
   if (budget - sa * a_stage - sb * b_bytes >= a_stage) sa = 3;
+  if (!x3 && a.kblocks2 > 0) {
+    // fused 1x1 skip conv in the fast mode: its k-blocks carry one tap (4 MMAs) per 23 KB raw box, so their cost is the TMA
+    // latency / number of stages in flight -- trade weight-pipeline depth for a fourth halo stage
+    int sbw = (budget - 4 * a_stage) / b_bytes;
+    if (sbw > T3_MAX_SB) sbw = T3_MAX_SB;
+    if (sbw >= 4) { sa = 4; sb = sbw; }
+  }
   {   // tuning aids: force the halo / weight pipeline depths (if they fit)
     const char* ea = getenv("PDAE_TC3_SA");
     const char* eb = getenv("PDAE_TC3_SB");

@@ -39,6 +39,21 @@ def _worker(rank, world, port, n_total, q):
     scale = allreduce_grads_(ps, bucket_bytes=4096)          # last param has no grad; several buckets
     ok = ok and scale == 1.0 / world and ps[-1].grad is None
     ok = ok and all(torch.equal(p.grad, torch.full_like(p, 3.0 * (i + 1))) for i, p in enumerate(ps[:-1]))
+    # overlapped variant: buckets launch from post-accumulate-grad hooks in gradient-ready order, finish() writes the sums back
+    from pdae_b200.utils.dist import OverlappedGradAllReduce
+    a = [torch.nn.Parameter(torch.ones(n)) for n in (7, 30000)]
+    bq = [torch.nn.Parameter(torch.ones(n)) for n in (5, 11)]
+    red = OverlappedGradAllReduce([a, bq], bucket_bytes=64 << 10)
+    for it in range(2):   # two steps: the per-step state resets
+        loss = sum((p * float(rank + 1 + it)).sum() for p in a + bq)
+        loss.backward()
+        sc = red.finish()
+        ok = ok and sc == 1.0 / world
+        want = float(sum(r + 1 + it for r in range(world)))
+        ok = ok and all(torch.equal(p.grad, torch.full_like(p, want)) for p in a + bq)
+        for p in a + bq:
+            p.grad = None
+    red.remove()
     q.put((rank, ok, (s, e)))
     dist.destroy_process_group()
 
