@@ -379,7 +379,8 @@ def main():
 
     # kernel-level view of ONE decoder step (CUDA events around every launch of the step plan)
     plan, _ = dec.plan_for(B, size, size)
-    launches_per_step = plan.n_launch + 2  # + timestep select + fused DDIM update (both inside the step graph)
+    # + timestep select (+ the DDIM update kernel unless it is fused into the last head conv's epilogue), all inside the step graph
+    launches_per_step = plan.n_launch + (1 if plan.head_fuse else 2)
     enc_plan = [v for k, v in enc._plans().items() if k[1] == chosen][0][0]
     gpu_launches = args.steps * (2 * S * launches_per_step + enc_plan.n_launch)
     peak_tf, peak_bw, peak_src = peaks()

@@ -246,6 +246,10 @@ int pdae_gemm_tc2_softmax_create(pdae_conv_tc2_plan** plan, const void* a_bf16, 
                                  const void* b_bf16, long long b_ld, long long b_bs, void* out_bf16, long long out_ld,
                                  long long out_bs, int batch, int M, int N, int K, float alpha);
 int pdae_conv_tc2_run(const pdae_conv_tc2_plan* plan, pdae_stream_t stream);
+/* Image-head plans (cout_valid > 0): fuse the per-step DDIM update (diffusion/ddim.py:43-55,66-79,91-107,123-138) into the head's
+ * epilogue.  fuse_desc_device: 8 x int64 in DEVICE memory, read at run time = { flags, eps*, x_t*, t*, tab_A*, tab_Bm*, tab_s1m*,
+ * tab_ab* }, flags = enabled | use_grad<<1 | eps_only<<2 | C<<8 | C_eps<<16; flags == 0 -> plain head.  Arithmetic identical to pdae_ddim_step. */
+int pdae_conv_tc2_set_head_fuse(pdae_conv_tc2_plan* plan, const int64_t* fuse_desc_device);
 /* P = softmax(alpha * S) per row, fp32 in -> bf16 out.  vT[b*heads+h][c][t] = V part of qkv (bf16 [B][T][3C]).        */
 int pdae_softmax_bf16(const float* S, void* P_bf16, int64_t rows, int cols, float alpha, pdae_stream_t stream);
 int pdae_transpose_v(const void* qkv_bf16, void* vT_bf16, int B, int T, int C, int heads, int legacy, pdae_stream_t stream);

@@ -101,6 +101,7 @@ _SIGS = {
     "pdae_gemm_tc2_softmax_create": (c_int, [POINTER(c_void_p), _P, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int64, c_int64,
                                              c_int, c_int, c_int, c_int, c_float]),
     "pdae_conv_tc2_run": (c_int, [_P, _P]),
+    "pdae_conv_tc2_set_head_fuse": (c_int, [_P, _P]),
     "pdae_conv_tc3_supported": (c_int, [c_int, c_int, c_int, c_int]),
     "pdae_conv_tc3_create": (c_int, [POINTER(c_void_p), _P, c_int, _P, c_int, c_int, _P, c_int, _P, _P, _P, c_int, _P, c_int, _P, _P,
                                      _P, c_int, _P, c_int, c_int, c_int, c_int, c_int]),

@@ -30,6 +30,7 @@ struct ConvTc2Args {
   const float* bias;
   float* ch_stats;    // [B][Cout][2] fp32 partial (sum, sum^2) accumulators or nullptr
   float* out_nchw;    // BN==16 head: NCHW fp32 output
+  const long long* fuse;  // BN==16 head: optional device-side descriptor of the fused DDIM update (see pdae_conv_tc2_set_head_fuse)
   int B, H, W, Cout;
   int tw, th, tn;
   int tiles_x, tiles_y, tiles_b, tiles_m, tiles_total;
@@ -343,10 +344,44 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int b = b0 + ni;
         if (b < p.B) {
           const long long hw = (long long)p.H * p.W;
-          float* o = p.out_nchw + (long long)b * p.cout_valid * hw + (long long)(y0 + yy) * p.W + (x0 + xx);
+          const long long pix = (long long)(y0 + yy) * p.W + (x0 + xx);
+          float* o = p.out_nchw + (long long)b * p.cout_valid * hw + pix;
+          float val[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < p.cout_valid) o[j * hw] = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + j) : 0.f);
+          for (int j = 0; j < 16; ++j) {
+            val[j] = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + j) : 0.f);
+            if (j < p.cout_valid) o[j * hw] = val[j];
+          }
+          // ---- fused DDIM update (diffusion/ddim.py:43-55, 66-79, 91-107, 123-138): this head's output is the last tensor the
+          // step needs, so x_t -> x_{t-1} (or x_{t+1}) is finished here, in place, with the exact arithmetic of ddim_step_kernel.
+          // The descriptor lives in device memory and is (re)written by the sampling loop; flags == 0 -> plain head conv.
+          if (p.fuse) {
+            const long long flags = __ldg(p.fuse);
+            if (flags & 1) {
+              const int C = (int)((flags >> 8) & 0xff), Ce = (int)((flags >> 16) & 0xff);
+              const float* eps = reinterpret_cast<const float*>(__ldg(p.fuse + 1));
+              float* xt = reinterpret_cast<float*>(__ldg(p.fuse + 2));
+              const long long tb = reinterpret_cast<const long long*>(__ldg(p.fuse + 3))[b];
+              const float A = reinterpret_cast<const float*>(__ldg(p.fuse + 4))[tb];
+              const float Bm = reinterpret_cast<const float*>(__ldg(p.fuse + 5))[tb];
+              const float abar = reinterpret_cast<const float*>(__ldg(p.fuse + 7))[tb];
+              const float s1m = (flags & 2) ? reinterpret_cast<const float*>(__ldg(p.fuse + 6))[tb] : 0.f;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (j < C) {
+                  const long long xi = ((long long)b * C + j) * hw + pix;
+                  float e = val[j];                                  // this head predicts epsilon itself
+                  if (flags & 2) e = __fsub_rn(eps[((long long)b * Ce + j) * hw + pix], __fmul_rn(s1m, val[j]));   // own output = shift term
+                  else if (flags & 4) e = eps[((long long)b * Ce + j) * hw + pix];   // shift unused this step: epsilon from the other head
+                  const float ax = __fmul_rn(A, xt[xi]);
+                  float x0 = __fsub_rn(ax, __fmul_rn(Bm, e));
+                  x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+                  const float e2 = __fdiv_rn(__fsub_rn(ax, x0), Bm);
+                  xt[xi] = __fadd_rn(__fmul_rn(x0, sqrtf(abar)), __fmul_rn(sqrtf(__fsub_rn(1.0f, abar)), e2));
+                }
+              }
+            }
+          }
         }
       } else {
         const int CW = p.out_bf16 ? 64 : 32;  // accumulator columns per staging tile (128-byte rows)
@@ -664,6 +699,7 @@ static int tc2_create(pdae_conv_tc2_plan** plan_out, const Tc2Desc& d) {
   pdae_conv_tc2_plan* pl = new pdae_conv_tc2_plan();
   ConvTc2Args& a = pl->args;
   a.bias = d.bias; a.ch_stats = d.ch_stats; a.out_nchw = head ? (float*)d.out : nullptr;
+  a.fuse = nullptr;
   a.B = B; a.H = H; a.W = W; a.Cout = Cout;
   a.tw = pow2_tile(W, T2_BM);
   a.th = pow2_tile(H, T2_BM / a.tw);
@@ -901,6 +937,16 @@ extern "C" int pdae_conv_tc2_run(const pdae_conv_tc2_plan* pl, pdae_stream_t str
     set_error("launch of conv_tc2_kernel<%d> failed: %s", pl->BN, cudaGetErrorString(e));
     return PDAE_ECUDA;
   }
+  return PDAE_OK;
+}
+
+// Image-head plans only: attach the device-side descriptor of the fused DDIM update, 8 x int64 =
+// { flags, eps*, x_t*, t*, sqrt_recip_alphas_cumprod*, sqrt_recip_alphas_cumprod_m1*, sqrt_one_minus_alphas_cumprod*, alphas_cumprod_prev|next* }
+// with flags = enabled | use_grad << 1 | eps_only << 2 | C << 8 | C_eps << 16.  The head keeps writing its own output; when enabled it also
+// updates x_t in place (use_grad: this head produces the shift/gradient term and `eps` comes from the other head).
+extern "C" int pdae_conv_tc2_set_head_fuse(pdae_conv_tc2_plan* pl, const int64_t* fuse_desc_device) {
+  PDAE_REQUIRE(pl && pl->BN == 16, "conv_tc2_set_head_fuse: not an image-head plan");
+  pl->args.fuse = reinterpret_cast<const long long*>(fuse_desc_device);
   return PDAE_OK;
 }
 

@@ -50,7 +50,10 @@ class _StepRunner:
         B = x_in.tensor.shape[0]
         self.B = B
         self.delta = -1 if direction == "sample" else 1
-        self.in_graph_update = eps.tensor.shape[1] == C      # learn_sigma heads: the update runs after the replay
+        # the update runs inside the step graph (separate kernel, or fused into the last head conv's epilogue); only a learn_sigma
+        # head on the CUDA-core path (2C output channels, no fusable epilogue) needs it after the replay
+        self.in_graph_update = eps.tensor.shape[1] == C or bool(getattr(plan, "head_fuse", None))
+        self.fused = False
         self.C = C
         cache = plan.__dict__.setdefault("_step_cache", {})
         key = (id(ddim), direction, grad is not None)
@@ -62,6 +65,15 @@ class _StepRunner:
             cache[key] = ent
         self.ent = ent
 
+    def _fuse_target(self):
+        """The image head that ends the step plan and can run the update in its epilogue (tensor-core heads only)."""
+        hf = getattr(self.plan, "head_fuse", None) or {}
+        if "grad" in hf:
+            return hf["grad"], True
+        if "eps" in hf:
+            return hf["eps"], False
+        return None, False
+
     def _launch_step(self):
         d, L = self.d, _native.lib()
         st = _stream(d.device)
@@ -69,29 +81,51 @@ class _StepRunner:
                                   _ptr(self.ent["t_loc"]), _ptr(self.t_in.tensor), self.B, st)
         _native.check(rc, "pdae_ddim_select_t")
         self.plan._launch_all()
-        if self.in_graph_update:
+        if self.in_graph_update and not self.fused:
             x = self.x_in.tensor
             d._update(x, self.ent["t_loc"], self.eps.tensor, self.grad.tensor if self.grad is not None else None,
                       self.direction, out=x)
 
     def begin(self, use_graph: bool):
         self.plan.run_prologue()          # forced weight re-pack + step-invariant ops (label_emb(z), emb_z_layers)
-        if use_graph and self.ent["graph"] is None:
+        # DDIM update fused into the last head conv's epilogue: point its device-side descriptor at this loop's tables
+        fuse, is_grad_head = self._fuse_target()
+        self.fused = fuse is not None and self.in_graph_update
+        self.fuse_buf = fuse if self.fused else None
+        if self.fused:
+            d = self.d
+            tab = d.alphas_cumprod_prev if self.direction == "sample" else d.alphas_cumprod_next
+            Ce = int(self.eps.tensor.shape[1])
+            flags = 1 | (self.C << 8) | (Ce << 16)
+            if is_grad_head:
+                flags |= 2 if self.grad is not None else 4
+            desc = [flags, self.eps.tensor.data_ptr(), self.x_in.tensor.data_ptr(), self.ent["t_loc"].data_ptr(),
+                    d.sqrt_recip_alphas_cumprod.data_ptr(), d.sqrt_recip_alphas_cumprod_m1.data_ptr(),
+                    d.sqrt_one_minus_alphas_cumprod.data_ptr(), tab.data_ptr()]
+            fuse.tensor.copy_(torch.tensor(desc, dtype=torch.int64))
+        gkey = "graph_fused" if self.fused else "graph"
+        if use_graph and self.ent.get(gkey) is None:
             self.seek(1 if self.direction == "sample" else 0)
             self._launch_step()           # warm-up outside capture (lazy module loading, cudaFuncSetAttribute, ...)
             torch.cuda.synchronize(self.d.device)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._launch_step()
-            self.ent["graph"] = g
+            self.ent[gkey] = g
+        self.graph = self.ent.get(gkey)
         self.use_graph = use_graph
+
+    def end(self):
+        """Switch the fused update off again: the plan is shared with plain forward calls."""
+        if getattr(self, "fuse_buf", None) is not None:
+            self.fuse_buf.tensor.zero_()
 
     def seek(self, i: int):
         self.ent["counter"].fill_(int(i))
 
     def step(self):
         if self.use_graph:
-            self.ent["graph"].replay()
+            self.graph.replay()
         else:
             self._launch_step()
         if not self.in_graph_update:
@@ -199,18 +233,23 @@ class DDIM:
         main.begin(self.use_cuda_graph)   # re-packs weights (forced: `.data` / raw-pointer updates bump no version), prologue
         if tail is not None:
             tail.begin(self.use_cuda_graph)
-        x_in.tensor.copy_(x)
-        cur = main
-        steps = list(self._steps(direction))
-        cur.seek(steps[0])
-        for i in steps:
-            use_shift = shift and (direction == "encode" or (i - 1) >= stop_step)
-            if tail is not None and not use_shift and cur is not tail:
-                tail.x_in.tensor.copy_(cur.x_in.tensor)
-                cur = tail
-                cur.seek(i)
-            cur.step()
-        return cur.x_in.tensor.clone()
+        try:
+            x_in.tensor.copy_(x)
+            cur = main
+            steps = list(self._steps(direction))
+            cur.seek(steps[0])
+            for i in steps:
+                use_shift = shift and (direction == "encode" or (i - 1) >= stop_step)
+                if tail is not None and not use_shift and cur is not tail:
+                    tail.x_in.tensor.copy_(cur.x_in.tensor)
+                    cur = tail
+                    cur.seek(i)
+                cur.step()
+            return cur.x_in.tensor.clone()
+        finally:
+            main.end()
+            if tail is not None:
+                tail.end()
 
     def ddim_sample_loop(self, denoise_fn, x_T, condition=None):
         return self._loop(denoise_fn, x_T, condition, "sample", shift=False)

@@ -152,6 +152,7 @@ class Plan:
         self._tc_handles: List[ctypes.c_void_p] = []
         self._tc2_handles: List[ctypes.c_void_p] = []
         self._tc3_handles: List[ctypes.c_void_p] = []
+        self.head_fuse: Dict[str, Buf] = {}   # image heads whose epilogue can run the DDIM update (set by a sampling loop)
         self.n_launch = 0
         self.keep_all = False
         self.dropout_masks: list = []   # (block, mask buffer, p): filled by the trainer before every training forward
@@ -342,13 +343,16 @@ class Plan:
         return (self.L.pdae_conv_tc_run, [h, None], 1, "conv_tc")
 
     def _compile_tc2(self, args):
-        x, w, bias, resid, out, odt, stats, B, H, W, Cin, Cout, k, cout_valid, bn = args
+        fuse = args[15] if len(args) > 15 else None
+        x, w, bias, resid, out, odt, stats, B, H, W, Cin, Cout, k, cout_valid, bn = args[:15]
         h = ctypes.c_void_p()
         rc = self.L.pdae_conv_tc2_create(ctypes.byref(h), self._resolve(x), self._resolve(w), self._resolve(bias),
                                          self._resolve(resid), self._resolve(out), odt, self._resolve(stats), B, H, W, Cin,
                                          Cout, k, cout_valid, bn)
         _native.check(rc, "pdae_conv_tc2_create")
         self._tc2_handles.append(h)
+        if fuse is not None:
+            _native.check(self.L.pdae_conv_tc2_set_head_fuse(h, self._resolve(fuse)), "pdae_conv_tc2_set_head_fuse")
         return (self.L.pdae_conv_tc2_run, [h, None], 1, "conv_tc2")
 
     def _compile_tc2_skip(self, args):
@@ -655,8 +659,11 @@ class Plan:
         self.call("conv2d_simt", x, PDAE_F32, 0, wp, bias, None, out, 0, B, 1, 1, Cin, Cout, 1, 1, 0, int(a_silu), _STREAM,
                   flops=2.0 * B * Cin * Cout)
 
-    def head_conv(self, x: Buf, weight: torch.Tensor, bias: torch.Tensor, out_nchw: Buf, *, B, H, W, Cin, Cout) -> None:
-        """3x3 conv to a few image channels (unet.py:171-175)."""
+    def head_conv(self, x: Buf, weight: torch.Tensor, bias: torch.Tensor, out_nchw: Buf, *, B, H, W, Cin, Cout,
+                  fuse_key: Optional[str] = None) -> None:
+        """3x3 conv to a few image channels (unet.py:171-175).  fuse_key ("eps" | "grad"): on the tensor-core head, reserve a
+        device-side descriptor through which a sampling loop can switch on the DDIM update fused into this head's epilogue
+        (Plan.head_fuse[fuse_key]; all-zero = plain head)."""
         fl = 2.0 * B * H * W * Cout * Cin * 9
         if self.v2 and x.dtype == torch.bfloat16 and Cout <= 16 and self.use_tc(Cin, 64, 3, 1, H, W):
             # tensor-core head: Cout zero-padded to one 16-wide UMMA tile, NCHW fp32 planes written by the epilogue
@@ -670,7 +677,12 @@ class Plan:
                 z[:, :Cout, :] = w
                 return z
             wp = self.pack((id(weight), "tc16_x3" if x3 else "tc16"), [weight], pack16)
-            self.call("conv_tc2", x, wp, self.param(bias), None, out_nchw, PDAE_F32, None, B, H, W, Ce, 16, 3, Cout, 0, flops=fl)
+            fuse = None
+            if fuse_key is not None and os.environ.get("PDAE_HEAD_FUSE", "1") == "1":
+                with torch.inference_mode(False):
+                    fuse = self.fixed(torch.zeros(8, dtype=torch.int64, device=self.device))
+                self.head_fuse[fuse_key] = fuse
+            self.call("conv_tc2", x, wp, self.param(bias), None, out_nchw, PDAE_F32, None, B, H, W, Ce, 16, 3, Cout, 0, fuse, flops=fl)
         elif Cout <= 4 and Cin % 4 == 0:
             assert x.dtype in (torch.float32, torch.bfloat16)
 

@@ -100,12 +100,12 @@ class ShiftUNet(PlannedModule):
                 shift_h = shift_stage.emit(P, shift_h.cat(skip), bank_t, bank_z)
         eps = P.new((B, self.output_channel, H, W), torch.float32, "eps_nchw")
         eps.keep = True
-        emit_head(P, self.out, eps_h, eps)
+        emit_head(P, self.out, eps_h, eps, fuse_key=None if with_shift else "eps")
         grad = None
         if with_shift:
             grad = P.new((B, self.input_channel, H, W), torch.float32, "shift_nchw")
             grad.keep = True
-            emit_head(P, self.shift_out, shift_h, grad)
+            emit_head(P, self.shift_out, shift_h, grad, fuse_key="grad")   # the step's LAST op: may carry the fused DDIM update
         return x_in, t_in, z_in, eps, grad
 
     def plan_for(self, B: int, H: int, W: int, with_shift: bool = True):

@@ -130,14 +130,15 @@ def emit_stem(P: Plan, stem: nn.Module, x_in: Buf, B: int, H: int, W: int, Cin: 
     return Src(P.to_stream(h0, c0, B=B, H=H, W=W), c0, B, H, W, s1=st0)
 
 
-def emit_head(P: Plan, head: Slots, x: Src, out: Buf, tape=None) -> None:
+def emit_head(P: Plan, head: Slots, x: Src, out: Buf, tape=None, fuse_key=None) -> None:
     gn, conv = head[0], head[2]
     B, H, W, C = x.B, x.H, x.W, x.C
     ab = P.gn_coef(x.b1, C, None, 0, gn.weight, gn.bias, B=B, HW=H * W, stats1=x.s1)
     sums = P.last_sums
     act, _ = P.gn_apply(x.b1, C, None, 0, ab, silu=True, resample=0, B=B, H=H, W=W,
                         act_dtype=P.head_act_dtype(C, conv.weight.shape[0], H, W))
-    P.head_conv(act, conv.weight, conv.bias, out, B=B, H=H, W=W, Cin=C, Cout=conv.weight.shape[0])
+    P.head_conv(act, conv.weight, conv.bias, out, B=B, H=H, W=W, Cin=C, Cout=conv.weight.shape[0],
+                fuse_key=fuse_key if tape is None else None)
     if tape is not None:
         tape.append(("head", head, dict(x=x, ab=ab, sums=sums, act=act)))
 
@@ -198,7 +199,7 @@ class UNet(PlannedModule):
             h = stage.emit(P, h.cat(hs.pop()), bank)
         out = P.new((B, self.output_channel, H, W), torch.float32, "eps_nchw")
         out.keep = True
-        emit_head(P, self.out, h, out)
+        emit_head(P, self.out, h, out, fuse_key="eps")
         return x_in, t_in, c_in, out
 
     def forward(self, x, time, condition=None):

@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_conv_tc3.py tests/test_gpu_parity.py -q -x -p no:cacheprovider 2>&1 | tail -3
-for m in bf16 bf16x3; do timeout 300 python scripts/profile_ops.py celeba64 256 70 $m > gpurun_out/r02_ops_$m.txt 2>&1; head -12 gpurun_out/r02_ops_$m.txt; done
-timeout 600 python scripts/train_bench.py --batch 32 --steps 5 2>&1 | tail -2 | tee gpurun_out/r02_train_n1.json
+timeout 900 python -m pytest tests -m gpu -q --maxfail=20 -p no:cacheprovider > gpurun_out/r02_pytest4.log 2>&1; tail -6 gpurun_out/r02_pytest4.log
+timeout 600 python bench.py --steps 2 --warmup 3 > gpurun_out/r02_bench3.json 2> gpurun_out/r02_bench3.err; tail -c 300 gpurun_out/r02_bench3.err; head -c 300 gpurun_out/r02_bench3.json

@@ -89,6 +89,13 @@ def test_loops(precision):
         fast = d.representation_learning_ddim_sample("ddim10", None, m, None, xT, z)
         if precision == "fp32":  # (bf16 on random weights is chaotic over 10 steps; see `check`)
             assert_close(slow, fast, rtol=1e-3, atol=2e-4, what="generic vs fast loop")
+        if precision == "bf16x3":
+            # tensor-core modes: the fast loop runs the DDIM update INSIDE the shift head's epilogue (one graph per step, no
+            # separate update kernel); the generic loop calls pdae_ddim_step -- same arithmetic, so they agree at fp32 grade
+            plan, _ = m.plan_for(2, 16, 16)
+            assert "grad" in plan.head_fuse, "fused DDIM head epilogue not available on the tensor-core head"
+            assert int(plan.head_fuse["grad"].tensor[0]) == 0, "fusion descriptor must be switched off after the loop"
+            assert_close(slow, fast, rtol=1e-3, atol=2e-3, what="generic vs fused-epilogue loop")
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16x3"])
