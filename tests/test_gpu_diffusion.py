@@ -89,13 +89,38 @@ def test_loops(precision):
         fast = d.representation_learning_ddim_sample("ddim10", None, m, None, xT, z)
         if precision == "fp32":  # (bf16 on random weights is chaotic over 10 steps; see `check`)
             assert_close(slow, fast, rtol=1e-3, atol=2e-4, what="generic vs fast loop")
-        if precision == "bf16x3":
-            # tensor-core modes: the fast loop runs the DDIM update INSIDE the shift head's epilogue (one graph per step, no
-            # separate update kernel); the generic loop calls pdae_ddim_step -- same arithmetic, so they agree at fp32 grade
-            plan, _ = m.plan_for(2, 16, 16)
-            assert "grad" in plan.head_fuse, "fused DDIM head epilogue not available on the tensor-core head"
-            assert int(plan.head_fuse["grad"].tensor[0]) == 0, "fusion descriptor must be switched off after the loop"
-            assert_close(slow, fast, rtol=1e-3, atol=2e-3, what="generic vs fused-epilogue loop")
+
+
+def test_ddim_update_fused_into_head_epilogue_matches_separate_kernel():
+    """Tensor-core image heads run the DDIM update inside their epilogue (a step = timestep select + network, one graph).  The
+    generic loop (black-box callable -> pdae_ddim_step) must agree: same arithmetic, fp32-grade network mode."""
+    from pdae_b200.utils.synth import synth_images, synth_normal
+    d = gd()
+    cfg, g = load_golden("model_shiftunet_b64")      # base 64: the heads take the tensor-core path
+    m, inp = cases.model_case(cfg)
+    m = m.cuda().eval()
+    m.precision = "bf16x3"
+    xT, z = inp["x"].cuda(), inp["z"].cuda()
+    x0 = synth_images(2, 3, 16, 26).cuda()
+    with torch.no_grad():
+        for direction, x, stop in (("sample", xT, 0.0), ("sample", xT, 0.3), ("encode", x0, 0.0)):
+            dd = d._ddim("ddim10")
+            if direction == "sample":
+                fast = dd.shift_ddim_sample_loop(m, z, x, stop_percent=stop)
+            else:
+                fast = dd.shift_ddim_encode_loop(m, z, x)
+            slow = dd._loop(lambda a, b, c: m(a, b, c), x, z, direction, shift=True, stop_step=int(stop * dd.timesteps))
+            assert_close(fast, slow, rtol=1e-3, atol=2e-3, what=f"fused-epilogue vs generic loop ({direction}, stop {stop})")
+        plain = d._ddim("ddim10").ddim_sample_loop(m, xT, z)     # a ShiftUNet used without its shift: epsilon-only update on the grad head
+        slow = d._ddim("ddim10")._loop(lambda a, b, c: m(a, b, c)[0], xT, z, "sample", shift=False)
+        assert_close(plain, slow, rtol=1e-3, atol=2e-3, what="eps-only update fused into the shift head")
+    plan, _ = m.plan_for(2, 16, 16)
+    assert "grad" in plan.head_fuse, "fused DDIM head epilogue not available on the tensor-core head"
+    assert int(plan.head_fuse["grad"].tensor[0]) == 0, "fusion descriptor must be switched off after the loop"
+    e1, g1 = m(xT, g["t"].cuda(), z)                  # plain forward after the loops: untouched by the (disabled) fusion
+    from tests.test_gpu_parity import check
+    check(e1, g["eps"], "bf16x3", "forward after fused loops (eps)")
+    check(g1, g["grad"], "bf16x3", "forward after fused loops (grad)")
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16x3"])
