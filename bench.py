@@ -440,6 +440,8 @@ def main():
         dec.precision = enc.precision = chosen
         torch.cuda.empty_cache()
         extras["ffhq256_global64_strong"] = strong_scaling_extra(gd, chosen, world, rank, dev, timed)
+        extras["latent_unconditional_sample"] = latent_sample_extra(gd, dec, chosen, world, rank, dev, timed, B, size)
+        extras["pdae_training_step"] = training_step_extra(world, rank, dev, timed)
 
     if rank != 0:
         if world > 1:
@@ -516,6 +518,80 @@ def strong_scaling_extra(gd, precision, world, rank, dev, timed):
                "images_per_sec_scaled_to_100_plus_100_steps": round(ips * s / 100, 4), "steps": 1, "warmup": 1,
                "algorithmic_tflops_per_gpu": round(ips * (2 * s * 967.20 + 0.616) * 1e9 / 1e12 / world, 2)}
         del dec, enc
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:
+        return {"error": repr(e)[:300]}
+
+
+def latent_sample_extra(gd, dec, precision, world, rank, dev, timed, B, size):
+    """BASELINE.json config 4: unconditional sampling -- MLPSkipNet latent DPM (config/ffhq_latent.yml:16-23: 512 -> 2048 x 10
+    layers) for DDIM-100 steps, then the ShiftUNet decoder for DDIM-100 steps with stop_percent = 0.3 (epsilon-only plan on
+    the last 30) -- through GaussianDiffusion.latent_diffusion_sample (gaussian_diffusion.py:400-415), on the bench's decoder."""
+    try:
+        from pdae_b200.configs import FFHQ_LATENT
+        from pdae_b200.model.mlp_skip_net import MLPSkipNet
+        from pdae_b200.utils.synth import fill_module_, synth_normal
+        mlp = fill_module_(MLPSkipNet(**{k: v for k, v in FFHQ_LATENT.items() if k != "model"}), seed=5).eval().to(dev)
+        x_T = synth_normal((B, 3, size, size), 400 + rank).to(dev)
+        mean, std = torch.zeros(1, 512, device=dev), torch.ones(1, 512, device=dev)
+
+        def run():
+            with torch.inference_mode():
+                gd.latent_diffusion_sample("ddim100", "ddim100", mlp, dec, x_T, mean, std)
+        run()
+        ms = timed(run, 1)
+        return {"workload": "MLPSkipNet(512, 2048, 10 layers) latent DDIM-100 + celeba64-proxy ShiftUNet DDIM-100 (stop_percent 0.3)",
+                "batch_per_gpu": B, "n_gpus": world, "precision": precision, "ms_per_pass": round(ms, 3),
+                "images_per_sec": round(world * B / (ms / 1e3), 4), "steps": 1, "warmup": 1}
+    except Exception as e:
+        return {"error": repr(e)[:300]}
+
+
+def training_step_extra(world, rank, dev, timed):
+    """BASELINE.json config 5: the PDAE training step (representation_learning_train_one_batch + backward + gradient all-reduce
+    overlapped with the encoder backward + fused Adam/EMA), celeba64-proxy, 32 images per GPU.  fp32 CUDA-core forward / weight
+    gradients, split-operand tensor-core data gradients -- the training path is NOT on the tensor cores yet."""
+    try:
+        import copy
+        from pdae_b200.diffusion.gaussian_diffusion import GaussianDiffusion
+        from pdae_b200.model.representation_learning.encoder import CELEBA64Encoder
+        from pdae_b200.model.shift_unet import ShiftUNet
+        from pdae_b200.optim import FusedAdamEMA
+        from pdae_b200.utils.dist import OverlappedGradAllReduce
+        from pdae_b200.utils.synth import fill_module_, synth_images
+        Bt = 32
+        dec = fill_module_(ShiftUNet(latent_dim=512, **dict(CELEBA64_PROXY, dropout=0.1)), seed=0).to(dev)
+        enc = fill_module_(CELEBA64Encoder(latent_dim=512), seed=1).to(dev).train()
+        dec.freeze()
+        dec.set_train_mode()
+        dec.precision = enc.precision = "fp32"
+        ema_dec, ema_enc = copy.deepcopy(dec).requires_grad_(False), copy.deepcopy(enc).requires_grad_(False)
+        gdt = GaussianDiffusion(DIFFUSION, dev)
+        groups = [list(enc.parameters()), list(dec.label_emb.parameters()), list(dec.shift_middle_block.parameters()),
+                  list(dec.shift_output_blocks.parameters()), list(dec.shift_out.parameters())]
+        opt = FusedAdamEMA([{"params": g} for g in groups], lr=1e-4, ema_decay=0.9999)
+        opt.attach_ema(enc, ema_enc)
+        opt.attach_ema(dec, ema_dec)
+        x0 = synth_images(Bt, 3, 64, 500 + rank).to(dev)
+        red = OverlappedGradAllReduce([[p for g in groups[1:] for p in g], groups[0]])
+
+        def step():
+            loss = gdt.representation_learning_train_one_batch(enc, dec, x0)["prediction_loss"]
+            loss.backward()
+            opt.step(grad_scale=red.finish())
+            opt.zero_grad(set_to_none=True)
+        for _ in range(3):
+            step()
+        k = 5
+        ms = timed(lambda: [step() for _ in range(k)], 1) / k
+        n_train = sum(p.numel() for g in groups for p in g)
+        red.remove()
+        out = {"workload": "celeba64-proxy encoder + ShiftUNet (shift half trainable), dropout 0.1, fused Adam+EMA", "batch_per_gpu": Bt,
+               "n_gpus": world, "ms_per_step": round(ms, 2), "images_per_sec": round(world * Bt / ms * 1e3, 2), "steps": k, "warmup": 3,
+               "scaling": "weak", "allreduce_bytes_per_step": 4 * n_train if world > 1 else 0,
+               "arithmetic": "fp32 CUDA-core forward + weight gradients, split-operand tensor-core data gradients"}
+        del dec, enc, ema_dec, ema_enc, opt
         torch.cuda.empty_cache()
         return out
     except Exception as e:

@@ -207,10 +207,17 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__
   __shared__ uint32_t tmem_slot;
   __shared__ float st_acc[2][2][BN];   // [epilogue group][sum | sum^2][channel] of the group's current (image, n-tile)
 
-  constexpr int B_BYTES = BN * T3_BK * 2;
+  // Split mode with 64 output channels: W_hi and W_lo of a (tap, k-block) arrive as ONE 128-row tile [W_hi | W_lo]; the issuer
+  // runs a_hi x [W_hi | W_lo] as a single N = 128 MMA (accumulator columns 0-63: hi*hi, 64-127: hi*lo) and a_lo x W_hi as an
+  // N = 64 MMA into columns 0-63; the epilogue adds the two halves.  8 instead of 12 MMAs per tap and 56 instead of 72 KB of
+  // operand reads -- the 64-wide layers are bound by the shared-memory port (the A tile is re-read per MMA), not the tensor pipe.
+  constexpr bool MRG = X3 && BN == 64;
+  constexpr int ACC_COLS = MRG ? 128 : BN;
+  constexpr int B_BYTES = (MRG ? 128 : BN) * T3_BK * 2;
   constexpr int A_STAGE = (X3 ? 2 : 1) * T3_HALO_BYTES;
-  constexpr int TMEM_COLS = 2 * BN;
-  constexpr int NMAT = X3 ? 2 : 1;   // weight tiles per (tap, k-block): W | (W_hi, W_lo)
+  constexpr int TMEM_COLS = 2 * ACC_COLS;
+  constexpr int NMAT = (X3 && !MRG) ? 2 : 1;   // weight tiles per (tap, k-block): W | (W_hi, W_lo) | merged [W_hi | W_lo]
+  constexpr int ZMUL = X3 ? 2 : 1;             // weight matrices per tap in global memory
   const uint32_t smem0 = (s_u32(smem_raw) + 1023u) & ~1023u;
   const int SA = p.sa, SB = p.sb;
   const uint32_t a_base = smem0;
@@ -278,7 +285,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__
             const uint32_t dst = b_base + (uint32_t)(s * B_BYTES);
             if (elect_one()) {
               mb_expect_tx(full, (uint32_t)B_BYTES);
-              if (!skipk) tma_ld3(dst, &tmB, full, it * T3_BK, n0, tap * NMAT + m);
+              if (!skipk) tma_ld3(dst, &tmB, full, it * T3_BK, n0, tap * ZMUL + m);
               else tma_ld3(dst, &tmB2, full, (it - p.kblocks) * T3_BK, n0, m);
             }
             __syncwarp();
@@ -301,7 +308,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__
       const int ab = tl & 1;
       mb_wait_t(s_u32(&bar_acc_empty[ab]), (uint32_t)(((tl >> 1) & 1) ^ 1), p.dbg, w_acc);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tmem_d = tmem_u + (uint32_t)(ab * BN);
+      const uint32_t tmem_d = tmem_u + (uint32_t)(ab * ACC_COLS);
       for (int it = 0; it < total_it; ++it) {
         mb_wait_t(s_u32(&bar_a_full[sa]), pha, p.dbg, w_a);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -318,6 +325,22 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__
           const uint64_t bd = sw128_desc(b_base + (uint32_t)(sb * B_BYTES), 1024u);
           const uint32_t first = (uint32_t)((it | tp) != 0);
           const uint32_t bar_be = s_u32(&bar_b_empty[sb]);
+          if (MRG) {
+            constexpr uint32_t IDESC128 =
+                (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(T3_BM >> 4) << 24);
+            if (elect_one()) {
+              const uint64_t ad_lo = sw128_desc(a_hi + (uint32_t)T3_HALO_BYTES + off, A_SBO);
+              umma(tmem_d, ad_hi, bd, IDESC128, first);                                   // a_hi x [W_hi | W_lo]
+#pragma unroll
+              for (int k = 1; k < T3_BK / 16; ++k) umma(tmem_d, ad_hi + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), IDESC128, 1u);
+#pragma unroll
+              for (int k = 0; k < T3_BK / 16; ++k) umma(tmem_d, ad_lo + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), IDESC, 1u);   // a_lo x W_hi
+              umma_commit_to(bar_be);
+            }
+            __syncwarp();
+            if (++sb == SB) { sb = 0; phb ^= 1u; }
+            continue;
+          }
           if (elect_one()) {
             umma(tmem_d, ad_hi, bd, IDESC, first);
 #pragma unroll
@@ -517,7 +540,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__
       const int b0 = mt / p.tiles_y;
       const int x0 = tx * T3_TW, y0 = ty * T3_TH, n0 = nt * BN;
       const int ab = tl & 1;
-      const uint32_t tmem_acc = tmem_base + (uint32_t)(ab * BN) + ((uint32_t)(q * 32) << 16);
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(ab * ACC_COLS) + ((uint32_t)(q * 32) << 16);
       if (!X3 && p.has_res && elected) {       // residual chunk 0 (issued before the accumulator is needed)
         mb_expect_tx(rbar, T3_STG_BYTES);
         tma_ld4(rbuf, &tmR, rbar, n0, x0, y0, b0);
@@ -532,6 +555,12 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(v[j]);
+          if (MRG) {   // + the a_hi x W_lo half of the merged accumulator (split mode stores fp32: CW = 32)
+            tmem_ld32(tmem_acc + (uint32_t)(64 + c * CW), v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) val[j] += __uint_as_float(v[j]);
+          }
           if (p.out_bf16) {
             tmem_ld32(tmem_acc + (uint32_t)(c * CW + 32), v);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -770,7 +799,8 @@ extern "C" int pdae_conv_tc3_create(pdae_conv_tc3_plan** plan_out, const void* s
   pl->BN = BN;
   a.tiles_total = a.tiles_m * (Cout / BN);
   pl->grid = a.tiles_total < g_num_sms3 ? a.tiles_total : g_num_sms3;
-  const int a_stage = (x3 ? 2 : 1) * T3_HALO_BYTES, b_bytes = BN * T3_BK * 2;
+  const bool mrg = x3 && BN == 64;   // merged [W_hi | W_lo] weight tiles (see the kernel)
+  const int a_stage = (x3 ? 2 : 1) * T3_HALO_BYTES, b_bytes = (mrg ? 128 : BN) * T3_BK * 2;
   const int staging = ((a.has_res && !x3) ? 4 : 2) * T3_STG_BYTES;   // split mode reads its residual from global memory
   const int budget = 220 * 1024 - 1024 - staging;
   // the transform is software-pipelined, so two halo stages suffice; the weight tiles need depth (bytes in flight from L2)
@@ -831,7 +861,7 @@ extern "C" int pdae_conv_tc3_create(pdae_conv_tc3_plan** plan_out, const void* s
   {
     cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)(9 * nmat)};
     cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
-    cuuint32_t box[3] = {(cuuint32_t)T3_BK, (cuuint32_t)BN, 1};
+    cuuint32_t box[3] = {(cuuint32_t)T3_BK, (cuuint32_t)BN, (cuuint32_t)(mrg ? 2 : 1)};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&pl->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -842,7 +872,7 @@ extern "C" int pdae_conv_tc3_create(pdae_conv_tc3_plan** plan_out, const void* s
   if (Cs > 0) {
     cuuint64_t dims[3] = {(cuuint64_t)Cs, (cuuint64_t)Cout, (cuuint64_t)nmat};
     cuuint64_t strides[2] = {(cuuint64_t)Cs * 2, (cuuint64_t)Cout * Cs * 2};
-    cuuint32_t box[3] = {(cuuint32_t)T3_BK, (cuuint32_t)BN, 1};
+    cuuint32_t box[3] = {(cuuint32_t)T3_BK, (cuuint32_t)BN, (cuuint32_t)(mrg ? 2 : 1)};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&pl->tmB2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_skip), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
