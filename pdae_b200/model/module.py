@@ -179,7 +179,7 @@ class PlannedModule(nn.Module):
         memo[id(self)] = new
         import copy
         for k, v in self.__dict__.items():
-            if k == "_plan_cache":
+            if k in ("_plan_cache", "_train_cache"):   # (trainer plans own native handles too: a copy would double-free them)
                 continue
             new.__dict__[k] = copy.deepcopy(v, memo)
         return new

@@ -160,3 +160,25 @@ def test_elementwise_wrappers_promote_non_fp32_inputs():
         gd.q_sample(x0, t[:2], noise)
     with pytest.raises(ValueError):
         d._update(x0, td[:1], noise, None, "sample")
+
+
+def test_deepcopy_after_training_forward_does_not_share_native_plans():
+    """`copy.deepcopy(decoder)` is how the reference makes EMA nets; done AFTER a training step it must not copy the trainer's
+    native plans (handles would be freed twice) -- the copy records its own."""
+    cfg, gd, enc, dec, x0, t, noise = _train_setup()
+    _loss(gd, enc, dec, x0, t, noise).backward()
+    clone = copy.deepcopy(dec)
+    assert "_train_cache" not in clone.__dict__ and "_plan_cache" not in clone.__dict__
+    clone = clone.eval().requires_grad_(False)
+    with torch.no_grad():
+        z = enc(x0)
+        e1, g1 = clone(noise, t, z)
+        dec.eval()
+        e2, g2 = dec(noise, t, z)
+    assert_close(e1, e2, rtol=1e-4, atol=1e-5, what="deep-copied net vs original (eps)")
+    assert_close(g1, g2, rtol=1e-4, atol=1e-5, what="deep-copied net vs original (grad)")
+    del clone
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    _loss(gd, enc, dec.train(), x0, t, noise).backward()    # the original's trainer plans are still alive
