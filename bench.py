@@ -442,6 +442,9 @@ def main():
         extras["ffhq256_global64_strong"] = strong_scaling_extra(gd, chosen, world, rank, dev, timed)
         extras["latent_unconditional_sample"] = latent_sample_extra(gd, dec, chosen, world, rank, dev, timed, B, size)
         extras["pdae_training_step"] = training_step_extra(world, rank, dev, timed)
+        if world == 1 and have_reference():
+            extras["reference_pytorch_on_this_gpu"] = reference_gpu_extra(dec_cpu, enc_cpu, c, enc_kind, S, B, size, enc_size, dev,
+                                                                          enc_input)
 
     if rank != 0:
         if world > 1:
@@ -518,6 +521,64 @@ def strong_scaling_extra(gd, precision, world, rank, dev, timed):
                "images_per_sec_scaled_to_100_plus_100_steps": round(ips * s / 100, 4), "steps": 1, "warmup": 1,
                "algorithmic_tflops_per_gpu": round(ips * (2 * s * 967.20 + 0.616) * 1e9 / 1e12 / world, 2)}
         del dec, enc
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:
+        return {"error": repr(e)[:300]}
+
+
+def reference_gpu_extra(dec_cpu, enc_cpu, c, enc_kind, S, B, size, enc_size, dev, enc_input):
+    """Context, not the contract's reference arm (that one is the CPU run): the UNMODIFIED reference modules (baseline/_ref) on
+    THIS GPU through stock PyTorch -- eager mode, fp32 parameters, TF32 convolutions / matmuls as the reference's trainers set
+    (trainer/base_trainer.py:24-25).  (1) images/s of the same workload from timed DDIM steps; (2) the same 1e-5 gate probe:
+    does the reference's own GPU arithmetic reproduce its CPU fp32 result on these weights?"""
+    try:
+        import copy
+        from pdae_b200.utils.synth import synth_images, synth_normal
+        old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = True
+        torch.backends.cuda.matmul.allow_tf32 = True
+        ref = ReferenceCPU(dec_cpu, enc_cpu, c, enc_kind, S)
+        rdec, renc = copy.deepcopy(ref.dec).to(dev), copy.deepcopy(ref.enc).to(dev)
+        import diffusion.gaussian_diffusion as rgd       # the reference (sys.path set by ReferenceCPU)
+        from diffusion.ddim import DDIM as RDDIM
+        g = rgd.GaussianDiffusion(DIFFUSION, device=dev)
+        nb, tmap = g.get_ddim_betas_and_timestep_map(f"ddim{S}", g.alphas_cumprod.cpu().numpy())
+        dd = RDDIM(nb, tmap, dev)
+        x = synth_normal((B, 3, size, size), 5).to(dev)
+        out = {"what": "unmodified reference modules, stock PyTorch eager on this GPU, TF32 convs/matmuls (trainer/base_trainer.py:24-25)",
+               "batch": B}
+        with torch.inference_mode():
+            z = renc(enc_input(synth_images(B, 3, size, 6).to(dev)))
+            t = torch.full((B,), S // 2, dtype=torch.long, device=dev)
+            for _ in range(2):
+                dd.shift_ddim_sample(rdec, z, x, t)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            n = 5
+            for _ in range(n):
+                x = dd.shift_ddim_sample(rdec, z, x, t)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n
+            out.update({"ms_per_decoder_step": round(ms, 2), "images_per_sec_extrapolated": round(B / (2 * S * ms / 1e3), 3),
+                        "sample": f"{n} timed shift_ddim_sample steps at batch {B}, extrapolated to {2 * S} steps per image"})
+            # gate probe: same images / schedule as cpu_baseline.parity
+            ns, s = (2, 10) if size <= 64 else ((1, 5) if size <= 128 else (1, 3))
+            x0 = synth_images(ns, 3, size, 4242)
+            enc_o, dec_o, O = oracle_fns(dec_cpu, enc_cpu, c, enc_kind)
+            D = O.DiffusionOracle(DIFFUSION)
+            zc = enc_o(enc_input(x0))
+            refc = D.representation_learning_ddim_sample(f"ddim{s}", dec_o, D.representation_learning_ddim_encode(f"ddim{s}", dec_o, x0, zc), zc)
+            xd = x0.to(dev)
+            rec = g.representation_learning_autoencoding(f"ddim{s}", f"ddim{s}", lambda a: renc(enc_input(a)), rdec, xd).cpu()
+            m_ref, m_gpu = mse01(refc, x0), mse01(rec, x0)
+            out["parity_tf32_vs_cpu_fp32"] = {"recon_mse": m_gpu, "delta_mse": abs(m_gpu - m_ref),
+                                              "rel_l2_vs_reference": float((rec - refc).norm() / refc.norm()),
+                                              "pass": bool(abs(m_gpu - m_ref) <= GATE)}
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+        del rdec, renc
         torch.cuda.empty_cache()
         return out
     except Exception as e:

@@ -121,3 +121,24 @@ def test_conv_tc3_many_tiles_per_cta_and_bn256():
 def test_conv_tc3_identity_prologue_is_a_plain_conv():
     out, stats, y = _run(2, 32, 16, 64, 0, 64, True, False, False, False, seed=5, silu=0)
     _check(out, stats, y, True, False, "no SiLU (a*x+b only)")
+
+
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+def test_shiftunet_step_plan_is_fused(precision):
+    """Structure of the benchmark network's step plan (celeba64-proxy): every ResBlock conv at H >= 16 is ONE conv_tc3 launch
+    (GroupNorm-apply / AdaGN / SiLU [/ hi-lo split] inside), the concatenated skip input is never materialised, and the only
+    activation-sized elementwise passes left are the resampling blocks, the 8x8 level, the attention norm and the two heads."""
+    from pdae_b200.configs import CELEBA64_PROXY
+    from pdae_b200.model.shift_unet import ShiftUNet
+    from pdae_b200.utils.synth import fill_module_
+    m = fill_module_(ShiftUNet(latent_dim=512, **CELEBA64_PROXY), seed=0).eval().cuda()
+    m.precision = precision
+    plan, _ = m.plan_for(2, 64, 64)
+    names = [op[0] for op in plan.ops]
+    n3 = names.count("conv_tc3")
+    apply = names.count("gn_apply") + names.count("gn_apply_split3")
+    assert n3 == 56, (n3, {k: names.count(k) for k in set(names)})
+    assert apply <= 56, apply          # round 1: 104 gn_apply launches per step, one in front of every conv
+    fused_skips = sum(1 for op in plan.ops if op[0] == "conv_tc3" and op[1][10] + op[1][12] > 0)
+    assert fused_skips >= 20, fused_skips       # channel-changing blocks: the 1x1 skip conv rides in conv2's k-loop
+    assert "grad" in plan.head_fuse              # DDIM update can run in the shift head's epilogue
