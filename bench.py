@@ -372,7 +372,7 @@ def main():
         rec = autoencode(xd)
         out_host.copy_(rec, non_blocking=True)
 
-    e2e_steps = max(1, min(args.steps, 5))
+    e2e_steps = max(1, min(args.steps, 3))     # (a full pass each; bounded so the default run stays within minutes)
     e2e_once()
     ms_e2e = timed(e2e_once, e2e_steps) / e2e_steps
     e2e_val = world * B / (ms_e2e / 1e3)
