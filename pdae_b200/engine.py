@@ -153,6 +153,9 @@ class Plan:
         self._tc2_handles: List[ctypes.c_void_p] = []
         self._tc3_handles: List[ctypes.c_void_p] = []
         self.head_fuse: Dict[str, Buf] = {}   # image heads whose epilogue can run the DDIM update (set by a sampling loop)
+        # training forward plans (fp32, every intermediate kept for the backward): run the eligible convs on the tensor cores in
+        # the split-operand mode -- the fp32 activation the backward needs stays as it is, a [hi | lo | hi] copy feeds conv_tc2
+        self.train_tc = False
         self.n_launch = 0
         self.keep_all = False
         self.dropout_masks: list = []   # (block, mask buffer, p): filled by the trainer before every training forward
@@ -516,7 +519,10 @@ class Plan:
 
     # ---- emitters: thin typed wrappers that pick kernels ------------------------------------------
     def use_tc(self, Cin: int, Cout: int, k: int, stride: int, H: int, W: int) -> bool:
-        if not self.tc or stride != 1 or k not in (1, 3) or Cin % 64 or Cout % 64:
+        return self.tc and self._tc_shape_ok(Cin, Cout, k, stride, H, W)
+
+    def _tc_shape_ok(self, Cin: int, Cout: int, k: int, stride: int, H: int, W: int) -> bool:
+        if stride != 1 or k not in (1, 3) or Cin % 64 or Cout % 64:
             return False
         if not self.v2 and ((H & (H - 1)) or (W & (W - 1))):
             return False   # the legacy v1 kernel (PDAE_TC_V1=1, A/B aid) only tiles power-of-two images
@@ -536,6 +542,16 @@ class Plan:
         with (e.g. the transposed, flipped weights of a dgrad) -- the packed copy still tracks the PARAMETER's version.
         Returns the per-channel (sum, sum^2) buffer [B][Cout][2] if the tensor-core epilogue produced one."""
         pad = k // 2 if pad is None else pad
+        if (self.train_tc and x.dtype == torch.float32 and out.dtype == torch.float32 and not (in_nchw or out_nchw or a_silu)
+                and skip is None and w_transform is None and pad == k // 2 and self._tc_shape_ok(Cin, Cout, k, stride, H, W)):
+            x3b = self.new((B, H, W, 3 * Cin), torch.bfloat16, "train_split3")
+            x3b.split3 = True
+            self.call("gn_apply_split3", x, Cin, None, 0, None, 0, RESAMPLE_NONE, B, H, W, x3b, None, PDAE_F32, _STREAM)
+            wp = self.pack((wkey or id(weight), "tc_x3"), [weight],
+                           lambda Cin=Cin: split3_weights(weight.detach().reshape(Cout, Cin, k * k)))
+            self.call("conv_tc2", x3b, wp, self.param(bias), residual, out, PDAE_F32, None, B, H, W, 3 * Cin, Cout, k, 0,
+                      bn_override or self.bn_override, flops=2.0 * B * H * W * Cout * Cin * k * k)
+            return None
         bias_b = self.param(bias)
         wkey = wkey or id(weight)
         if x.dtype == torch.bfloat16 and self.use_tc(Cin, Cout, k, stride, H, W) and not (in_nchw or out_nchw or a_silu):

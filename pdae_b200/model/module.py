@@ -159,7 +159,7 @@ class PlannedModule(nn.Module):
         for m in self.modules():
             for cache_name in ("_plan_cache", "_train_cache"):
                 for ent in (m.__dict__.get(cache_name) or {}).values():
-                    plans = [ent[0]] if isinstance(ent, tuple) else [getattr(ent, "fwd", None), getattr(ent, "bwd", None)]
+                    plans = [ent[0]] if isinstance(ent, tuple) else [getattr(ent, "fwd", None), getattr(ent, "bwd", None), getattr(ent, "frozen", None)]
                     for pl in plans:
                         if pl is not None:
                             for pk in pl.packed:

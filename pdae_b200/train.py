@@ -4,10 +4,12 @@
 
 Scope (the PDAE training step, diffusion/gaussian_diffusion.py:234-255): the semantic encoder (all parameters) and the
 trainable half of the ShiftUNet (``label_emb``, ``shift_middle_block``, ``shift_output_blocks``, ``shift_out``); the frozen
-half builds no graph in the reference either (its parameters and x_t do not require grad).  Arithmetic is fp32 on CUDA
-cores (``pdae_conv2d_wgrad_simt``, ``pdae_gn_bwd_*``, ``pdae_gemm_batched_simt``, ``pdae_softmax_bwd``) except the data
-gradients of the stride-1 convs, which run on the tensor cores in the split-operand fp32-grade mode (``bwd_plan``); tensor-core
-weight gradients and a tensor-core training forward are future work.  Dropout is inverted dropout with masks drawn by torch's CUDA generator.
+half builds no graph in the reference either (its parameters and x_t do not require grad) -- it runs as a tensor-core plan
+in the split-operand (fp32-grade) mode with the fused-prologue convs.  The trainable half keeps its fp32 activations for the
+backward; its forward convs and the data gradients of the stride-1 convs run on the tensor cores on split operands
+(``Plan.train_tc``, ``bwd_plan``).  Weight gradients, GroupNorm / attention backward stay fp32 on CUDA cores
+(``pdae_conv2d_wgrad_simt``, ``pdae_gn_bwd_*``, ``pdae_gemm_batched_simt``, ``pdae_softmax_bwd``): tensor-core weight gradients
+are future work.  Dropout is inverted dropout with masks drawn by torch's CUDA generator.
 """
 from __future__ import annotations
 
@@ -261,44 +263,84 @@ class ShiftUNetTrainer(_Generation):
     """Forward (fp32, all intermediates kept) + backward plans of a ShiftUNet for one input shape."""
 
     def __init__(self, net, B: int, H: int, W: int):
-        from .model.unet import EmbBank, emit_head, emit_time_embed, res_blocks_of
+        from .model.unet import EmbBank, emit_head, emit_stem, emit_time_embed, res_blocks_of
         self.net = net
         dev = net._device()
-        P = Plan(dev, "fp32")
-        P.keep_all = True
         E, base = net.time_embed_dim, net.base_channel
-        self.x_in = P.new((B, net.input_channel, H, W), torch.float32, "x_nchw")
-        self.t_in = P.new((B,), torch.int64, "t")
-        self.z_in = P.new((B, net.latent_dim), torch.float32, "z")
-        emb = emit_time_embed(P, net.time_embed, self.t_in, B, base, E, dev)
-        shift_emb = P.new((B, E), torch.float32, "shift_emb")
-        P.linear(self.z_in, net.label_emb.weight, net.label_emb.bias, shift_emb, B=B, Cin=net.latent_dim, Cout=E)
         shift_blocks = res_blocks_of(net.shift_middle_block, net.shift_output_blocks)
         frozen_blocks = res_blocks_of(net.input_blocks, net.middle_block, net.output_blocks)
-        bank_f = EmbBank(P, frozen_blocks, "t", emb, B, E, "train_t_frozen")
+        # The FROZEN half (input / middle / output blocks, `out` head: 55 % of the forward FLOPs) builds no autograd graph in
+        # the reference either (its parameters do not require grad): it runs as a tensor-core plan in the split-operand
+        # (fp32-grade) mode with the fused-prologue convs, exactly like sampling; only its skip tensors and bottleneck output
+        # are handed to the trainable half.  PDAE_TRAIN_TC_FWD=0 restores the single fp32 CUDA-core forward plan (A/B aid).
+        tc_fwd = os.environ.get("PDAE_TRAIN_TC_FWD", "1") == "1"
+        self.frozen = None
+        if tc_fwd:
+            Fp = Plan(dev, "bf16x3")
+            self.x_in = Fp.new((B, net.input_channel, H, W), torch.float32, "x_nchw")
+            self.t_in = Fp.new((B,), torch.int64, "t")
+            self.x_in.keep = self.t_in.keep = True
+            emb_f = emit_time_embed(Fp, net.time_embed, self.t_in, B, base, E, dev)
+            bank_f = EmbBank(Fp, frozen_blocks, "t", emb_f, B, E, "train_t_frozen")
+            hf = emit_stem(Fp, net.input_blocks[0][0], self.x_in, B, H, W, net.input_channel)
+            hs_f = [hf]
+            for stage in list(net.input_blocks)[1:]:
+                hf = stage.emit(Fp, hf, bank_f)
+                hs_f.append(hf)
+            for sfrc in hs_f:                      # consumed by the trainable half's plan: private storage
+                sfrc.b1.keep = True
+            eps_h = net.middle_block.emit(Fp, hf, bank_f)
+            for stage, skip in zip(net.output_blocks, reversed(hs_f)):
+                eps_h = stage.emit(Fp, eps_h.cat(skip), bank_f)
+            self.eps = Fp.new((B, net.output_channel, H, W), torch.float32, "eps_nchw")
+            self.eps.keep = True
+            emit_head(Fp, net.out, eps_h, self.eps)
+            Fp.finalize()
+            self.frozen = Fp
+        P = Plan(dev, "fp32")
+        P.keep_all = True
+        P.train_tc = tc_fwd       # trainable half: fp32 activations kept for the backward, convs on the tensor cores (split operands)
+        if tc_fwd:
+            t_src = P.fixed(self.t_in.tensor)
+        else:
+            self.x_in = P.new((B, net.input_channel, H, W), torch.float32, "x_nchw")
+            self.t_in = P.new((B,), torch.int64, "t")
+            t_src = self.t_in
+        self.z_in = P.new((B, net.latent_dim), torch.float32, "z")
+        emb = emit_time_embed(P, net.time_embed, t_src, B, base, E, dev)
+        shift_emb = P.new((B, E), torch.float32, "shift_emb")
+        P.linear(self.z_in, net.label_emb.weight, net.label_emb.bias, shift_emb, B=B, Cin=net.latent_dim, Cout=E)
         bank_t = EmbBank(P, shift_blocks, "t", emb, B, E, "train_t_shift")
         bank_z = EmbBank(P, shift_blocks, "z", shift_emb, B, E, "train_z_shift")
-        emb_of = lambda blk: (bank_t if id(blk) in bank_t.offsets else bank_f)(blk)
-
-        stem = net.input_blocks[0][0]
-        c0 = stem.weight.shape[0]
-        h0 = P.new((B, H, W, c0), torch.float32, "stem")
-        P.conv(self.x_in, stem.weight, stem.bias, h0, B=B, H=H, W=W, Cin=net.input_channel, Cout=c0, k=3, in_nchw=True)
-        h = Src(h0, c0, B, H, W)
-        hs = [h]
-        for stage in list(net.input_blocks)[1:]:
-            h = stage.emit(P, h, emb_of)
-            hs.append(h)
-        eps_h = net.middle_block.emit(P, h, emb_of)
         tape: list = []
-        shift_h = net.shift_middle_block.emit(P, h, emb_of, bank_z, tape=tape)
-        for stage, shift_stage in zip(net.output_blocks, net.shift_output_blocks):
-            skip = hs.pop()
-            eps_h = stage.emit(P, eps_h.cat(skip), emb_of)
-            shift_h = shift_stage.emit(P, shift_h.cat(skip), emb_of, bank_z, tape=tape)
-        self.eps = P.new((B, net.output_channel, H, W), torch.float32, "eps_nchw")
+        if tc_fwd:
+            hs = [Src(P.fixed(sfrc.b1.tensor), sfrc.C, B, sfrc.H, sfrc.W) for sfrc in hs_f]
+            h = hs[-1]
+            emb_of = bank_t
+            shift_h = net.shift_middle_block.emit(P, h, emb_of, bank_z, tape=tape)
+            for shift_stage in net.shift_output_blocks:
+                shift_h = shift_stage.emit(P, shift_h.cat(hs.pop()), emb_of, bank_z, tape=tape)
+        else:
+            bank_f = EmbBank(P, frozen_blocks, "t", emb, B, E, "train_t_frozen")
+            emb_of = lambda blk: (bank_t if id(blk) in bank_t.offsets else bank_f)(blk)
+            stem = net.input_blocks[0][0]
+            c0 = stem.weight.shape[0]
+            h0 = P.new((B, H, W, c0), torch.float32, "stem")
+            P.conv(self.x_in, stem.weight, stem.bias, h0, B=B, H=H, W=W, Cin=net.input_channel, Cout=c0, k=3, in_nchw=True)
+            h = Src(h0, c0, B, H, W)
+            hs = [h]
+            for stage in list(net.input_blocks)[1:]:
+                h = stage.emit(P, h, emb_of)
+                hs.append(h)
+            eps_h = net.middle_block.emit(P, h, emb_of)
+            shift_h = net.shift_middle_block.emit(P, h, emb_of, bank_z, tape=tape)
+            for stage, shift_stage in zip(net.output_blocks, net.shift_output_blocks):
+                skip = hs.pop()
+                eps_h = stage.emit(P, eps_h.cat(skip), emb_of)
+                shift_h = shift_stage.emit(P, shift_h.cat(skip), emb_of, bank_z, tape=tape)
+            self.eps = P.new((B, net.output_channel, H, W), torch.float32, "eps_nchw")
+            emit_head(P, net.out, eps_h, self.eps)
         self.grad = P.new((B, net.input_channel, H, W), torch.float32, "shift_nchw")
-        emit_head(P, net.out, eps_h, self.eps)
         emit_head(P, net.shift_out, shift_h, self.grad, tape=tape)
         P.finalize()
         self.fwd = P
@@ -333,11 +375,16 @@ class ShiftUNetTrainer(_Generation):
         self.bwd = BP
         self.params = [p for m in net._shift_parts() for p in m.parameters()]
 
+    def stale(self) -> bool:
+        return self.fwd.stale() or self.bwd.stale() or (self.frozen is not None and self.frozen.stale())
+
     def forward(self, x, t, z):
         draw_dropout_masks(self.fwd)
         self.x_in.tensor.copy_(x)
         self.t_in.tensor.copy_(t)
         self.z_in.tensor.copy_(z)
+        if self.frozen is not None:
+            self.frozen.run()
         self.fwd.run()
         return self.eps.tensor.clone(), self.grad.tensor.clone()
 
@@ -373,7 +420,7 @@ def shiftunet_train_forward(net, x, t, z):
     key = ("train", B, H, W, tuple(m.training for m in net._shift_parts()))
     cache = net.__dict__.setdefault("_train_cache", {})
     tr = cache.get(key)
-    if tr is None or tr.fwd.stale() or tr.bwd.stale():
+    if tr is None or tr.stale():
         tr = ShiftUNetTrainer(net, B, H, W)
         cache[key] = tr
     return _ShiftUNetFn.apply(tr, x, t, z, *tr.params)
@@ -390,6 +437,7 @@ class UNetTrainer(_Generation):
         dev = net._device()
         P = Plan(dev, "fp32")
         P.keep_all = True
+        P.train_tc = os.environ.get("PDAE_TRAIN_TC_FWD", "1") == "1"   # convs on the tensor cores (split operands), fp32 activations kept
         E, base, Cimg = net.time_embed_dim, net.base_channel, net.input_channel
         self.x_in = P.new((B, Cimg, H, W), torch.float32, "x_nchw")
         self.t_in = P.new((B,), torch.int64, "t")
