@@ -215,6 +215,19 @@ int pdae_conv_tc3_create(pdae_conv_tc3_plan** plan, const void* src1, int C1, co
 int pdae_conv_tc3_run(const pdae_conv_tc3_plan* plan, pdae_stream_t stream);
 void pdae_conv_tc3_destroy(pdae_conv_tc3_plan* plan);
 
+/* Weight gradient of a stride-1 3x3 / 1x1 "same" convolution on the tensor cores (what autograd computes for conv weights
+ * under trainer/train_representation_learning.py:112 loss.backward(); convs of model/module.py:241-259, 278-297):
+ * dw[tap][cin][cout] += sum_{b,y,x} act[b, y+dy, x+dx, cin] * dy[b, y, x, cout].  act3 / dy3: bf16 NHWC with 3*C channels,
+ * split-operand blocks [hi | lo | hi] (pdae_gn_apply_split3); every product is a_hi*d_hi + a_lo*d_hi + a_hi*d_lo with fp32
+ * accumulation in TMEM (fp32-grade).  dw must be zeroed by the caller (split-K partial sums are added with fp32 reductions).
+ * Shapes: Cin % 64 == 0, Cout % 64 == 0, one of them % 128 == 0, H*W tileable by 64-pixel boxes (pdae_wgrad_tc_supported). */
+typedef struct pdae_wgrad_tc_plan pdae_wgrad_tc_plan;
+int pdae_wgrad_tc_supported(int H, int W, int Cin, int Cout, int ksize);
+int pdae_wgrad_tc_create(pdae_wgrad_tc_plan** plan, const void* act3_bf16, const void* dy3_bf16, float* dw, int B, int H, int W,
+                         int Cin, int Cout, int ksize);
+int pdae_wgrad_tc_run(const pdae_wgrad_tc_plan* plan, pdae_stream_t stream);
+void pdae_wgrad_tc_destroy(pdae_wgrad_tc_plan* plan);
+
 /* v2: persistent CTAs, double-buffered TMEM accumulators (epilogue overlaps the next tile's main loop), TMA-store
  * epilogue.  out_dtype PDAE_F32|PDAE_BF16; ch_stats (optional) fp32 [B][Cout][2] accumulates per-channel (sum, sum^2)
  * of the stored values (zero it first); a residual is read in the OUTPUT's dtype.  cout_valid > 0 selects the image-head variant:

@@ -16,7 +16,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libpdae_b200.so")
-SOURCES = ["conv_simt.cu", "norm_elementwise.cu", "attention_simt.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc3.cu", "backward_simt.cu", "train_io.cu"]
+SOURCES = ["conv_simt.cu", "norm_elementwise.cu", "attention_simt.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc3.cu", "wgrad_tc.cu", "backward_simt.cu", "train_io.cu"]
 
 PDAE_F32, PDAE_BF16 = 0, 1
 RESAMPLE_NONE, RESAMPLE_UP2, RESAMPLE_DOWN2 = 0, 1, 2
@@ -107,6 +107,10 @@ _SIGS = {
                                      _P, c_int, _P, c_int, c_int, c_int, c_int, c_int]),
     "pdae_conv_tc3_run": (c_int, [_P, _P]),
     "pdae_conv_tc3_destroy": (None, [_P]),
+    "pdae_wgrad_tc_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),
+    "pdae_wgrad_tc_create": (c_int, [POINTER(c_void_p), _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "pdae_wgrad_tc_run": (c_int, [_P, _P]),
+    "pdae_wgrad_tc_destroy": (None, [_P]),
     "pdae_softmax_bf16": (c_int, [_P, _P, c_int64, c_int, c_float, _P]),
     "pdae_transpose_v": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "pdae_qkv_split3": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),

@@ -152,6 +152,7 @@ class Plan:
         self._tc_handles: List[ctypes.c_void_p] = []
         self._tc2_handles: List[ctypes.c_void_p] = []
         self._tc3_handles: List[ctypes.c_void_p] = []
+        self._wg_handles: List[ctypes.c_void_p] = []
         self.head_fuse: Dict[str, Buf] = {}   # image heads whose epilogue can run the DDIM update (set by a sampling loop)
         # training forward plans (fp32, every intermediate kept for the backward): run the eligible convs on the tensor cores in
         # the split-operand mode -- the fp32 activation the backward needs stays as it is, a [hi | lo | hi] copy feeds conv_tc2
@@ -310,6 +311,9 @@ class Plan:
             if fn == "conv_tc3":
                 compiled.append(self._compile_tc3(args))
                 continue
+            if fn == "wgrad_tc":
+                compiled.append(self._compile_wgrad(args))
+                continue
             cargs = []
             sidx = -1
             for k, a in enumerate(args):
@@ -387,6 +391,15 @@ class Plan:
         self._tc3_handles.append(h)
         return (self.L.pdae_conv_tc3_run, [h, None], 1, "conv_tc3")
 
+    def _compile_wgrad(self, args):
+        act3, dy3, dw, B, H, W, Cin, Cout, k = args
+        h = ctypes.c_void_p()
+        rc = self.L.pdae_wgrad_tc_create(ctypes.byref(h), self._resolve(act3), self._resolve(dy3), self._resolve(dw), B, H, W, Cin,
+                                         Cout, k)
+        _native.check(rc, "pdae_wgrad_tc_create")
+        self._wg_handles.append(h)
+        return (self.L.pdae_wgrad_tc_run, [h, None], 1, "wgrad_tc")
+
     def _compile_gemm_softmax(self, args):
         a, a_ld, a_bs, b, b_ld, b_bs, out, o_ld, o_bs, batch, M, N, K, alpha = args
         h = ctypes.c_void_p()
@@ -433,6 +446,8 @@ class Plan:
                 self.L.pdae_conv_tc2_destroy(h)
             for h in self._tc3_handles:
                 self.L.pdae_conv_tc3_destroy(h)
+            for h in self._wg_handles:
+                self.L.pdae_wgrad_tc_destroy(h)
         except Exception:
             pass
 

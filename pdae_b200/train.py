@@ -68,6 +68,7 @@ class Backward:
         self.sink = sink
         self._fixed: Dict[int, Buf] = {}
         self.tc_dgrad = bool(getattr(BP, "x3", False))
+        self.tc_wgrad = self.tc_dgrad and os.environ.get("PDAE_TRAIN_TC_WGRAD", "1") == "1"
 
     def fx(self, b):
         if b is None:
@@ -89,9 +90,20 @@ class Backward:
         pad = k // 2 if pad is None else pad
         Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
         kk = k * k
+        same = stride == 1 and k in (1, 3) and pad == k // 2 and not in_nchw
+        dy3 = None
         if trainable:
             dw = P.new_zeroed(kk * Cin * Cout)
-            P.call("conv2d_wgrad_simt", self.fx(x), int(in_nchw), int(a_silu), dy, dw, B, H, W, Cin, Cout, k, stride, pad, _STREAM)
+            if self.tc_wgrad and same and not a_silu and P.L.pdae_wgrad_tc_supported(H, W, Cin, Cout, k):
+                # weight gradient on the tensor cores (wgrad_tc.cu): both operands split [hi | lo | hi], fp32-grade products
+                a3, _ = P.gn_apply(self.fx(x), Cin, None, 0, None, silu=False, resample=RESAMPLE_NONE, B=B, H=H, W=W,
+                                   act_dtype=torch.bfloat16)
+                dy3, _ = P.gn_apply(dy, Cout, None, 0, None, silu=False, resample=RESAMPLE_NONE, B=B, H=H, W=W,
+                                    act_dtype=torch.bfloat16)
+                P.call("wgrad_tc", a3, dy3, dw, B, H, W, Cin, Cout, k, flops=2.0 * B * H * W * Cin * Cout * kk)
+            else:
+                P.call("conv2d_wgrad_simt", self.fx(x), int(in_nchw), int(a_silu), dy, dw, B, H, W, Cin, Cout, k, stride, pad,
+                       _STREAM)
             unpack = w_unpack or (lambda t, kk=kk, Cin=Cin, Cout=Cout: t.view(kk, Cin, Cout).permute(2, 1, 0))
             self.sink.add(weight, dw, kk * Cin * Cout, unpack)
             if bias is not None:
@@ -100,11 +112,12 @@ class Backward:
                 self.sink.add(bias, db, Cout, lambda t: t)
         if not need_dx:
             return None
-        if self.tc_dgrad and stride == 1 and k in (1, 3) and pad == k // 2 and not in_nchw and P.use_tc(Cout, Cin, k, 1, H, W):
+        if self.tc_dgrad and same and P.use_tc(Cout, Cin, k, 1, H, W):
             # dgrad of a stride-1 "same" conv = conv of dy with the transposed, spatially flipped weights: on the tensor
             # cores in the split-operand (fp32-grade) mode -- dy is split [hi | lo | hi], W' packed [W'_hi | W'_hi | W'_lo]
-            dy3, _ = P.gn_apply(dy, Cout, None, 0, None, silu=False, resample=RESAMPLE_NONE, B=B, H=H, W=W,
-                                act_dtype=torch.bfloat16)
+            if dy3 is None:
+                dy3, _ = P.gn_apply(dy, Cout, None, 0, None, silu=False, resample=RESAMPLE_NONE, B=B, H=H, W=W,
+                                    act_dtype=torch.bfloat16)
             dx = P.new((B, H, W, Cin), torch.float32, "dx")
             P.conv(dy3, weight, None, dx, B=B, H=H, W=W, Cin=Cout, Cout=Cin, k=k, wkey=(id(weight), "dgrad"),
                    w_transform=lambda w, Cout=Cout, Cin=Cin, k=k: w.reshape(Cout, Cin, k, k).flip(2, 3).transpose(0, 1).contiguous())
