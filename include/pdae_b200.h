@@ -220,7 +220,7 @@ void pdae_conv_tc3_destroy(pdae_conv_tc3_plan* plan);
  * dw[tap][cin][cout] += sum_{b,y,x} act[b, y+dy, x+dx, cin] * dy[b, y, x, cout].  act3 / dy3: bf16 NHWC with 3*C channels,
  * split-operand blocks [hi | lo | hi] (pdae_gn_apply_split3); every product is a_hi*d_hi + a_lo*d_hi + a_hi*d_lo with fp32
  * accumulation in TMEM (fp32-grade).  dw must be zeroed by the caller (split-K partial sums are added with fp32 reductions).
- * Shapes: Cin % 64 == 0, Cout % 64 == 0, one of them % 128 == 0, H*W tileable by 64-pixel boxes (pdae_wgrad_tc_supported). */
+ * Shapes: Cin % 64 == 0, Cout % 64 == 0, images tileable by 64-pixel TMA boxes (pdae_wgrad_tc_supported). */
 typedef struct pdae_wgrad_tc_plan pdae_wgrad_tc_plan;
 int pdae_wgrad_tc_supported(int H, int W, int Cin, int Cout, int ksize);
 int pdae_wgrad_tc_create(pdae_wgrad_tc_plan** plan, const void* act3_bf16, const void* dy3_bf16, float* dw, int B, int H, int W,

@@ -186,6 +186,44 @@ __global__ void colsum_kernel(const float* __restrict__ dy, long long M, int N, 
   }
 }
 
+// N % 4 == 0: a warp reads 32 float4 columns (512 contiguous bytes) of one row, the 8 warps of a CTA take interleaved rows
+// (four independent loads in flight per thread), partial sums meet in shared memory, one fp32 reduction per column and CTA
+__global__ void __launch_bounds__(256) colsum_v4_kernel(const float* __restrict__ dy, long long M, int N, float* __restrict__ out,
+                                                        int rows_per_cta) {
+  __shared__ float4 part[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nv = N >> 2;
+  const long long m0 = (long long)blockIdx.x * rows_per_cta, m1 = min(M, m0 + rows_per_cta);
+  const float4* src = reinterpret_cast<const float4*>(dy);
+  for (int cb = 0; cb < nv; cb += 32) {
+    const int cv = cb + lane;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cv < nv) {
+      long long m = m0 + w;
+      for (; m + 24 < m1; m += 32) {
+        const float4 a = src[m * nv + cv], b = src[(m + 8) * nv + cv], c = src[(m + 16) * nv + cv], d = src[(m + 24) * nv + cv];
+        s.x += (a.x + b.x) + (c.x + d.x); s.y += (a.y + b.y) + (c.y + d.y);
+        s.z += (a.z + b.z) + (c.z + d.z); s.w += (a.w + b.w) + (c.w + d.w);
+      }
+      for (; m < m1; m += 8) {
+        const float4 a = src[m * nv + cv];
+        s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      }
+    }
+    part[w][lane] = s;
+    __syncthreads();
+    if (w == 0 && cv < nv) {
+#pragma unroll
+      for (int i = 1; i < 8; ++i) {
+        const float4 t = part[i][lane];
+        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+      }
+      float* o = out + 4 * cv;
+      atomicAdd(o, s.x); atomicAdd(o + 1, s.y); atomicAdd(o + 2, s.z); atomicAdd(o + 3, s.w);
+    }
+    __syncthreads();
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // GroupNorm(+AdaGN)+SiLU(+resample) backward.  Forward: y = R( f(a*x + b) ), f = SiLU or id, R = none / nearest-up2 / avg-pool2.
 // pass 1: per (b,c):  S1 = sum du,  S2 = sum du * x   with du = f'(u) * R^T(dy)
@@ -559,6 +597,13 @@ extern "C" int pdae_conv2d_wgrad_simt(const float* x, int in_nchw, int a_silu, c
 
 extern "C" int pdae_colsum(const float* dy, int64_t M, int N, float* out, pdae_stream_t stream) {
   PDAE_REQUIRE(dy && out && N > 0, "colsum: bad args");
+  if (N % 4 == 0 && !((uintptr_t)dy & 15)) {
+    long long rows = (M / 592 + 7) / 8 * 8;      // about four CTAs per SM, eight-row granules
+    rows = rows < 32 ? 32 : (rows > 512 ? 512 : rows);
+    colsum_v4_kernel<<<(unsigned)cdiv(M, rows), 256, 0, (cudaStream_t)stream>>>(dy, M, N, out, (int)rows);
+    PDAE_LAUNCH_CHECK("colsum_v4_kernel");
+    return PDAE_OK;
+  }
   const int rows = 256;
   colsum_kernel<<<cdiv(M, rows), N < 256 ? (N < 32 ? 32 : N) : 256, 0, (cudaStream_t)stream>>>(dy, M, N, out, rows);
   PDAE_LAUNCH_CHECK("colsum_kernel");

@@ -17,7 +17,9 @@
 //   warp 4: TMA producer, warp 5: MMA issuer (warp-uniform loops, elect.sync), warps 0-3: epilogue (one TMEM lane quadrant each).
 // The tap shift is applied to whichever operand is the activation (4-D box at shifted coordinates, out-of-image = zero = padding).
 // `a_is_act` selects which tensor sits on the M side: with dY there (M = cout) the 32 lanes of a warp reduce into 32
-// consecutive dW addresses (coalesced), which is the preferred form whenever Cout % 128 == 0.
+// consecutive dW addresses (coalesced), which is the preferred form whenever Cout % 128 == 0.  When neither channel count is a
+// multiple of 128 (64 -> 64, 192 -> 64) the M side is the activation in 64-channel chunks and the two 64-row halves of the
+// accumulator hold two different TAPS of it ("pair" mode; the odd ninth tap is paired with a discarded duplicate).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -35,6 +37,7 @@ struct WgradArgs {
   int a_is_act;             // 1: M side = activation (shifted per tap), N side = dY; 0: M side = dY, N side = activation
   int Ma, Nb;               // real channel counts on the M / N side (the tensors hold 3x: [hi | lo | hi])
   int mchunks, nchunks, taps, ksize;
+  int pair;                 // 1: 64-channel M chunks, the 128 accumulator rows hold TWO taps (activation on the M side)
   int tw, th, tn, tiles_x, tiles_y, tiles_b, ktiles;
   int B, H, W;
   int stages;
@@ -164,10 +167,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int ty = kt % p.tiles_y;
       const int bt = kt / p.tiles_y;
       const int x0 = tx * p.tw, y0 = ty * p.th, b0 = bt * p.tn;
-      const int dy = p.ksize == 3 ? tap / 3 - 1 : 0, dx = p.ksize == 3 ? tap % 3 - 1 : 0;
-      const int ax = p.a_is_act ? x0 + dx : x0, ay = p.a_is_act ? y0 + dy : y0;      // the activation carries the tap shift
-      const int bx = p.a_is_act ? x0 : x0 + dx, by = p.a_is_act ? y0 : y0 + dy;
-      const int m0 = mc * 128, n0 = nc * BN;
+      // the activation carries the tap shift; in pair mode the two M boxes are two taps of the same 64 channels
+      int tj[2], ax[2], ay[2], am[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        tj[j] = p.pair ? min(2 * tap + j, p.taps - 1) : tap;
+        const int dy = p.ksize == 3 ? tj[j] / 3 - 1 : 0, dx = p.ksize == 3 ? tj[j] % 3 - 1 : 0;
+        ax[j] = p.a_is_act ? x0 + dx : x0;
+        ay[j] = p.a_is_act ? y0 + dy : y0;
+        am[j] = p.pair ? mc * 64 : mc * 128 + j * 64;
+      }
+      const int bdy = p.ksize == 3 ? tap / 3 - 1 : 0, bdx = p.ksize == 3 ? tap % 3 - 1 : 0;
+      const int bx = p.a_is_act ? x0 : x0 + bdx, by = p.a_is_act ? y0 : y0 + bdy;
+      const int n0 = nc * BN;
       mb_wait(s_u32(&bar_empty[s]), ph ^ 1u);
       const uint32_t full = s_u32(&bar_full[s]);
       const uint32_t base = smem0 + (uint32_t)(s * STAGE);
@@ -177,7 +189,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int h = 0; h < 2; ++h) {          // hi block (channel offset 0), lo block (channel offset Ma / Nb)
 #pragma unroll
           for (int j = 0; j < 2; ++j)
-            tma_ld4(base + (uint32_t)(h * A_BYTES + j * WG_BOX), &tmA, full, h * p.Ma + m0 + j * 64, ax, ay, b0);
+            tma_ld4(base + (uint32_t)(h * A_BYTES + j * WG_BOX), &tmA, full, h * p.Ma + am[j], ax[j], ay[j], b0);
 #pragma unroll
           for (int j = 0; j < NBOX_B; ++j)
             tma_ld4(base + (uint32_t)(2 * A_BYTES + h * B_BYTES + j * WG_BOX), &tmB, full, h * p.Nb + n0 + j * 64, bx, by, b0);
@@ -249,7 +261,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int nc = gg % p.nchunks; gg /= p.nchunks;
         const int mc = gg % p.mchunks;
         const int tap = gg / p.mchunks;
-        float* dst = p.dw + (long long)tap * p.stap + (long long)(mc * 128 + m) * p.sm + (long long)(nc * BN) * p.sn;
+        const int tap_w = p.pair ? 2 * tap + (m >> 6) : tap;             // pair mode: rows 64-127 belong to the second tap
+        const int ch_m = p.pair ? mc * 64 + (m & 63) : mc * 128 + m;
+        const bool live = tap_w < p.taps;
+        float* dst = p.dw + (long long)tap_w * p.stap + (long long)ch_m * p.sm + (long long)(nc * BN) * p.sn;
         const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
@@ -257,7 +272,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tmem_ld32(tacc + (uint32_t)(c * 32), v);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(dst + (long long)(c * 32 + j) * p.sn, __uint_as_float(v[j]));
+          if (live) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(dst + (long long)(c * 32 + j) * p.sn, __uint_as_float(v[j]));
+          }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -326,7 +344,6 @@ static int g_num_sms_w = 0;
 extern "C" int pdae_wgrad_tc_supported(int H, int W, int Cin, int Cout, int ksize) {
   if (ksize != 1 && ksize != 3) return 0;
   if (Cin % 64 || Cout % 64) return 0;
-  if (Cin % 128 && Cout % 128) return 0;             // one side must fill the 128 accumulator rows
   const int tw = pow2_tile_w(W, WG_KT), th = pow2_tile_w(H, WG_KT / tw);
   const int tn = WG_KT / (tw * th);
   return (W % tw == 0 && H % th == 0 && tw * th * tn == WG_KT && tn <= 64) ? 1 : 0;
@@ -337,7 +354,8 @@ extern "C" int pdae_wgrad_tc_create(pdae_wgrad_tc_plan** plan_out, const void* a
   PDAE_REQUIRE(plan_out && act3_bf16 && dy3_bf16 && dw, "wgrad_tc_create: null pointer");
   PDAE_REQUIRE(pdae_wgrad_tc_supported(H, W, Cin, Cout, ksize), "wgrad_tc_create: unsupported shape H=%d W=%d Cin=%d Cout=%d k=%d", H, W,
                Cin, Cout, ksize);
-  PDAE_REQUIRE(!(((uintptr_t)act3_bf16 | (uintptr_t)dy3_bf16 | (uintptr_t)dw) & 15), "wgrad_tc_create: pointers must be 16-byte aligned");
+  PDAE_REQUIRE(!(((uintptr_t)act3_bf16 | (uintptr_t)dy3_bf16) & 15) && !((uintptr_t)dw & 3),
+               "wgrad_tc_create: act3 / dy3 must be 16-byte aligned (TMA), dw 4-byte aligned");
   EncodeTiledFnW enc = encode_fnw();
   PDAE_REQUIRE(enc != nullptr, "wgrad_tc_create: cuTensorMapEncodeTiled unavailable (no driver)");
   if (g_num_sms_w == 0) {
@@ -349,6 +367,7 @@ extern "C" int pdae_wgrad_tc_create(pdae_wgrad_tc_plan** plan_out, const void* a
   WgradArgs& a = pl->args;
   a.dw = dw;
   a.a_is_act = (Cout % 128 == 0) ? 0 : 1;        // prefer dY on the M side: coalesced reductions into dW[tap][cin][cout]
+  a.pair = (a.a_is_act && Cin % 128) ? 1 : 0;    // neither side fills 128 accumulator rows: two taps of 64 channels do
   a.Ma = a.a_is_act ? Cin : Cout;
   a.Nb = a.a_is_act ? Cout : Cin;
   a.sm = a.a_is_act ? Cout : 1;
@@ -356,12 +375,12 @@ extern "C" int pdae_wgrad_tc_create(pdae_wgrad_tc_plan** plan_out, const void* a
   a.stap = (long long)Cin * Cout;
   const int BN = (a.Nb % 128 == 0) ? 128 : 64;
   pl->BN = BN;
-  a.mchunks = a.Ma / 128; a.nchunks = a.Nb / BN; a.taps = ksize * ksize; a.ksize = ksize;
+  a.mchunks = a.pair ? a.Ma / 64 : a.Ma / 128; a.nchunks = a.Nb / BN; a.taps = ksize * ksize; a.ksize = ksize;
   a.tw = pow2_tile_w(W, WG_KT); a.th = pow2_tile_w(H, WG_KT / a.tw); a.tn = WG_KT / (a.tw * a.th);
   a.tiles_x = W / a.tw; a.tiles_y = H / a.th; a.tiles_b = (B + a.tn - 1) / a.tn;
   a.ktiles = a.tiles_x * a.tiles_y * a.tiles_b;
   a.B = B; a.H = H; a.W = W;
-  a.items = (long long)a.taps * a.mchunks * a.nchunks * a.ktiles;
+  a.items = (long long)(a.pair ? (a.taps + 1) / 2 : a.taps) * a.mchunks * a.nchunks * a.ktiles;
   const int stage = 2 * (2 * WG_BOX) + 2 * (BN / 64) * WG_BOX;
   int stages = (220 * 1024 - 1024) / stage;
   if (stages > WG_MAX_ST) stages = WG_MAX_ST;

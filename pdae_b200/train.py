@@ -102,6 +102,8 @@ class Backward:
                                     act_dtype=torch.bfloat16)
                 P.call("wgrad_tc", a3, dy3, dw, B, H, W, Cin, Cout, k, flops=2.0 * B * H * W * Cin * Cout * kk)
             else:
+                if os.environ.get("PDAE_TRAIN_DEBUG") == "1":
+                    print(f"[train] CUDA-core wgrad: B{B} {H}x{W} {Cin}->{Cout} k{k} s{stride} nchw{int(in_nchw)} silu{int(a_silu)}")
                 P.call("conv2d_wgrad_simt", self.fx(x), int(in_nchw), int(a_silu), dy, dw, B, H, W, Cin, Cout, k, stride, pad,
                        _STREAM)
             unpack = w_unpack or (lambda t, kk=kk, Cin=Cin, Cout=Cout: t.view(kk, Cin, Cout).permute(2, 1, 0))
@@ -122,6 +124,8 @@ class Backward:
             P.conv(dy3, weight, None, dx, B=B, H=H, W=W, Cin=Cout, Cout=Cin, k=k, wkey=(id(weight), "dgrad"),
                    w_transform=lambda w, Cout=Cout, Cin=Cin, k=k: w.reshape(Cout, Cin, k, k).flip(2, 3).transpose(0, 1).contiguous())
             return dx
+        if os.environ.get("PDAE_TRAIN_DEBUG") == "1":
+            print(f"[train] CUDA-core dgrad: B{B} {H}x{W} {Cin}->{Cout} k{k} s{stride} nchw{int(in_nchw)}")
         wt = P.pack((id(weight), "tco"), [weight], lambda: weight.detach().reshape(Cout, Cin, kk).permute(2, 0, 1).float())
         dx = P.new((B, H, W, Cin), torch.float32, "dx")
         P.call("conv2d_dgrad_simt", dy, wt, dx, B, H, W, Cin, Cout, k, stride, pad, 0, _STREAM)

@@ -4,8 +4,8 @@ all-reduce + fused Adam/EMA step on the celeba64-proxy decoder + encoder.
   python scripts/train_bench.py [--batch 32] [--steps 5]                                   # 1 GPU
   python -m torch.distributed.run --nproc-per-node N ... scripts/train_bench.py --overlap 1   # N GPUs, batch per GPU fixed
 
-Arithmetic: fp32 CUDA-core forward / weight gradients, tensor-core (split-operand, fp32-grade) data gradients -- the
-training path's mode.  --overlap 1: the decoder bucket's NCCL all-reduce is launched from a
+Arithmetic: decoder forward, data gradients (conv_tc2) and weight gradients (wgrad_tc) on the tensor cores in the
+split-operand fp32-grade mode; encoder and the stride-2 / 3-channel convs in fp32 on CUDA cores.  --overlap 1: the decoder bucket's NCCL all-reduce is launched from a
 post-accumulate-grad hook as soon as the ShiftUNet backward has delivered its gradients and runs while the encoder
 backward computes (pdae_b200.utils.dist.OverlappedGradAllReduce); --overlap 0: all-reduce after backward.
 Rank 0 prints one JSON line."""
@@ -92,7 +92,8 @@ if rank == 0:
                       "scaling": "weak", "grad_allreduce": ("overlapped with the encoder backward" if red is not None else
                                                             ("after backward" if world > 1 else "none (1 GPU)")),
                       "trainable_params": n_train, "allreduce_bytes_per_step": 4 * n_train if world > 1 else 0,
-                      "config": "celeba64-proxy encoder + ShiftUNet (shift half trainable), dropout 0.1, fused Adam+EMA; fp32 "
-                                "CUDA-core forward/wgrad, split-operand tensor-core dgrad", "loss": float(loss.detach())}))
+                      "config": "celeba64-proxy encoder + ShiftUNet (shift half trainable), dropout 0.1, fused Adam+EMA; decoder "
+                                "forward, data and weight gradients on the tensor cores (split-operand, fp32-grade); encoder "
+                                "and stride-2 / 3-channel convs on CUDA cores (fp32)", "loss": float(loss.detach())}))
 if world > 1:
     dist.destroy_process_group()

@@ -34,7 +34,7 @@ def timeit(fn, n=10):
 
 st = None
 for (B, H, W, Cin, Cout, k) in [(32, 32, 32, 128, 128, 3), (32, 32, 32, 256, 128, 3), (32, 16, 16, 256, 256, 3), (32, 16, 16, 512, 256, 3),
-                                (32, 8, 8, 512, 512, 3), (32, 8, 8, 1024, 512, 3), (32, 64, 64, 128, 64, 3), (32, 16, 16, 256, 256, 1)]:
+                                (32, 8, 8, 512, 512, 3), (32, 8, 8, 1024, 512, 3), (32, 64, 64, 128, 64, 3), (32, 64, 64, 64, 64, 3), (32, 64, 64, 192, 64, 3), (32, 16, 16, 256, 256, 1)]:
     act = torch.randn(B, H, W, Cin, device=DEV)
     dy = torch.randn(B, H, W, Cout, device=DEV) * 0.05
     dw = torch.zeros(k * k, Cin, Cout, device=DEV)

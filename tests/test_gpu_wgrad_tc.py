@@ -1,5 +1,5 @@
 """wgrad_tc (tensor-core weight gradient of a stride-1 "same" conv, split-operand fp32-grade) through the C-ABI vs the float64
-autograd weight gradient of F.conv2d on the device: both operand placements (dY or the activation on the M side), both N tiles,
+autograd weight gradient of F.conv2d on the device: both operand placements (dY or the activation on the M side), the tap-pair mode, both N tiles,
 1x1 and 3x3, ragged batch tiles, split-K over many CTAs and a single-item CTA range."""
 import ctypes
 
@@ -55,6 +55,9 @@ CASES = [
     (5, 4, 4, 128, 128, 3),       # 4x4 images: 4 images per box, ragged batch tile
     (1, 8, 8, 128, 128, 3),       # one k-tile per (tap, chunk) group: every CTA drains after a single item
     (32, 16, 16, 256, 256, 3),    # long split-K ranges
+    (2, 32, 32, 64, 64, 3),       # neither side fills 128 rows: two taps of 64 channels share the accumulator (pair mode)
+    (2, 16, 16, 192, 64, 3),      # pair mode, three M chunks
+    (3, 16, 16, 64, 64, 1),       # pair mode with a single tap
 ]
 
 
