@@ -254,14 +254,14 @@ __device__ __forceinline__ float dsilu(float u) {
 template <int RS>
 __global__ void __launch_bounds__(256) gn_bwd_sums_kernel(const float* __restrict__ s1, int C1, const float* __restrict__ s2,
                                                           int C2, const float* __restrict__ ab, const float* __restrict__ dy,
-                                                          int silu, int H, int W, float* __restrict__ S) {
+                                                          int silu, int H, int W, float* __restrict__ S, int ppc) {
   extern __shared__ float sh[];  // [2][C]
   const int C = C1 + C2, L = C >> 2;
   const int Lb = L < 256 ? L : 256, R = 256 / Lb;
   const int tid = threadIdx.x, lane = tid % Lb, row = tid / Lb;
   const int b = blockIdx.y;
   const int HW = H * W;
-  const int p0 = blockIdx.x * 256, p1 = min(HW, p0 + 256);
+  const int p0 = blockIdx.x * ppc, p1 = min(HW, p0 + ppc);     // ppc pixels per CTA (host: enough CTAs to fill the SMs)
   for (int i = tid; i < 2 * C; i += 256) sh[i] = 0.f;
   __syncthreads();
   if (row < R) {
@@ -555,6 +555,76 @@ __global__ void mul_mask_cols_kernel(float* __restrict__ a, int ld, const float*
   a[(long long)b * ld + j] *= mask[i] * scale;
 }
 
+
+// dgrad of a wide Linear (H = W = 1, k = 1, Cout = N large): dx[b][e] = sum_n dy[b][n] * w[n][e].  The generic kernel gives one
+// thread a serial reduction over all N; here each CTA owns a 64-row chunk of w (split-K) and adds its partial sums.
+__global__ void __launch_bounds__(256) linear_dgrad_splitk_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                                  float* __restrict__ dx, int B, int N, int E) {
+  __shared__ float ds[32][65];
+  const int n0 = blockIdx.x * 64, e = blockIdx.y * 256 + threadIdx.x;
+  const int nn = min(64, N - n0);
+  for (int b0 = 0; b0 < B; b0 += 32) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * 64; i += 256) {
+      const int bi = i >> 6, j = i & 63;
+      ds[bi][j] = (b0 + bi < B && j < nn) ? dy[(long long)(b0 + bi) * N + n0 + j] : 0.f;
+    }
+    __syncthreads();
+    if (e >= E) continue;
+#pragma unroll 1
+    for (int bb = 0; bb < 32 && b0 + bb < B; bb += 8) {
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int j = 0; j < nn; ++j) {
+        const float wv = w[(long long)(n0 + j) * E + e];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(ds[bb + i][j], wv, acc[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (b0 + bb + i < B) atomicAdd(dx + (long long)(b0 + bb + i) * E + e, acc[i]);
+    }
+  }
+}
+
+// dgrad of a 3x3 stride-1 conv onto <= 4 output channels (the image heads: C -> 3): dx[b,y,x,ci] = sum_{tap,co} dy[b,y+1-ky,
+// x+1-kx,co] * w[tap][co][ci].  One thread = one pixel x 4 input channels; the (<= 36 x Cin) weights sit in shared memory.
+__global__ void __launch_bounds__(256) conv3x3_dgrad_smalln_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                                   float* __restrict__ dx, int B, int H, int W, int Cin, int Cout,
+                                                                   int accumulate) {
+  extern __shared__ float ws[];   // [9][Cout][Cin]
+  for (int i = threadIdx.x; i < 9 * Cout * Cin; i += 256) ws[i] = w[i];
+  __syncthreads();
+  const int L = Cin >> 2;
+  const long long total = (long long)B * H * W * L;
+  for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+    const int cq = (int)(idx % L);
+    long long pix = idx / L;
+    const int x = (int)(pix % W); pix /= W;
+    const int y = (int)(pix % H);
+    const int b = (int)(pix / H);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + 1 - ky;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = x + 1 - kx;
+        if (xx < 0 || xx >= W) continue;
+        const float* g = dy + (((long long)b * H + yy) * W + xx) * Cout;
+        for (int co = 0; co < Cout; ++co) {
+          const float gv = g[co];
+          const float4 wv = *reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * Cout + co) * Cin + 4 * cq);
+          acc.x = fmaf(gv, wv.x, acc.x); acc.y = fmaf(gv, wv.y, acc.y); acc.z = fmaf(gv, wv.z, acc.z); acc.w = fmaf(gv, wv.w, acc.w);
+        }
+      }
+    }
+    float4* o = reinterpret_cast<float4*>(dx + ((((long long)b * H + y) * W + x) * Cin + 4 * cq));
+    if (accumulate) { const float4 t = *o; acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w; }
+    *o = acc;
+  }
+}
+
 }  // namespace pdae
 
 using namespace pdae;
@@ -562,6 +632,22 @@ using namespace pdae;
 extern "C" int pdae_conv2d_dgrad_simt(const float* dy, const float* w_tco, float* dx, int B, int H, int W, int Cin, int Cout,
                                       int ksize, int stride, int pad, int accumulate, pdae_stream_t stream) {
   PDAE_REQUIRE(dy && w_tco && dx, "conv2d_dgrad: null pointer");
+  if (H == 1 && W == 1 && ksize == 1 && stride == 1 && pad == 0 && Cout >= 1024 && !accumulate) {   // wide Linear: split-K
+    PDAE_CUDA(cudaMemsetAsync(dx, 0, (size_t)B * Cin * sizeof(float), (cudaStream_t)stream));
+    linear_dgrad_splitk_kernel<<<dim3(cdiv(Cout, 64), cdiv(Cin, 256)), 256, 0, (cudaStream_t)stream>>>(dy, w_tco, dx, B, Cout, Cin);
+    PDAE_LAUNCH_CHECK("linear_dgrad_splitk_kernel");
+    return PDAE_OK;
+  }
+  if (ksize == 3 && stride == 1 && pad == 1 && Cout <= 4 && Cin % 4 == 0 && (size_t)9 * Cout * Cin * 4 <= 48 * 1024 &&
+      !((uintptr_t)dx & 15)) {                                                                       // image heads
+    const long long items = (long long)B * H * W * (Cin / 4);
+    long long gx = (items + 255) / 256;
+    if (gx > 148 * 16) gx = 148 * 16;
+    conv3x3_dgrad_smalln_kernel<<<(unsigned)gx, 256, (size_t)9 * Cout * Cin * 4, (cudaStream_t)stream>>>(dy, w_tco, dx, B, H, W, Cin,
+                                                                                                       Cout, accumulate);
+    PDAE_LAUNCH_CHECK("conv3x3_dgrad_smalln_kernel");
+    return PDAE_OK;
+  }
   DgradArgs p;
   p.dy = dy; p.w = w_tco; p.dx = dx; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.ksize = ksize; p.stride = stride; p.pad = pad; p.accumulate = accumulate;
@@ -618,11 +704,13 @@ extern "C" int pdae_gn_bwd_sums(const float* src1, int C1, const float* src2, in
   PDAE_REQUIRE(C1 % 4 == 0 && C2 % 4 == 0 && C % 32 == 0 && (size_t)2 * C * 4 <= 48 * 1024, "gn_bwd_sums: bad channels");
   cudaStream_t s = (cudaStream_t)stream;
   PDAE_CUDA(cudaMemsetAsync(S, 0, (size_t)B * C * 2 * sizeof(float), s));
-  dim3 grid(cdiv((long long)H * W, 256), B);
+  int ppc = 256;                                   // low-resolution layers: fewer pixels per CTA so that >= ~4 CTAs/SM exist
+  while (ppc > 8 && (long long)B * cdiv((long long)H * W, ppc) < 592) ppc >>= 1;
+  dim3 grid(cdiv((long long)H * W, ppc), B);
   const size_t sm = 2 * C * sizeof(float);
-  if (resample == PDAE_RESAMPLE_NONE) gn_bwd_sums_kernel<PDAE_RESAMPLE_NONE><<<grid, 256, sm, s>>>(src1, C1, src2, C2, ab, dy, silu, H, W, S);
-  else if (resample == PDAE_RESAMPLE_UP2) gn_bwd_sums_kernel<PDAE_RESAMPLE_UP2><<<grid, 256, sm, s>>>(src1, C1, src2, C2, ab, dy, silu, H, W, S);
-  else gn_bwd_sums_kernel<PDAE_RESAMPLE_DOWN2><<<grid, 256, sm, s>>>(src1, C1, src2, C2, ab, dy, silu, H, W, S);
+  if (resample == PDAE_RESAMPLE_NONE) gn_bwd_sums_kernel<PDAE_RESAMPLE_NONE><<<grid, 256, sm, s>>>(src1, C1, src2, C2, ab, dy, silu, H, W, S, ppc);
+  else if (resample == PDAE_RESAMPLE_UP2) gn_bwd_sums_kernel<PDAE_RESAMPLE_UP2><<<grid, 256, sm, s>>>(src1, C1, src2, C2, ab, dy, silu, H, W, S, ppc);
+  else gn_bwd_sums_kernel<PDAE_RESAMPLE_DOWN2><<<grid, 256, sm, s>>>(src1, C1, src2, C2, ab, dy, silu, H, W, S, ppc);
   PDAE_LAUNCH_CHECK("gn_bwd_sums_kernel");
   return PDAE_OK;
 }

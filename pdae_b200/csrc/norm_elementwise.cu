@@ -20,10 +20,16 @@ void set_error(const char* fmt, ...) {
 // stats: grid (pixel chunks, B). Thread = (channel quad, pixel row) ; per-channel partial sums in
 // registers -> shared per-channel fp32 -> per-group fp64 atomics.
 constexpr int STATS_PIX = 256;
+// pixels per CTA of the statistics kernels: fewer for low-resolution layers so that >= ~4 CTAs per SM exist
+static inline int stats_ppc(int B, int HW) {
+  int ppc = STATS_PIX;
+  while (ppc > 8 && (long long)B * ((HW + ppc - 1) / ppc) < 592) ppc >>= 1;
+  return ppc;
+}
 
 __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ s1, int C1,
                                                        const float* __restrict__ s2, int C2, int HW,
-                                                       double* __restrict__ sums) {
+                                                       double* __restrict__ sums, int ppc) {
   extern __shared__ float sh[];  // [2][C]
   const int C = C1 + C2, L = C >> 2;
   const int Lb = L < 256 ? L : 256;
@@ -31,8 +37,8 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
   const int tid = threadIdx.x;
   const int lane = tid % Lb, row = tid / Lb;
   const int b = blockIdx.y;
-  const int p0 = blockIdx.x * STATS_PIX;
-  const int p1 = min(HW, p0 + STATS_PIX);
+  const int p0 = blockIdx.x * ppc;
+  const int p1 = min(HW, p0 + ppc);
   for (int i = tid; i < 2 * C; i += 256) sh[i] = 0.f;
   __syncthreads();
   if (row < R) {
@@ -63,7 +69,8 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
 }
 
 // per-channel (sum, sum^2) fp32 accumulators [B][C][2] -- the form the tensor-core conv epilogue produces
-__global__ void __launch_bounds__(256) ch_stats_kernel(const float* __restrict__ src, int C, int HW, float* __restrict__ chs) {
+__global__ void __launch_bounds__(256) ch_stats_kernel(const float* __restrict__ src, int C, int HW, float* __restrict__ chs,
+                                                       int ppc) {
   extern __shared__ float sh[];  // [2][C]
   const int L = C >> 2;
   const int Lb = L < 256 ? L : 256;
@@ -71,8 +78,8 @@ __global__ void __launch_bounds__(256) ch_stats_kernel(const float* __restrict__
   const int tid = threadIdx.x;
   const int lane = tid % Lb, row = tid / Lb;
   const int b = blockIdx.y;
-  const int p0 = blockIdx.x * STATS_PIX;
-  const int p1 = min(HW, p0 + STATS_PIX);
+  const int p0 = blockIdx.x * ppc;
+  const int p1 = min(HW, p0 + ppc);
   for (int i = tid; i < 2 * C; i += 256) sh[i] = 0.f;
   __syncthreads();
   if (row < R) {
@@ -686,8 +693,9 @@ extern "C" int pdae_gn_stats(const float* src1, int C1, const float* src2, int C
   PDAE_REQUIRE((size_t)2 * C * sizeof(float) <= 48 * 1024, "gn_stats: C too large");
   cudaStream_t s = (cudaStream_t)stream;
   PDAE_CUDA(cudaMemsetAsync(sums, 0, (size_t)B * 32 * 2 * sizeof(double), s));
-  dim3 grid(cdiv(HW, STATS_PIX), B);
-  gn_stats_kernel<<<grid, 256, 2 * C * sizeof(float), s>>>(src1, C1, src2, C2, HW, sums);
+  const int ppc = stats_ppc(B, HW);
+  dim3 grid(cdiv(HW, ppc), B);
+  gn_stats_kernel<<<grid, 256, 2 * C * sizeof(float), s>>>(src1, C1, src2, C2, HW, sums, ppc);
   PDAE_LAUNCH_CHECK("gn_stats_kernel");
   return PDAE_OK;
 }
@@ -714,8 +722,9 @@ extern "C" int pdae_ch_stats(const float* src, int B, int HW, int C, float* chs,
   PDAE_REQUIRE(C % 4 == 0 && C > 0 && (size_t)2 * C * sizeof(float) <= 48 * 1024, "ch_stats: C=%d unsupported", C);
   cudaStream_t s = (cudaStream_t)stream;
   PDAE_CUDA(cudaMemsetAsync(chs, 0, (size_t)B * C * 2 * sizeof(float), s));
-  dim3 grid(cdiv(HW, STATS_PIX), B);
-  ch_stats_kernel<<<grid, 256, 2 * C * sizeof(float), s>>>(src, C, HW, chs);
+  const int ppc = stats_ppc(B, HW);
+  dim3 grid(cdiv(HW, ppc), B);
+  ch_stats_kernel<<<grid, 256, 2 * C * sizeof(float), s>>>(src, C, HW, chs, ppc);
   PDAE_LAUNCH_CHECK("ch_stats_kernel");
   return PDAE_OK;
 }

@@ -47,7 +47,7 @@ def get_default_precision() -> str:
 
 class Buf:
     """A device buffer known to a plan: either plan-owned (arena) or fixed (parameter / caller tensor)."""
-    __slots__ = ("shape", "dtype", "tensor", "first", "last", "fixed", "keep", "name", "_block", "split3")
+    __slots__ = ("shape", "dtype", "tensor", "first", "last", "fixed", "keep", "name", "_block", "split3", "split3_copy")
 
     def __init__(self, shape, dtype, tensor=None, name=""):
         self.shape = tuple(int(s) for s in shape)
@@ -59,6 +59,7 @@ class Buf:
         self.keep = False
         self.name = name
         self.split3 = False   # "bf16x3" activation: last dim holds three bf16 channel blocks [hi | lo | hi]
+        self.split3_copy = None   # training forward: the [hi | lo | hi] copy of this fp32 activation (Plan.conv, train_tc)
 
     @property
     def nbytes(self) -> int:
@@ -561,6 +562,7 @@ class Plan:
                 and skip is None and w_transform is None and pad == k // 2 and self._tc_shape_ok(Cin, Cout, k, stride, H, W)):
             x3b = self.new((B, H, W, 3 * Cin), torch.bfloat16, "train_split3")
             x3b.split3 = True
+            x.split3_copy = x3b      # the backward's tensor-core weight gradient reads the same split activation
             self.call("gn_apply_split3", x, Cin, None, 0, None, 0, RESAMPLE_NONE, B, H, W, x3b, None, PDAE_F32, _STREAM)
             wp = self.pack((wkey or id(weight), "tc_x3"), [weight],
                            lambda Cin=Cin: split3_weights(weight.detach().reshape(Cout, Cin, k * k)))

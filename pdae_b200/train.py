@@ -96,8 +96,12 @@ class Backward:
             dw = P.new_zeroed(kk * Cin * Cout)
             if self.tc_wgrad and same and not a_silu and P.L.pdae_wgrad_tc_supported(H, W, Cin, Cout, k):
                 # weight gradient on the tensor cores (wgrad_tc.cu): both operands split [hi | lo | hi], fp32-grade products
-                a3, _ = P.gn_apply(self.fx(x), Cin, None, 0, None, silu=False, resample=RESAMPLE_NONE, B=B, H=H, W=W,
-                                   act_dtype=torch.bfloat16)
+                a3 = getattr(x, "split3_copy", None)       # left by the tensor-core training forward (Plan.conv, train_tc)
+                if a3 is not None and tuple(a3.shape) == (B, H, W, 3 * Cin):
+                    a3 = self.fx(a3)
+                else:
+                    a3, _ = P.gn_apply(self.fx(x), Cin, None, 0, None, silu=False, resample=RESAMPLE_NONE, B=B, H=H, W=W,
+                                       act_dtype=torch.bfloat16)
                 dy3, _ = P.gn_apply(dy, Cout, None, 0, None, silu=False, resample=RESAMPLE_NONE, B=B, H=H, W=W,
                                     act_dtype=torch.bfloat16)
                 P.call("wgrad_tc", a3, dy3, dw, B, H, W, Cin, Cout, k, flops=2.0 * B * H * W * Cin * Cout * kk)
