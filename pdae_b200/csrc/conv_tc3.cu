@@ -193,7 +193,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 }  // namespace t3
 
-template <int BN, bool X3>
+template <int BN, bool X3, bool MG = true>
 __global__ void __launch_bounds__(T3_THREADS, 1)
 conv_tc3_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2,
                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
@@ -207,13 +207,14 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__
   __shared__ uint32_t tmem_slot;
   __shared__ float st_acc[2][2][BN];   // [epilogue group][sum | sum^2][channel] of the group's current (image, n-tile)
 
-  // Split mode with 64 output channels: W_hi and W_lo of a (tap, k-block) arrive as ONE 128-row tile [W_hi | W_lo]; the issuer
-  // runs a_hi x [W_hi | W_lo] as a single N = 128 MMA (accumulator columns 0-63: hi*hi, 64-127: hi*lo) and a_lo x W_hi as an
-  // N = 64 MMA into columns 0-63; the epilogue adds the two halves.  8 instead of 12 MMAs per tap and 56 instead of 72 KB of
-  // operand reads -- the 64-wide layers are bound by the shared-memory port (the A tile is re-read per MMA), not the tensor pipe.
-  constexpr bool MRG = X3 && BN == 64;
-  constexpr int ACC_COLS = MRG ? 128 : BN;
-  constexpr int B_BYTES = (MRG ? 128 : BN) * T3_BK * 2;
+  // Split mode: W_hi and W_lo of a (tap, k-block) arrive as ONE 2*BN-row tile [W_hi | W_lo]; the issuer runs
+  // a_hi x [W_hi | W_lo] as a single N = 2*BN MMA (accumulator columns 0..BN-1: hi*hi, BN..2BN-1: hi*lo) and a_lo x W_hi as an
+  // N = BN MMA into columns 0..BN-1; the epilogue adds the two halves.  8 instead of 12 MMAs per tap and a third less operand
+  // traffic -- the 64/128-wide layers are bound by the shared-memory port (the A tile is re-read per MMA), not the tensor pipe.
+  // (MG = false keeps the unmerged BN = 128 schedule for A/B measurements, PDAE_TC3_MRG128=0.)
+  constexpr bool MRG = X3 && (BN == 64 || MG);
+  constexpr int ACC_COLS = MRG ? 2 * BN : BN;
+  constexpr int B_BYTES = (MRG ? 2 * BN : BN) * T3_BK * 2;
   constexpr int A_STAGE = (X3 ? 2 : 1) * T3_HALO_BYTES;
   constexpr int TMEM_COLS = 2 * ACC_COLS;
   constexpr int NMAT = (X3 && !MRG) ? 2 : 1;   // weight tiles per (tap, k-block): W | (W_hi, W_lo) | merged [W_hi | W_lo]
@@ -327,7 +328,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__
           const uint32_t bar_be = s_u32(&bar_b_empty[sb]);
           if (MRG) {
             constexpr uint32_t IDESC128 =
-                (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(T3_BM >> 4) << 24);
+                (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(T3_BM >> 4) << 24);
             if (elect_one()) {
               const uint64_t ad_lo = sw128_desc(a_hi + (uint32_t)T3_HALO_BYTES + off, A_SBO);
               umma(tmem_d, ad_hi, bd, IDESC128, first);                                   // a_hi x [W_hi | W_lo]
@@ -556,7 +557,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(v[j]);
           if (MRG) {   // + the a_hi x W_lo half of the merged accumulator (split mode stores fp32: CW = 32)
-            tmem_ld32(tmem_acc + (uint32_t)(64 + c * CW), v);
+            tmem_ld32(tmem_acc + (uint32_t)(BN + c * CW), v);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
             for (int j = 0; j < 32; ++j) val[j] += __uint_as_float(v[j]);
@@ -717,16 +718,16 @@ static EncodeTiledFn3 encode_fn3() {
   return fn;
 }
 
-template <int BN, bool X3>
+template <int BN, bool X3, bool MG = true>
 static cudaError_t launch_tc3(const CUtensorMap& b, const CUtensorMap& b2, const CUtensorMap& o, const CUtensorMap& r,
                               const CUtensorMap* sk, const ConvTc3Args& args, int grid, size_t smem, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<BN, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<BN, X3, MG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  conv_tc3_kernel<BN, X3><<<grid, T3_THREADS, smem, s>>>(b, b2, o, r, sk[0], sk[1], sk[2], sk[3], args);
+  conv_tc3_kernel<BN, X3, MG><<<grid, T3_THREADS, smem, s>>>(b, b2, o, r, sk[0], sk[1], sk[2], sk[3], args);
   return cudaPeekAtLastError();
 }
 
@@ -739,7 +740,7 @@ struct pdae_conv_tc3_plan {
   CUtensorMap tmB, tmB2, tmO, tmR;
   CUtensorMap tmS[4];   // raw halo sources: conv input (C1 | C2), skip-conv input (S1 | S2)
   ConvTc3Args args;
-  int BN, x3, grid;
+  int BN, x3, grid, mrg;
   size_t smem;
 };
 
@@ -799,8 +800,10 @@ extern "C" int pdae_conv_tc3_create(pdae_conv_tc3_plan** plan_out, const void* s
   pl->BN = BN;
   a.tiles_total = a.tiles_m * (Cout / BN);
   pl->grid = a.tiles_total < g_num_sms3 ? a.tiles_total : g_num_sms3;
-  const bool mrg = x3 && BN == 64;   // merged [W_hi | W_lo] weight tiles (see the kernel)
-  const int a_stage = (x3 ? 2 : 1) * T3_HALO_BYTES, b_bytes = (mrg ? 128 : BN) * T3_BK * 2;
+  const char* em = getenv("PDAE_TC3_MRG128");
+  const bool mrg = x3 && (BN == 64 || !(em && atoi(em) == 0));   // merged [W_hi | W_lo] weight tiles (see the kernel)
+  pl->mrg = mrg ? 1 : 0;
+  const int a_stage = (x3 ? 2 : 1) * T3_HALO_BYTES, b_bytes = (mrg ? 2 * BN : BN) * T3_BK * 2;
   const int staging = ((a.has_res && !x3) ? 4 : 2) * T3_STG_BYTES;   // split mode reads its residual from global memory
   const int budget = 220 * 1024 - 1024 - staging;
   // the transform is software-pipelined, so two halo stages suffice; the weight tiles need depth (bytes in flight from L2)
@@ -906,7 +909,8 @@ extern "C" int pdae_conv_tc3_run(const pdae_conv_tc3_plan* pl, pdae_stream_t str
   cudaError_t e;
   if (pl->x3) {
     if (pl->BN == 64) e = launch_tc3<64, true>(pl->tmB, pl->tmB2, pl->tmO, pl->tmR, pl->tmS, pl->args, pl->grid, pl->smem, s);
-    else e = launch_tc3<128, true>(pl->tmB, pl->tmB2, pl->tmO, pl->tmR, pl->tmS, pl->args, pl->grid, pl->smem, s);
+    else if (pl->mrg) e = launch_tc3<128, true, true>(pl->tmB, pl->tmB2, pl->tmO, pl->tmR, pl->tmS, pl->args, pl->grid, pl->smem, s);
+    else e = launch_tc3<128, true, false>(pl->tmB, pl->tmB2, pl->tmO, pl->tmR, pl->tmS, pl->args, pl->grid, pl->smem, s);
   } else {
     switch (pl->BN) {
       case 64: e = launch_tc3<64, false>(pl->tmB, pl->tmB2, pl->tmO, pl->tmR, pl->tmS, pl->args, pl->grid, pl->smem, s); break;

@@ -36,3 +36,38 @@ for name, plan in (("decoder frozen fwd", tr.frozen), ("decoder trainable fwd", 
     print(f"{name}: {tot:.2f} ms")
     for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:8]:
         print(f"    {k:22s} {v['ms']:8.3f} ms  n={v['launches']:4d}")
+
+# ---- segment timeline of whole steps (CUDA events around the Python-level phases; host time of the same calls) ----
+import copy
+import time
+
+from pdae_b200.optim import FusedAdamEMA
+
+ema_dec, ema_enc = copy.deepcopy(dec).requires_grad_(False), copy.deepcopy(enc).requires_grad_(False)
+groups = [list(enc.parameters()), list(dec.label_emb.parameters()), list(dec.shift_middle_block.parameters()),
+          list(dec.shift_output_blocks.parameters()), list(dec.shift_out.parameters())]
+opt = FusedAdamEMA([{"params": g} for g in groups], lr=1e-4, ema_decay=0.9999)
+opt.attach_ema(enc, ema_enc)
+opt.attach_ema(dec, ema_dec)
+seg = {"forward+loss": [0.0, 0.0], "backward": [0.0, 0.0], "optimizer+EMA": [0.0, 0.0]}
+N = 5
+for it in range(N + 2):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    torch.cuda.synchronize()
+    h = [time.perf_counter()]
+    ev[0].record()
+    loss = gd.representation_learning_train_one_batch(enc, dec, x0)["prediction_loss"]
+    ev[1].record(); h.append(time.perf_counter())
+    loss.backward()
+    ev[2].record(); h.append(time.perf_counter())
+    opt.step()
+    opt.zero_grad(set_to_none=True)
+    ev[3].record(); h.append(time.perf_counter())
+    torch.cuda.synchronize()
+    if it >= 2:
+        for i, k in enumerate(seg):
+            seg[k][0] += ev[i].elapsed_time(ev[i + 1]) / N
+            seg[k][1] += (h[i + 1] - h[i]) * 1e3 / N
+print("whole-step segments (device ms between events | host ms spent issuing):")
+for k, (d, hh) in seg.items():
+    print(f"    {k:16s} {d:7.2f} | {hh:7.2f}")
