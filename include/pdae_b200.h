@@ -301,6 +301,21 @@ typedef struct pdae_adam_tensor {
 int pdae_adam_ema_step(const pdae_adam_tensor* table, const int32_t* block_map, int n_blocks, int chunk, float lr,
                        float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
                        float ema_decay, pdae_stream_t stream);
+/* Hand the weight gradients of a backward plan to autograd in the parameters' own layouts (what loss.backward() leaves in
+ * p.grad, trainer/train_representation_learning.py:112): item i copies a <= 4-D strided fp32 view (element strides; e.g. the
+ * packed conv accumulator [k*k][Cin][Cout] viewed as [Cout][Cin][k*k]) to g[dst_off ...] contiguously, or adds to it (`add`,
+ * a parameter that received a second contribution -- such items must be in a LATER launch than the first write).
+ * `items`, `block_map` ((item, chunk) int32 pairs, `chunk` elements each) are DEVICE arrays.                              */
+typedef struct pdae_unpack_item {
+  const float* src;
+  int64_t dst_off;
+  int32_t shape[4];
+  int64_t stride[4];
+  int32_t add;
+  int32_t pad_;
+} pdae_unpack_item;
+int pdae_unpack_grads(const pdae_unpack_item* items, const int32_t* block_map, int n_blocks, int chunk, float* g,
+                      pdae_stream_t stream);
 /* Wire formats.  fp32 NCHW in [-1,1] -> uint8 NHWC with the reference's exact op sequence
  * `x.mul(0.5).add(0.5).mul(255).add(0.5).clamp(0,255).permute(0,2,3,1).to(uint8)`
  * (trainer/train_representation_learning.py:173-174, sampler/autoencoding_example.py:53 ...): bit-exact.

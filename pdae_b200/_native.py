@@ -124,6 +124,7 @@ _SIGS = {
                                    c_int, c_int, _P, _P, c_int, _P]),
     "pdae_adam_ema_step": (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_int64, c_float,
                                    c_float, _P]),
+    "pdae_unpack_grads": (c_int, [_P, _P, c_int, c_int, _P, _P]),
     "pdae_images_to_u8_nhwc": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "pdae_u8_nhwc_to_images": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "pdae_mse_per_image": (c_int, [_P, _P, c_int, c_int64, _P, _P, _P]),

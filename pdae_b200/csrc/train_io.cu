@@ -178,6 +178,28 @@ __global__ void __launch_bounds__(256) ssim_kernel(const float* __restrict__ img
   }
 }
 
+
+// Gather every weight-gradient accumulator of a backward plan (packed layouts, e.g. conv [k*k][Cin][Cout]) into ONE flat buffer
+// in the parameters' own layouts: item i copies a <=4-D strided view to a contiguous run of `g` (dst linear order = row-major
+// order of the view).  One launch replaces the per-parameter permute / contiguous / clone chain.
+__global__ void __launch_bounds__(256) unpack_grads_kernel(const pdae_unpack_item* __restrict__ items, const int2* __restrict__ blocks,
+                                                           int chunk, float* __restrict__ g) {
+  const int2 bc = blocks[blockIdx.x];
+  const pdae_unpack_item it = items[bc.x];
+  const long long numel = (long long)it.shape[0] * it.shape[1] * it.shape[2] * it.shape[3];
+  const long long lo = (long long)bc.y * chunk, hi = lo + chunk < numel ? lo + chunk : numel;
+  float* dst = g + it.dst_off;
+  for (long long i = lo + threadIdx.x; i < hi; i += 256) {
+    long long r = i;
+    const int i3 = (int)(r % it.shape[3]); r /= it.shape[3];
+    const int i2 = (int)(r % it.shape[2]); r /= it.shape[2];
+    const int i1 = (int)(r % it.shape[1]);
+    const int i0 = (int)(r / it.shape[1]);
+    const float v = it.src[i0 * it.stride[0] + i1 * it.stride[1] + i2 * it.stride[2] + i3 * it.stride[3]];
+    dst[i] = it.add ? dst[i] + v : v;
+  }
+}
+
 }  // namespace pdae
 
 using namespace pdae;
@@ -196,6 +218,14 @@ extern "C" int pdae_adam_ema_step(const pdae_adam_tensor* table, const int32_t* 
                                                               beta1, beta2, eps, weight_decay, inv_sqrt_bc2, grad_scale,
                                                               ema_decay);
   PDAE_LAUNCH_CHECK("adam_ema_kernel");
+  return PDAE_OK;
+}
+
+extern "C" int pdae_unpack_grads(const pdae_unpack_item* items, const int32_t* block_map, int n_blocks, int chunk, float* g,
+                                 pdae_stream_t stream) {
+  PDAE_REQUIRE(items && block_map && g && n_blocks > 0 && chunk > 0, "unpack_grads: bad arguments");
+  unpack_grads_kernel<<<n_blocks, 256, 0, (cudaStream_t)stream>>>(items, reinterpret_cast<const int2*>(block_map), chunk, g);
+  PDAE_LAUNCH_CHECK("unpack_grads_kernel");
   return PDAE_OK;
 }
 

@@ -18,31 +18,80 @@ import math
 import os
 from typing import Callable, Dict, List, Optional, Tuple
 
+import numpy as np
 import torch
 import torch.nn as nn
 
+from . import _native
 from .engine import Buf, BufView, Plan, RESAMPLE_NONE, _STREAM
 from .model.module import AttentionBlock, Src
 
 F32 = ctypes.c_float
 
 
+_UNPACK_ITEM = np.dtype([("src", "<u8"), ("dst_off", "<i8"), ("shape", "<i4", (4,)), ("stride", "<i8", (4,)), ("add", "<i4"),
+                         ("pad", "<i4")])       # = pdae_unpack_item (include/pdae_b200.h)
+_UNPACK_CHUNK = 4096
+
+
 class GradSink:
-    """parameter -> (zero-initialised accumulation view in the backward plan, un-packing function)."""
+    """parameter -> (zero-initialised accumulation view in the backward plan, un-packing function).
+
+    `collect()` hands every gradient to autograd in the parameter's own layout.  The un-packing functions are pure VIEWS of the
+    backward plan's accumulator arena (permute / slice / transpose), so their (shape, strides, offset) are recorded once and
+    one `pdae_unpack_grads` launch gathers all of them into a fresh flat buffer; the returned gradients are views of that
+    buffer (autograd adopts them as `.grad` without a copy)."""
 
     def __init__(self):
         self.items: List[Tuple[torch.Tensor, BufView, Callable[[torch.Tensor], torch.Tensor], int]] = []
+        self._launches = None     # [(items table, block map, n_blocks)] per contribution rank
+        self._slots: Dict[int, Tuple[torch.Tensor, int, int]] = {}
+        self._total = 0
 
     def add(self, param: torch.Tensor, view: BufView, nelems: int, unpack: Callable[[torch.Tensor], torch.Tensor]) -> None:
         self.items.append((param, view, unpack, nelems))
 
-    def collect(self) -> Dict[int, torch.Tensor]:
-        out: Dict[int, torch.Tensor] = {}
+    def _build(self) -> None:
+        rank: Dict[int, int] = {}
+        rows: Dict[int, list] = {}
+        dev = None
         for param, view, unpack, n in self.items:
-            flat = view.buf.tensor[view.off: view.off + n]
-            g = unpack(flat).reshape(param.shape).contiguous()
-            out[id(param)] = out[id(param)] + g if id(param) in out else g.clone()
-        return out
+            arena = view.buf.tensor
+            dev = arena.device
+            v = unpack(arena[view.off: view.off + n])
+            if v.untyped_storage().data_ptr() != arena.untyped_storage().data_ptr() or v.numel() != param.numel() or v.dim() > 4:
+                raise _native.NativeError("pdae_b200: a gradient un-packing function must be a <=4-D view of the accumulator")
+            if id(param) not in self._slots:
+                self._slots[id(param)] = (param, self._total, param.numel())
+                self._total += (param.numel() + 3) // 4 * 4          # 16-byte aligned slots
+            r = rank[id(param)] = rank.get(id(param), -1) + 1
+            shape = [1] * (4 - v.dim()) + list(v.shape)
+            stride = [0] * (4 - v.dim()) + list(v.stride())
+            rows.setdefault(r, []).append((v.data_ptr(), self._slots[id(param)][1], shape, stride, 1 if r else 0, 0))
+        self._launches = []
+        for r in sorted(rows):
+            tab = np.array([tuple(x) for x in rows[r]], dtype=_UNPACK_ITEM)
+            pairs = [(i, c) for i, x in enumerate(rows[r])
+                     for c in range((int(np.prod(x[2])) + _UNPACK_CHUNK - 1) // _UNPACK_CHUNK)]
+            t_dev = torch.from_numpy(tab.view(np.uint8).reshape(-1)).to(dev)
+            b_dev = torch.tensor(pairs, dtype=torch.int32, device=dev).contiguous()
+            self._launches.append((t_dev, b_dev, len(pairs)))
+        self._dev = dev
+
+    def collect(self) -> Dict[int, torch.Tensor]:
+        if not self.items:
+            return {}
+        if self._launches is None:
+            self._build()
+        # a fresh buffer per backward (the caching allocator makes this free): gradients handed out earlier stay valid for as
+        # long as the caller holds them, exactly like autograd's own
+        flat = torch.empty(self._total, dtype=torch.float32, device=self._dev)
+        L = _native.lib()
+        st = ctypes.c_void_p(torch.cuda.current_stream(self._dev).cuda_stream)
+        for t_dev, b_dev, nb in self._launches:
+            _native.check(L.pdae_unpack_grads(t_dev.data_ptr(), b_dev.data_ptr(), nb, _UNPACK_CHUNK, flat.data_ptr(), st),
+                          "pdae_unpack_grads")
+        return {pid: flat[off: off + n].view(p.shape) for pid, (p, off, n) in self._slots.items()}
 
 
 def draw_dropout_masks(plan: Plan) -> None:
@@ -655,7 +704,7 @@ class EncoderTrainer(_Generation):
                 dw = BP.new_zeroed(K * L)
                 BP.call("conv2d_wgrad_simt", bw.fx(sv["act"]), 0, 0, d, dw, Bc, 1, 1, K, L, 1, 1, 0, _STREAM)
                 # packed [HW*C][L] (NHWC flatten) -> reference layout [L][C*HW] (NCHW flatten)
-                self.sink.add(m.weight, dw, K * L, lambda t, HW=HW, Cc=Cc: t.view(HW, Cc, L).permute(2, 1, 0).reshape(L, Cc * HW))
+                self.sink.add(m.weight, dw, K * L, lambda t, HW=HW, Cc=Cc: t.view(HW, Cc, L).permute(2, 1, 0))
                 db = BP.new_zeroed(L)
                 BP.call("colsum", d, ctypes.c_int64(Bc), L, db, _STREAM)
                 self.sink.add(m.bias, db, L, lambda t: t)
