@@ -611,8 +611,9 @@ def latent_sample_extra(gd, dec, precision, world, rank, dev, timed, B, size):
 
 def training_step_extra(world, rank, dev, timed):
     """BASELINE.json config 5: the PDAE training step (representation_learning_train_one_batch + backward + gradient all-reduce
-    overlapped with the encoder backward + fused Adam/EMA), celeba64-proxy, 32 images per GPU.  fp32 CUDA-core forward / weight
-    gradients, split-operand tensor-core data gradients -- the training path is NOT on the tensor cores yet."""
+    overlapped with the encoder backward + fused Adam/EMA), celeba64-proxy, 32 images per GPU.  Decoder forward, data gradients and
+    weight gradients run on the tensor cores in the split-operand fp32-grade mode (conv_tc2 / conv_tc3 / wgrad_tc); the encoder
+    and the stride-2 / 3-channel convs are fp32 CUDA-core kernels."""
     try:
         import copy
         from pdae_b200.diffusion.gaussian_diffusion import GaussianDiffusion
@@ -651,7 +652,8 @@ def training_step_extra(world, rank, dev, timed):
         out = {"workload": "celeba64-proxy encoder + ShiftUNet (shift half trainable), dropout 0.1, fused Adam+EMA", "batch_per_gpu": Bt,
                "n_gpus": world, "ms_per_step": round(ms, 2), "images_per_sec": round(world * Bt / ms * 1e3, 2), "steps": k, "warmup": 3,
                "scaling": "weak", "allreduce_bytes_per_step": 4 * n_train if world > 1 else 0,
-               "arithmetic": "fp32 CUDA-core forward + weight gradients, split-operand tensor-core data gradients"}
+               "arithmetic": "decoder forward, data and weight gradients on the tensor cores (split-operand, fp32-grade); encoder "
+                             "and stride-2 / 3-channel convs fp32 on CUDA cores"}
         del dec, enc, ema_dec, ema_enc, opt
         torch.cuda.empty_cache()
         return out
