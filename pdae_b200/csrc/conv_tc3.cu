@@ -214,7 +214,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__
   // traffic -- the 64/128-wide layers are bound by the shared-memory port (the A tile is re-read per MMA), not the tensor pipe.
   // (MG = false keeps the unmerged BN = 128 schedule for A/B measurements, PDAE_TC3_MRG128=0.)
   constexpr bool MRG = X3 && (BN == 64 || MG);
-  // DU: TWO MMA-issuer warps take alternate taps and accumulate into separate TMEM blocks (the epilogue adds them).  One
+  // DU (experimental, opt-in -- see pdae_conv_tc3_create): TWO MMA-issuer warps take alternate taps and accumulate into separate TMEM blocks (the epilogue adds them).  One
   // issuer spends ~100 cycles of uniform-datapath work per MMA (descriptor arithmetic, barrier polls, commit) -- more than a
   // 64- or 128-wide MMA occupies the tensor pipe -- so the narrow layers are issue-bound with a single issuer.
   constexpr int ACC1 = MRG ? 2 * BN : BN;                       // accumulator columns of one issuer
@@ -834,10 +834,13 @@ extern "C" int pdae_conv_tc3_create(pdae_conv_tc3_plan** plan_out, const void* s
   const char* em = getenv("PDAE_TC3_MRG128");
   const bool mrg = x3 && (BN == 64 || !(em && atoi(em) == 0));   // merged [W_hi | W_lo] weight tiles (see the kernel)
   pl->mrg = mrg ? 1 : 0;
-  {   // two MMA issuers (see the kernel) for the 64-wide split-mode layers (+8 % on multi-k-block layers; in the bf16 mode the
-      // heavier epilogue costs more than the second issuer gains: 176 -> 220 us at 64 -> 64); PDAE_TC3_DUAL=0: one issuer
+  {   // EXPERIMENTAL, off by default (PDAE_TC3_DUAL=1 to enable): two MMA issuers (see the kernel) for the 64-wide split-mode
+      // layers.  +8 % on multi-k-block layers and bit-identical results in every single-GPU run, but under torchrun with two
+      // ranks the launch died with 'unspecified launch failure' in 2 of 4 rank-runs (scripts/n2_check.sh; with the second
+      // issuer off the same runs pass) -- an unresolved protocol race, so the product path keeps one issuer.  (In the bf16
+      // mode the heavier epilogue costs more than the second issuer gains: 176 -> 220 us at 64 -> 64.)
     const char* ed = getenv("PDAE_TC3_DUAL");
-    pl->dual = (x3 && BN == 64 && !(ed && atoi(ed) == 0)) ? 1 : 0;
+    pl->dual = (x3 && BN == 64 && ed && atoi(ed) == 1) ? 1 : 0;
   }
   const int a_stage = (x3 ? 2 : 1) * T3_HALO_BYTES, b_bytes = (mrg ? 2 * BN : BN) * T3_BK * 2;
   const int staging = ((a.has_res && !x3) ? 4 : 2) * T3_STG_BYTES;   // split mode reads its residual from global memory
