@@ -6,10 +6,11 @@ Scope (the PDAE training step, diffusion/gaussian_diffusion.py:234-255): the sem
 trainable half of the ShiftUNet (``label_emb``, ``shift_middle_block``, ``shift_output_blocks``, ``shift_out``); the frozen
 half builds no graph in the reference either (its parameters and x_t do not require grad) -- it runs as a tensor-core plan
 in the split-operand (fp32-grade) mode with the fused-prologue convs.  The trainable half keeps its fp32 activations for the
-backward; its forward convs and the data gradients of the stride-1 convs run on the tensor cores on split operands
-(``Plan.train_tc``, ``bwd_plan``).  Weight gradients, GroupNorm / attention backward stay fp32 on CUDA cores
-(``pdae_conv2d_wgrad_simt``, ``pdae_gn_bwd_*``, ``pdae_gemm_batched_simt``, ``pdae_softmax_bwd``): tensor-core weight gradients
-are future work.  Dropout is inverted dropout with masks drawn by torch's CUDA generator.
+backward; its forward convs, the data gradients and the weight gradients of the stride-1 convs run on the tensor cores on
+split operands (``Plan.train_tc``, ``bwd_plan``, ``pdae_wgrad_tc_*``).  GroupNorm / attention backward, the encoder and the
+stride-2 / 3-channel convs stay fp32 on CUDA cores (``pdae_gn_bwd_*``, ``pdae_gemm_batched_simt``, ``pdae_softmax_bwd``,
+``pdae_conv2d_wgrad_simt`` / ``pdae_conv2d_dgrad_simt``).  Gradients reach autograd through one ``pdae_unpack_grads`` launch
+(``GradSink``).  Dropout is inverted dropout with masks drawn by torch's CUDA generator.
 """
 from __future__ import annotations
 
@@ -103,14 +104,14 @@ def draw_dropout_masks(plan: Plan) -> None:
 
 def bwd_plan(dev) -> Plan:
     """Backward plans are split-operand tensor-core plans: the data gradient of every eligible stride-1 conv runs on
-    `conv_tc2` in the fp32-grade "bf16x3" mode (Backward.conv); everything else in them is fp32 CUDA-core arithmetic.
-    PDAE_TRAIN_TC_DGRAD=0 selects pure fp32 CUDA-core backward plans (A/B aid: 176 vs 127 ms per celeba64-proxy step at
-    B=32; both pass the same gradient checks of tests/test_gpu_training.py)."""
+    `conv_tc2` and its weight gradient on `wgrad_tc`, both in the fp32-grade "bf16x3" mode (Backward.conv); everything else
+    in them is fp32 CUDA-core arithmetic.  PDAE_TRAIN_TC_DGRAD=0 selects pure fp32 CUDA-core backward plans (A/B aid: 176 vs
+    127 ms per celeba64-proxy step at B=32 in round 1; both pass the same gradient checks of tests/test_gpu_training.py)."""
     return Plan(dev, "bf16x3" if os.environ.get("PDAE_TRAIN_TC_DGRAD", "1") == "1" else "fp32")
 
 
 class Backward:
-    """Emission helpers for the backward plan (fp32)."""
+    """Emission helpers for the backward plan (fp32 activations / gradients; eligible convs on the tensor cores)."""
 
     def __init__(self, BP: Plan, sink: GradSink):
         self.P = BP
