@@ -316,6 +316,28 @@ typedef struct pdae_unpack_item {
 } pdae_unpack_item;
 int pdae_unpack_grads(const pdae_unpack_item* items, const int32_t* block_map, int n_blocks, int chunk, float* g,
                       pdae_stream_t stream);
+/* ---- launch plans (plan_create / destroy / run_step) ---------------------------------------------------
+ * An ordered list of recorded calls of the entry points above, replayed from native code: what one `forward()` of a
+ * reference module (model/unet.py:178-202, model/shift_unet.py:251-310) or one autograd backward pass amounts to here.
+ * `pdae_plan_add(plan, "pdae_gn_apply", args, nargs, stream_slot)` records one call: `args` holds the argument values in the
+ * entry point's order (pointers in .p, int / int64 in .i, float in .f), `stream_slot` is the index of its pdae_stream_t
+ * argument (patched at every run) or -1.  Every entry point that returns int and takes only pointers / int / int64 / float
+ * is recordable (incl. the `*_run` functions of the tensor-core kernel plans).  `pdae_plan_run_step` issues the calls in order
+ * on `stream` and stops at the first failure (returns its code; pdae_last_error() describes it).  The caller owns every
+ * buffer; one plan per stream (not thread-safe).                                                                          */
+typedef union pdae_arg {
+  void* p;
+  int64_t i;
+  double f;
+} pdae_arg;
+typedef struct pdae_plan pdae_plan;
+int pdae_plan_create(pdae_plan** plan);
+int pdae_plan_add(pdae_plan* plan, const char* entry, const pdae_arg* args, int nargs, int stream_slot);
+int pdae_plan_run_step(pdae_plan* plan, pdae_stream_t stream);
+int pdae_plan_size(const pdae_plan* plan);
+const char* pdae_plan_op_name(const pdae_plan* plan, int index);
+void pdae_plan_destroy(pdae_plan* plan);
+
 /* Wire formats.  fp32 NCHW in [-1,1] -> uint8 NHWC with the reference's exact op sequence
  * `x.mul(0.5).add(0.5).mul(255).add(0.5).clamp(0,255).permute(0,2,3,1).to(uint8)`
  * (trainer/train_representation_learning.py:173-174, sampler/autoencoding_example.py:53 ...): bit-exact.

@@ -16,7 +16,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libpdae_b200.so")
-SOURCES = ["conv_simt.cu", "norm_elementwise.cu", "attention_simt.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc3.cu", "wgrad_tc.cu", "backward_simt.cu", "train_io.cu"]
+SOURCES = ["conv_simt.cu", "norm_elementwise.cu", "attention_simt.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc3.cu", "wgrad_tc.cu", "plan_exec.cu", "backward_simt.cu", "train_io.cu"]
 
 PDAE_F32, PDAE_BF16 = 0, 1
 RESAMPLE_NONE, RESAMPLE_UP2, RESAMPLE_DOWN2 = 0, 1, 2
@@ -31,7 +31,8 @@ class NativeError(RuntimeError):
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source for sm_100a into pdae_b200/libpdae_b200.so (cross-compiles without a GPU)."""
     srcs = [os.path.join(_HERE, "csrc", s) for s in SOURCES]
-    deps = srcs + [os.path.join(_HERE, "csrc", "common.cuh"), os.path.join(_ROOT, "include", "pdae_b200.h")]
+    deps = srcs + [os.path.join(_HERE, "csrc", "common.cuh"), os.path.join(_HERE, "csrc", "plan_exec_table.inc"),
+                   os.path.join(_ROOT, "include", "pdae_b200.h")]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -125,6 +126,12 @@ _SIGS = {
     "pdae_adam_ema_step": (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_int64, c_float,
                                    c_float, _P]),
     "pdae_unpack_grads": (c_int, [_P, _P, c_int, c_int, _P, _P]),
+    "pdae_plan_create": (c_int, [POINTER(c_void_p)]),
+    "pdae_plan_add": (c_int, [_P, c_char_p, _P, c_int, c_int]),
+    "pdae_plan_run_step": (c_int, [_P, _P]),
+    "pdae_plan_size": (c_int, [_P]),
+    "pdae_plan_op_name": (c_char_p, [_P, c_int]),
+    "pdae_plan_destroy": (None, [_P]),
     "pdae_images_to_u8_nhwc": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "pdae_u8_nhwc_to_images": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "pdae_mse_per_image": (c_int, [_P, _P, c_int, c_int64, _P, _P, _P]),
@@ -147,6 +154,25 @@ def lib() -> ctypes.CDLL:
             fn.argtypes = args
         _lib = L
     return _lib
+
+
+def pack_args(cfn, cargs) -> bytes:
+    """Argument values of one recorded call as an array of `pdae_arg` (8-byte union: pointer / int64 / double), in the entry
+    point's declared order; a None (stream placeholder, null pointer) becomes 0."""
+    import struct
+    out = []
+    assert len(cargs) == len(cfn.argtypes), (cfn.__name__, len(cargs), len(cfn.argtypes))
+    for t, a in zip(cfn.argtypes, cargs):
+        v = a.value if isinstance(a, ctypes._SimpleCData) else a
+        if t is c_float:
+            out.append(struct.pack("<d", float(v)))
+        elif t is c_void_p:
+            out.append(struct.pack("<Q", int(v) if v else 0))
+        elif t in (c_int, c_int64):
+            out.append(struct.pack("<q", int(v)))
+        else:
+            raise NativeError(f"{cfn.__name__}: argument type {t} cannot be recorded in a native plan")
+    return b"".join(out)
 
 
 def check(rc: int, what: str = "") -> None:

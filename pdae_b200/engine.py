@@ -154,6 +154,8 @@ class Plan:
         self._tc2_handles: List[ctypes.c_void_p] = []
         self._tc3_handles: List[ctypes.c_void_p] = []
         self._wg_handles: List[ctypes.c_void_p] = []
+        self._nplan_handles: List[ctypes.c_void_p] = []
+        self._native_plans: dict = {}
         self.head_fuse: Dict[str, Buf] = {}   # image heads whose epilogue can run the DDIM update (set by a sampling loop)
         # training forward plans (fp32, every intermediate kept for the backward): run the eligible convs on the tensor cores in
         # the split-operand mode -- the fp32 activation the backward needs stays as it is, a [hi | lo | hi] copy feeds conv_tc2
@@ -327,6 +329,11 @@ class Plan:
         self._compiled = compiled
         self._pro_idx = [i for i, p in enumerate(self.op_pro) if p]
         self._main_idx = [i for i, p in enumerate(self.op_pro) if not p]
+        # PDAE_NATIVE_PLAN=1: replay through the C-ABI plan executor (pdae_plan_*): one foreign call per pass instead of one
+        # ctypes call per op.  Off by default (the Python loop is the path the GPU suite of this round validated).
+        self._native_plans = {}
+        if os.environ.get("PDAE_NATIVE_PLAN", "0") == "1":
+            self._native_plans = {"pro": self._build_native(self._pro_idx), "main": self._build_native(self._main_idx)}
         for b in self.bufs:  # a recycled buffer must not carry data from the prologue into the per-step ops
             if b.first is not None and not b.keep and not b.fixed and self.op_pro[b.first] and not self.op_pro[b.last]:
                 raise AssertionError(f"plan buffer {b.name!r} crosses the prologue boundary but is not `keep`")
@@ -449,6 +456,8 @@ class Plan:
                 self.L.pdae_conv_tc3_destroy(h)
             for h in self._wg_handles:
                 self.L.pdae_wgrad_tc_destroy(h)
+            for h in self._nplan_handles:
+                self.L.pdae_plan_destroy(h)
         except Exception:
             pass
 
@@ -456,8 +465,26 @@ class Plan:
     def stale(self) -> bool:
         return any(p.data_ptr() != ptr for p, ptr in self.params)
 
+    def _build_native(self, idx: List[int]):
+        """Record the compiled ops `idx` into a native launch plan (include/pdae_b200.h: pdae_plan_*)."""
+        if not idx:
+            return None
+        h = ctypes.c_void_p()
+        _native.check(self.L.pdae_plan_create(ctypes.byref(h)), "pdae_plan_create")
+        self._nplan_handles.append(h)
+        for i in idx:
+            cfn, cargs, sidx, name = self._compiled[i]
+            blob = _native.pack_args(cfn, cargs)
+            _native.check(self.L.pdae_plan_add(h, cfn.__name__.encode(), blob, len(cargs), sidx), "pdae_plan_add(" + cfn.__name__ + ")")
+        return h
+
     def _launch_all(self, idx: Optional[List[int]] = None) -> None:
         stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        if self._native_plans and (idx is None or idx is self._pro_idx):
+            h = self._native_plans["main" if idx is None else "pro"]
+            if h is not None:
+                _native.check(self.L.pdae_plan_run_step(h, stream), "pdae_plan_run_step")
+            return
         for i in (self._main_idx if idx is None else idx):
             cfn, cargs, sidx, name = self._compiled[i]
             cargs[sidx] = stream
