@@ -54,6 +54,37 @@ def _worker(rank, world, port, n_total, q):
         for p in a + bq:
             p.grad = None
     red.remove()
+    # gradients handed out as VIEWS of one flat buffer (what the trainers' GradSink returns: autograd adopts them as `.grad`
+    # without a copy) go through both exchanges unchanged
+    class _FlatGrads(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, *params):
+            ctx.shapes = [p.shape for p in params]
+            return x.sum() + sum(p.sum() for p in params) * 0.0
+
+        @staticmethod
+        def backward(ctx, g):
+            flat = torch.arange(sum(int(torch.Size(s).numel()) for s in ctx.shapes), dtype=torch.float32) * float(rank + 1)
+            outs, off = [], 0
+            for s in ctx.shapes:
+                n = int(torch.Size(s).numel())
+                outs.append(flat[off: off + n].view(s))
+                off += n
+            return (None, *outs)
+
+    vs = [torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(2, 2, 2))]
+    total = torch.arange(12 + 5 + 8, dtype=torch.float32) * float(sum(r + 1 for r in range(world)))
+    for mode in ("after", "overlapped"):
+        red2 = OverlappedGradAllReduce([vs]) if mode == "overlapped" else None
+        _FlatGrads.apply(torch.ones(2), *vs).backward()
+        ok = ok and vs[0].grad.untyped_storage().data_ptr() == vs[2].grad.untyped_storage().data_ptr()   # adopted, not copied
+        sc = red2.finish() if red2 is not None else allreduce_grads_(vs)
+        got = torch.cat([p.grad.reshape(-1) for p in vs])
+        ok = ok and sc == 1.0 / world and torch.equal(got, total)
+        for p in vs:
+            p.grad = None
+        if red2 is not None:
+            red2.remove()
     q.put((rank, ok, (s, e)))
     dist.destroy_process_group()
 
